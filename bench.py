@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- grid-cell-days/s of the NESOSIM daily snow-budget hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): 100 km Arctic grid (90x90), one Aug 15 - May 1 season (260 days -> 259
+steps), a 1024-member calibration ensemble sharded 128 members per GPU (weak scaling: each rank runs 128
+members; N=8 is the named 1024-member job).  One "step" = one full season pass of this rank's 128 members =
+128 x 8100 x 259 = 2.685e8 member-cell-days, synthetic forcing (nesosim_b200/synthetic.py, seeded).
+
+Reported (one JSON line, rank 0):
+  value      member-cell-days/s, all ranks, forcing resident in HBM, full 12-array output contract in HBM
+  roofline   algorithmic HBM bytes (96 + 41/M per member-cell-day) / device time, against the
+             measured copy bandwidth in MEASURED_PEAKS.json
+  e2e        the same metric through nesosim_run_season_host with HOST buffers (H2D + D2H inside the timing)
+  cpu_baseline  the numpy oracle port of the reference's calcBudget loop on this box's host cores
+`--impl reference` times only that CPU port (all host cores) and prints the same line shape.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DX = 100000
+NUM_DAYS = 260                 # Aug 15 - May 1
+MEMBERS_PER_GPU = 128          # 1024 members / 8 GPUs
+METRIC = "grid-cell-days/s (members x cells x days)"
+UNIT = "cell-days/s"
+SEED = 2024
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def workload_config(members, n_gpus, extra=None):
+    cfg = {"workload": "100 km Arctic season (90x90, Aug15-May1: 260 days, 259 steps), %d-member calibration "
+                       "ensemble, %d members per GPU, full 12-array output" % (members * n_gpus, members),
+           "grid": [90, 90], "dx_m": DX, "num_days": NUM_DAYS, "members_per_gpu": members,
+           "members_total": members * n_gpus,
+           "l2": "no flush: each step writes %.1f GB of outputs per GPU (>> 126 MB L2)"
+                 % (members * NUM_DAYS * 8100 * 96 / 1e9)}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ----------------------------------------------------------------------------------------- CPU baseline
+
+_CPU_CACHE = {}
+
+
+def _cpu_member_season(args):
+    """One member-season of the numpy oracle (= the reference's calcBudget loop, NESOSIM.py:614-639)."""
+    os.environ["OMP_NUM_THREADS"] = "1"
+    seed, row, num_days = args
+    from nesosim_b200 import synthetic as S
+    from oracle import nesosim_oracle as O
+    key = (seed, num_days)
+    if key not in _CPU_CACHE:
+        mask = S.region_mask(dx=DX)
+        _CPU_CACHE[key] = (mask, S.make_season(mask, num_days, seed=seed), S.make_ic(mask, seed=seed))
+    mask, forcing, ic = _CPU_CACHE[key]
+    p = O.Params(windPackFactor=row[0], windPackThresh=row[1], leadLossFactor=row[2], atmLossFactor=row[3])
+    t0 = time.perf_counter()
+    O.run_season(forcing, ic, mask, DX, p, O.Flags(atmlossInc=1))
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(members_per_core=1, cores=None, num_days=NUM_DAYS):
+    """Process-parallel over members on all host cores; returns (cell-days/s, cores, sample text, seconds)."""
+    import multiprocessing as mp
+    from nesosim_b200 import synthetic as S
+    cores = cores or os.cpu_count() or 1
+    n = cores * members_per_core
+    params = S.ensemble_params(n, seed=SEED)
+    jobs = [(SEED, params[i], num_days) for i in range(n)]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_member_season, jobs[:cores])          # warm the workers (imports, forcing cache)
+        t0 = time.perf_counter()
+        pool.map(_cpu_member_season, jobs)
+        dt = time.perf_counter() - t0
+    cells = 8100 * (num_days - 1) * n
+    return cells / dt, cores, "%d member-seasons (90x90x%d steps each), %d processes" % (n, num_days - 1, cores), dt
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    vals = []
+    cores = os.cpu_count() or 1
+    per_core = 1
+    for _ in range(args.warmup and 1):
+        cpu_baseline(per_core, cores)
+    t_total = 0.0
+    sample = ""
+    for _ in range(args.steps):
+        v, cores, sample, dt = cpu_baseline(per_core, cores)
+        vals.append(v)
+        t_total += dt
+    value = float(np.mean(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(MEMBERS_PER_GPU, args.gpus,
+                                                           {"reference_step": "bounded sample: " + sample}),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append(ln.strip())
+
+    def wait_first(self, timeout=5.0):
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.05)
+
+    def mark(self):
+        """Samples taken from now on belong to the timed region."""
+        self.first = len(self.rows)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows[getattr(self, "first", 0):]:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------- ours
+
+def run_ours(args):
+    import torch
+    rank, world, local = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    from nesosim_b200 import build
+    if rank == 0:
+        build.build(verbose=False)
+    if world > 1:
+        dist.barrier()
+    from nesosim_b200 import synthetic as S
+    from nesosim_b200.engine import SnowBudgetEngine
+
+    M = args.members
+    T = args.days
+    mask = S.region_mask(dx=DX)
+    ny, nx = mask.shape
+    forcing = S.make_season(mask, T, seed=SEED)
+    ic = S.make_ic(mask, seed=SEED)
+    params = S.ensemble_params(M * world, seed=SEED)[rank * M:(rank + 1) * M]     # this rank's members
+
+    eng = SnowBudgetEngine(mask, T, DX, n_members=M, atmlossInc=1, device=local)
+    eng.set_forcing(forcing["precip"], forcing["conc"], forcing["wind"], forcing["drift"])
+    out = eng.alloc_outputs()
+    cells_per_step = M * ny * nx * (T - 1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 0)):
+        eng.run_season(params, ic, out)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_first()
+    l0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.mark()
+    ev0.record()
+    for _ in range(args.steps):
+        eng.run_season(params, ic, out)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * cells_per_step * args.steps / (ms * 1e-3)
+
+    # roofline of the dominant kernel: algorithmic bytes per launch / average launch duration in the timed region
+    b_alg = 96.0 + 41.0 / M
+    season_kernels = launches / max(args.steps, 1)
+    bytes_per_step = cells_per_step * b_alg
+    achieved = bytes_per_step * args.steps / (ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": eng.dominant_kernel() if hasattr(eng, "dominant_kernel") else "day_step_kernel",
+                "bytes_per_member_cell_day": b_alg, "launches_per_step": season_kernels, "peak_source": peak_src,
+                "avg_launch_us": 1e3 * ms / max(launches, 1)}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(prof):
+        try:
+            with open(prof) as f:
+                roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # end to end through the host-buffer C-ABI call
+    e2e = None
+    try:
+        e2e = run_e2e(args, eng, forcing, params, ic, rank, world, cells_per_step, barrier)
+    except Exception as ex:   # keep the headline line even if the host path cannot allocate
+        e2e = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, cores, sample, _ = cpu_baseline(1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(M, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, eng, forcing, params, ic, rank, world, cells_per_step, barrier):
+    """Season through nesosim_run_season_host: pinned HOST forcing in, all 12 HOST arrays out, every step."""
+    import torch
+    M, T, ny, nx = eng.M, eng.T, eng.ny, eng.nx
+    names = list(__import__("nesosim_b200._lib", fromlist=["x"]).OUTPUT_NAMES)
+    need = 12 * M * T * ny * nx * 8
+    avail = None
+    try:
+        with open("/proc/meminfo") as f:
+            for ln in f:
+                if ln.startswith("MemAvailable"):
+                    avail = int(ln.split()[1]) * 1024
+    except OSError:
+        pass
+    note = "all 12 arrays to pinned host memory"
+    if avail is not None and need * world > 0.6 * avail:
+        names = ["snowDepths", "density"]
+        note = "host RAM too small for the full contract x %d ranks: snowDepths+density only" % world
+    host_out = {}
+    for n in names:
+        shape = (M, T, 2, ny, nx) if n == "snowDepths" else (M, T, ny, nx)
+        host_out[n] = torch.empty(shape, dtype=torch.float64, pin_memory=True)
+    hf = {k: torch.from_numpy(np.ascontiguousarray(forcing[k])).pin_memory() for k in ("precip", "conc", "wind", "drift")}
+    ic_h = torch.from_numpy(np.ascontiguousarray(ic)).pin_memory()
+    steps = max(1, min(args.steps, args.e2e_steps))
+    eng.run_season_host(hf, params, ic_h, host_out)      # warm-up (allocates device staging)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, up, down = eng.run_season_host(hf, params, ic_h, host_out)
+    barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    return {"value": world * cells_per_step * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(up),
+            "d2h_bytes_per_step": int(down), "steps": steps, "ms_per_step": 1e3 * dt / steps, "outputs": note}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--members", type=int, default=MEMBERS_PER_GPU)
+    ap.add_argument("--days", type=int, default=NUM_DAYS)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,147 @@
+/* nesosim_b200.h -- C ABI of the B200-native NESOSIM daily snow-budget path.
+ *
+ * Drop-in boundary for ONE hot path of ac137/NESOSIM: `calcBudget` and its callees
+ * (reference: source/NESOSIM.py:51-347,458-473) plus the day loop of `main` that drives it
+ * (source/NESOSIM.py:586-649).  The reference is pure Python, so there is no existing FFI; these are the
+ * entry points a ctypes binding for that path binds (see INTEGRATION.md for the reference-side stub).
+ *
+ * Conventions
+ *   - plain C, no torch/CUDA types in signatures; `stream` is a cudaStream_t passed as void* (NULL = default).
+ *   - every `*_dev` / "device pointer" argument is a CUDA device address (e.g. torch.Tensor.data_ptr());
+ *     arguments documented "host" are ordinary host memory.
+ *   - all fields are float64 unless stated; planes are dense row-major (ny rows, nx columns), time-major
+ *     stacks are [T][ny][nx] exactly like the reference's numpy arrays (genEmptyArrays, NESOSIM.py:350-376).
+ *   - functions return 0 (NESOSIM_OK) or a negative error code; nesosim_last_error() gives the message for
+ *     the calling thread.  NaN/inf in the data are data, not errors (NESOSIM.py relies on NaN algebra).
+ *   - the caller owns every buffer; the library allocates only an opaque context (and optional scratch).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns NESOSIM_ERR_CUDA.
+ */
+#ifndef NESOSIM_B200_H
+#define NESOSIM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NESOSIM_ABI_VERSION 1
+
+#define NESOSIM_OK            0
+#define NESOSIM_ERR_ARG      -1   /* bad argument (NULL, non-positive size, ny or nx < 2, ...) */
+#define NESOSIM_ERR_CUDA     -2   /* CUDA runtime error or no device */
+#define NESOSIM_ERR_STATE    -3   /* call order (e.g. run_season before set_forcing) */
+#define NESOSIM_ERR_NOMEM    -4
+
+typedef struct nesosim_ctx nesosim_ctx;
+
+/* Model constants `main` assigns to module globals (NESOSIM.py:527-541) + grid + switches of calcBudget
+ * (NESOSIM.py:227).  conv_weights is `Gaussian2DKernel(x_stddev=1,x_size=3,y_size=3).array` (row-major 3x3)
+ * and conv_divisor its `.sum()`, both computed by the HOST with numpy so the device uses bit-identical
+ * constants (smooth_snow, NESOSIM.py:170-187); pass weights/sum and divisor 1.0 for a pre-normalised kernel. */
+typedef struct nesosim_config {
+    int32_t ny, nx;              /* grid rows / columns (>= 2 each: np.gradient needs two points)        */
+    int32_t num_days;            /* T = numDays: number of time slots; the season has T-1 steps          */
+    int32_t n_members;           /* M parameter sets sharing one forcing (1 for a plain `main` run)      */
+    double  dx;                  /* grid spacing [m]: the `dx` argument of main / calcDynamics           */
+    double  deltaT;              /* 86400.                                                               */
+    double  snowDensityFresh;    /* 200.                                                                 */
+    double  snowDensityOld;      /* 350.                                                                 */
+    double  minSnowD;            /* 0.02                                                                 */
+    double  minConc;             /* 0.15                                                                 */
+    double  conv_weights[9];
+    double  conv_divisor;
+    int32_t dynamicsInc, leadlossInc, windpackInc, atmlossInc;
+    int32_t density_clim;        /* 0: densityType='variable', 1: 'clim' (needs rho_clim)                */
+    int32_t device;              /* CUDA device ordinal                                                  */
+} nesosim_config;
+
+/* Per-member coefficients: windPackFactorT, windPackThreshT, leadLossFactorT, atmLossFactorT of main. */
+typedef struct nesosim_member_params {
+    double windPackFactor, windPackThresh, leadLossFactor, atmLossFactor;
+} nesosim_member_params;
+
+/* The twelve arrays calcBudget advances (NESOSIM.py:264-347).  Device pointers; member m of variable v
+ * starts at v + m*member_stride elements; within a member the layout is the reference's:
+ * snowDepths [T][2][ny][nx], everything else [T][ny][nx].  NULL = not wanted (kept in internal scratch). */
+typedef struct nesosim_outputs {
+    double *snowDepths;
+    double *density;
+    double *snowAcc, *snowOcean, *snowAdv, *snowDiv, *snowLead, *snowAtm;
+    double *snowWindPackLoss, *snowWindPackGain, *snowWindPack;
+    int64_t depth_member_stride;   /* elements between members in snowDepths (>= T*2*ny*nx)             */
+    int64_t plane_member_stride;   /* elements between members in every other array (>= T*ny*nx)         */
+} nesosim_outputs;
+
+int         nesosim_abi_version(void);
+const char *nesosim_last_error(void);
+/* Number of CUDA devices visible (0 on a CPU-only host; never fails). */
+int         nesosim_device_count(void);
+
+/* Context = grid, constants, region mask.  `region_mask_host` is ny*nx uint8 region codes (host memory);
+ * only `>10` (land/coast) and `<1` (lakes) are ever tested (fill_nan_no_negative, NESOSIM.py:158-162). */
+int nesosim_create(const nesosim_config *cfg, const uint8_t *region_mask_host, nesosim_ctx **out);
+int nesosim_destroy(nesosim_ctx *ctx);
+
+/* Register a season of forcing already resident in HBM (what loadData returns per day, NESOSIM.py:379-456,
+ * stacked over T days): precip/conc/wind [T][ny][nx], drift [T][2][ny][nx], rho_clim [T] (fresh-snow density
+ * per step for density_clim=1, else NULL).  Pointers are borrowed, not copied. */
+int nesosim_set_forcing(nesosim_ctx *ctx, const double *precip_dev, const double *conc_dev,
+                        const double *wind_dev, const double *drift_dev, const double *rho_clim_dev);
+
+/* The season: IC handling of main (NESOSIM.py:604-609; ic_dev = [ny][nx] total depth shared by all members,
+ * or [M][ny][nx] when ic_per_member != 0, or NULL for zero depth) when first_step == 0, then steps
+ * x = first_step .. first_step+num_steps-1 of `for x in range(numDays-1): calcBudget(...)`
+ * (NESOSIM.py:614-639) for every member.  Slot 0 of every non-NULL output is (re)written when
+ * first_step == 0 (zeros; IC halves for snowDepths) so callers need not zero-fill.  num_steps < 0 means
+ * "to the end" (T-1-first_step).  Asynchronous on `stream`. */
+int nesosim_run_season(nesosim_ctx *ctx, const nesosim_member_params *params_host, const double *ic_dev,
+                       int ic_per_member, const nesosim_outputs *out, int first_step, int num_steps,
+                       void *stream);
+
+/* One calcBudget call (NESOSIM.py:224-347) with that day's forcing planes given explicitly: advances slot x
+ * to slot x+1 of `out` in place for every member.  rho_new is used only when density_clim=1. */
+int nesosim_step_day(nesosim_ctx *ctx, int x, const double *conc_dev, const double *precip_dev,
+                     const double *drift_dev, const double *wind_dev, double rho_new,
+                     const nesosim_member_params *params_host, const nesosim_outputs *out, void *stream);
+
+/* Same as nesosim_run_season but every data pointer is HOST memory (pinned or pageable): copies the forcing
+ * to the device, runs the season, copies every non-NULL output back, synchronises.  This is the call
+ * bench.py times for the end-to-end figure.  `out_host` strides are in elements like nesosim_outputs.
+ * Members are processed in batches so that device and pinned staging memory stay bounded; bytes moved are
+ * reported through h2d_bytes / d2h_bytes when non-NULL. */
+int nesosim_run_season_host(nesosim_ctx *ctx, const double *precip, const double *conc, const double *wind,
+                            const double *drift, const double *rho_clim,
+                            const nesosim_member_params *params, const double *ic, int ic_per_member,
+                            const nesosim_outputs *out_host, int64_t *h2d_bytes, int64_t *d2h_bytes);
+
+/* smooth_snow (NESOSIM.py:170-187) = astropy convolve(arr, 3x3 kernel) with defaults, both branches
+ * (plain, and NaN-interpolating when the input sum is NaN).  in/out are distinct [ny][nx] device planes. */
+int nesosim_smooth(const double *in_dev, double *out_dev, int ny, int nx, const double weights_host[9],
+                   double divisor, void *stream);
+
+/* Per-function entry points (device planes), one per reference function, for known-answer tests. */
+/* calcDynamics (NESOSIM.py:189-222): drift [2][ny][nx], depths [2][ny][nx] -> adv [2][ny][nx], div [2][ny][nx] */
+int nesosim_op_dynamics(const double *drift_dev, const double *depths_dev, double dx, double deltaT,
+                        int ny, int nx, double *adv_dev, double *div_dev, void *stream);
+/* calcLeadLoss / calcAtmLoss / calcWindPacking (NESOSIM.py:51-125): five output planes, any may be NULL */
+int nesosim_op_wind_terms(const double *h0_dev, const double *wind_dev, const double *conc_dev, int64_t n,
+                          const nesosim_member_params *p_host, double deltaT, double rhoFresh, double rhoOld,
+                          double *lead_dev, double *atm_dev, double *wp_loss_dev, double *wp_gain_dev,
+                          double *wp_net_dev, void *stream);
+/* fillMaskAndNaNWithZero (NESOSIM.py:127-139), in place */
+int nesosim_op_fill_zero(double *arr_dev, int64_t n, void *stream);
+/* fill_nan_no_negative (NESOSIM.py:141-166), in place; mask_dev is uint8 [n] on the device */
+int nesosim_op_fill_nan_no_negative(double *arr_dev, const uint8_t *mask_dev, int64_t n,
+                                    int negative_to_zero, void *stream);
+/* densityCalc (NESOSIM.py:458-473): depths [2][n] -> density [n] */
+int nesosim_op_density(const double *depths_dev, const uint8_t *mask_dev, int64_t n, double rhoFresh,
+                       double rhoOld, double minSnowD, double *density_dev, void *stream);
+
+/* Number of kernel launches this context has issued since creation (bench.py reports it). */
+int64_t nesosim_launch_count(const nesosim_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NESOSIM_B200_H */

@@ -1,0 +1,137 @@
+// cell_math.cuh -- per-cell fp64 arithmetic of NESOSIM's daily budget, in the reference's evaluation order.
+//
+// Every expression below mirrors one line of /root/reference/source/NESOSIM.py (cited) as a tree of single
+// IEEE-754 double operations.  The explicit __dmul_rn/__dadd_rn/... intrinsics are never contracted into FMAs
+// by nvcc, which is what makes finite results bit-identical to numpy (SURVEY.md §7 "bit-exactness discipline").
+// NaN algebra is never short-circuited: 0*NaN stays NaN (NESOSIM.py:69-71).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nesosim {
+
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+__device__ __forceinline__ bool finite(double x) { return fabs(x) <= 1.7976931348623157e308; }
+
+// x / c for a divisor that is fixed for the whole launch.  `rc` = RN(1/c) from the host.
+// Fast path (Markstein / Brisebarre-Muller-Raina "division by a known constant"): q0 = RN(x*rc);
+// r = fma(-c, q0, x); q = RN(q0 + r*rc).  Before the last rounding the value is x/c*(1+eta), |eta| <= 3*2^-107
+// relative to the quotient's binade, so q is the correctly rounded quotient unless x/c lies that close to a
+// rounding midpoint.  The host only sets `fast` for divisors where that cannot happen (const_div_host() in
+// nesosim_abi.cu proves it per divisor); otherwise, and for operands outside the magnitude window (0, inf, NaN,
+// tiny, huge), the IEEE division instruction sequence is used.  Either way the result equals numpy's `x / c`.
+struct ConstDiv {
+    double c, rc;
+    int fast;
+};
+__device__ __forceinline__ double div_const(double x, const ConstDiv &d) {
+    const double ax = fabs(x);
+    if (d.fast && ax >= 1e-200 && ax <= 1e200) {   // the window is also false for NaN
+        const double q0 = __dmul_rn(x, d.rc);
+        const double r = __fma_rn(-d.c, q0, x);
+        return __fma_rn(r, d.rc, q0);
+    }
+    return __ddiv_rn(x, d.c);
+}
+
+// np.gradient(f, dx, axis) with edge_order=1 and uniform spacing (numpy; call sites NESOSIM.py:204-211):
+// interior (f[+1]-f[-1])/(2.*dx), first (f[1]-f[0])/dx, last (f[n-1]-f[n-2])/dx.
+struct GradConsts {
+    ConstDiv dx, two_dx;
+};
+// `fm`, `fc`, `fp` are the values at index-1, index, index+1 (fm/fp ignored where they fall off the grid).
+__device__ __forceinline__ double gradient1d(double fm, double fc, double fp, int idx, int n, const GradConsts &g) {
+    if (idx == 0) return div_const(sub(fp, fc), g.dx);
+    if (idx == n - 1) return div_const(sub(fc, fm), g.dx);
+    return div_const(sub(fp, fm), g.two_dx);
+}
+
+// fillMaskAndNaNWithZero (NESOSIM.py:127-139): NaN -> 0, +-inf -> 0
+__device__ __forceinline__ double zero_if_nonfinite(double x) { return finite(x) ? x : 0.0; }
+
+// fill_nan_no_negative (NESOSIM.py:141-166): non-finite -> NaN; land/coast/lakes -> NaN; optionally <0 -> 0.
+// `land` = (mask > 10) || (mask < 1).
+__device__ __forceinline__ double mask_nan(double x, bool land, bool negative_to_zero) {
+    if (!finite(x) || land) return qnan();
+    if (negative_to_zero && x < 0.0) return 0.0;
+    return x;
+}
+__device__ __forceinline__ bool is_land(uint8_t m) { return m > 10 || m < 1; }
+
+// calcDynamics (NESOSIM.py:204-213) for one layer at one cell, before the NaN->0 fill.
+//   div = -((h*gx(U*dT)) + (h*gy(V*dT)));  adv = -(((U*dT)*gx(h)) + ((V*dT)*gy(h)))
+__device__ __forceinline__ double div_term(double h, double gxu, double gyv) { return -add(mul(h, gxu), mul(h, gyv)); }
+__device__ __forceinline__ double adv_term(double ut, double vt, double gxh, double gyh) {
+    return -add(mul(ut, gxh), mul(vt, gyh));
+}
+
+// Per-member coefficients with the scalar sub-products the reference forms in Python floats first.
+struct MemberCoef {
+    double llf;       // leadLossFactor
+    double alf;       // atmLossFactor
+    double wpt;       // windPackThresh
+    double neg_wpf_dt;  // (-windPackFactor)*deltaT   (NESOSIM.py:119, scalar*scalar before the array multiply)
+    double wpf_dt;      // windPackFactor*deltaT      (NESOSIM.py:122)
+};
+
+struct ModelConsts {
+    double deltaT, rhoFresh, rhoOld, rho_ratio /* rhoFresh/rhoOld, NESOSIM.py:122 */, minSnowD, minConc;
+};
+
+// windT = np.where(W > thresh, 1, 0) as a double (NaN > thr is False)
+__device__ __forceinline__ double wind_flag(double W, double thr) { return (W > thr) ? 1.0 : 0.0; }
+
+// calcLeadLoss (NESOSIM.py:71): -(windT*LLF*dT*h0*W*(1-C))
+__device__ __forceinline__ double lead_loss(double wt, double h0, double W, double C, const MemberCoef &m,
+                                            const ModelConsts &k) {
+    return -mul(mul(mul(mul(mul(wt, m.llf), k.deltaT), h0), W), sub(1.0, C));
+}
+// calcAtmLoss (NESOSIM.py:94): -(windT*dT*h0*W*ALF)
+__device__ __forceinline__ double atm_loss(double wt, double h0, double W, const MemberCoef &m, const ModelConsts &k) {
+    return -mul(mul(mul(mul(wt, k.deltaT), h0), W), m.alf);
+}
+// calcWindPacking (NESOSIM.py:119-124)
+__device__ __forceinline__ void wind_packing(double wt, double h0, const MemberCoef &m, const ModelConsts &k,
+                                             double &loss, double &gain, double &net) {
+    loss = mul(mul(m.neg_wpf_dt, wt), h0);
+    gain = mul(mul(mul(m.wpf_dt, wt), h0), k.rho_ratio);
+    net = add(loss, gain);
+}
+
+// densityCalc (NESOSIM.py:464-471) on the updated depths
+__device__ __forceinline__ double density_variable(double h0, double h1, bool land, const ModelConsts &k) {
+    const double den = add(h0, h1);
+    double rho = __ddiv_rn(add(mul(h0, k.rhoFresh), mul(h1, k.rhoOld)), den);
+    if (rho > k.rhoOld) rho = k.rhoOld;
+    if (rho < k.rhoFresh) rho = k.rhoFresh;
+    if (land) rho = qnan();
+    if (den < k.minSnowD) rho = qnan();
+    return rho;
+}
+// clim branch (NESOSIM.py:339-344)
+__device__ __forceinline__ double density_clim(double rho_new, double h0, double h1, double C, bool land,
+                                               const ModelConsts &k) {
+    double rho = rho_new;
+    if (land) rho = qnan();
+    if (C < k.minConc) rho = qnan();
+    if (add(h0, h1) < k.minSnowD) rho = qnan();
+    return rho;
+}
+
+// 3x3 convolution tap order of astropy's C loop (rows outer, columns inner, flipped kernel, accumulator
+// starting at 0.0): see oracle/astropy_restated.py.  w[] is the 3x3 kernel row-major; v(r,c) fetches the
+// zero-padded input at offset (r-1, c-1) from the output cell.
+template <typename Fetch>
+__device__ __forceinline__ double conv3x3(const double *w, Fetch v) {
+    double top = 0.0;
+#pragma unroll
+    for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj) top = add(top, mul(v(ii, jj), w[(2 - ii) * 3 + (2 - jj)]));
+    return top;
+}
+
+}  // namespace nesosim

@@ -1,0 +1,302 @@
+// day_kernels.cuh -- the general (any grid, any member count) day-step path: one launch advances every member
+// from slot x to slot x+1.  This is the path `NESOSIM.main` (M=1) and the large grids use; the 100 km ensemble
+// has its own season-resident kernel in ensemble_kernel.cuh.
+//
+// Data flow per output cell: h[x] (2 layers, radius 2) + U,V (radius 2) + P,C,W,mask (point)
+//   -> raw adv/div on the tile grown by 1 (calcDynamics, NESOSIM.py:189-222) -> NaN/inf->0
+//   -> 3x3 Gaussian (smooth_snow, NESOSIM.py:170-187) -> land mask -> 7 point-wise deltas -> 12 planes of x+1.
+// Tiles of TY x TX cells with a 2-cell halo are staged in shared memory; everything else is fused.
+#pragma once
+#include "cell_math.cuh"
+
+namespace nesosim {
+
+enum Var {
+    V_H0 = 0, V_H1, V_DENS, V_ACC, V_OCEAN, V_ADV, V_DIV, V_LEAD, V_ATM, V_WPL, V_WPG, V_WP, NVAR
+};
+
+struct Switches {
+    int dynamics, leadloss, windpack, atmloss, clim;
+};
+
+struct DayArgs {
+    int ny, nx;
+    const double *P, *C, *W, *U, *V;      // this day's forcing planes (shared by all members)
+    const uint8_t *mask;
+    const double *prev[NVAR];              // slot x   (prev[V_DENS] unused)
+    double *next[NVAR];                    // slot x+1 (NULL: not stored)
+    long long prev_stride[NVAR], next_stride[NVAR];   // elements between members
+    const MemberCoef *coef;                // device [M]
+    ModelConsts k;
+    GradConsts g;
+    ConstDiv conv_div;                     // divisor applied after the 3x3 sum
+    ConstDiv rho_new;                      // fresh-snow density of this step (200 or the clim value)
+    double w[9];                           // 3x3 kernel, row-major
+    Switches sw;
+};
+
+constexpr int TX = 32;
+constexpr int TY = 16;
+constexpr int DAY_THREADS = 256;
+
+__global__ void __launch_bounds__(DAY_THREADS)
+day_step_kernel(const __grid_constant__ DayArgs a) {
+    __shared__ double s_h[2][TY + 4][TX + 4];
+    __shared__ double s_ut[TY + 4][TX + 4];
+    __shared__ double s_vt[TY + 4][TX + 4];
+    __shared__ double s_raw[4][TY + 2][TX + 2];   // adv0, adv1, div0, div1 after the NaN->0 fill
+
+    const int m = blockIdx.z;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int tid = threadIdx.x;
+    const int ny = a.ny, nx = a.nx;
+    const double *h0p = a.prev[V_H0] + (long long)m * a.prev_stride[V_H0];
+    const double *h1p = a.prev[V_H1] + (long long)m * a.prev_stride[V_H1];
+
+    if (a.sw.dynamics) {
+        for (int i = tid; i < (TY + 4) * (TX + 4); i += DAY_THREADS) {
+            const int r = i / (TX + 4), c = i - r * (TX + 4);
+            const int gy = y0 + r - 2, gx = x0 + c - 2;
+            double h0 = 0.0, h1 = 0.0, ut = 0.0, vt = 0.0;
+            if (gy >= 0 && gy < ny && gx >= 0 && gx < nx) {
+                const long long o = (long long)gy * nx + gx;
+                h0 = h0p[o];
+                h1 = h1p[o];
+                ut = mul(__ldg(a.U + o), a.k.deltaT);   // driftGday[0]*deltaT (NESOSIM.py:204,210)
+                vt = mul(__ldg(a.V + o), a.k.deltaT);
+            }
+            s_h[0][r][c] = h0;
+            s_h[1][r][c] = h1;
+            s_ut[r][c] = ut;
+            s_vt[r][c] = vt;
+        }
+        __syncthreads();
+        for (int i = tid; i < (TY + 2) * (TX + 2); i += DAY_THREADS) {
+            const int r = i / (TX + 2), c = i - r * (TX + 2);
+            const int gy = y0 + r - 1, gx = x0 + c - 1;
+            double adv0 = 0.0, adv1 = 0.0, div0 = 0.0, div1 = 0.0;   // zero padding of convolve(boundary='fill')
+            if (gy >= 0 && gy < ny && gx >= 0 && gx < nx) {
+                const int sr = r + 1, sc = c + 1;
+                const double ut = s_ut[sr][sc], vt = s_vt[sr][sc];
+                const double gxu = gradient1d(s_ut[sr][sc - 1], ut, s_ut[sr][sc + 1], gx, nx, a.g);
+                const double gyv = gradient1d(s_vt[sr - 1][sc], vt, s_vt[sr + 1][sc], gy, ny, a.g);
+#pragma unroll
+                for (int l = 0; l < 2; ++l) {
+                    const double h = s_h[l][sr][sc];
+                    const double gxh = gradient1d(s_h[l][sr][sc - 1], h, s_h[l][sr][sc + 1], gx, nx, a.g);
+                    const double gyh = gradient1d(s_h[l][sr - 1][sc], h, s_h[l][sr + 1][sc], gy, ny, a.g);
+                    const double dv = zero_if_nonfinite(div_term(h, gxu, gyv));
+                    const double ad = zero_if_nonfinite(adv_term(ut, vt, gxh, gyh));
+                    if (l == 0) { adv0 = ad; div0 = dv; } else { adv1 = ad; div1 = dv; }
+                }
+            }
+            s_raw[0][r][c] = adv0;
+            s_raw[1][r][c] = adv1;
+            s_raw[2][r][c] = div0;
+            s_raw[3][r][c] = div1;
+        }
+        __syncthreads();
+    }
+
+    const MemberCoef mc = a.coef[m];
+    const int tx = tid & (TX - 1);
+    const int gx = x0 + tx;
+    if (gx >= nx) return;
+#pragma unroll
+    for (int rr = 0; rr < TY / (DAY_THREADS / TX); ++rr) {
+        const int ty = (tid / TX) + rr * (DAY_THREADS / TX);
+        const int gy = y0 + ty;
+        if (gy >= ny) break;
+        const long long o = (long long)gy * nx + gx;
+        const bool land = is_land(__ldg(a.mask + o));
+
+        double adv0 = 0.0, adv1 = 0.0, div0 = 0.0, div1 = 0.0, h0, h1;
+        if (a.sw.dynamics) {
+            double sm[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const double top = conv3x3(a.w, [&](int ii, int jj) { return s_raw[p][ty + ii][tx + jj]; });
+                sm[p] = mask_nan(div_const(top, a.conv_div), land, false);   // NESOSIM.py:276-284
+            }
+            adv0 = sm[0]; adv1 = sm[1]; div0 = sm[2]; div1 = sm[3];
+            h0 = s_h[0][ty + 2][tx + 2];
+            h1 = s_h[1][ty + 2][tx + 2];
+        } else {
+            h0 = h0p[o];
+            h1 = h1p[o];
+        }
+
+        const double P = __ldg(a.P + o), C = __ldg(a.C + o), W = __ldg(a.W + o);
+        const double pd = div_const(P, a.rho_new);           // precipDayT/snowDensityNew (NESOSIM.py:260)
+        const double acc = mul(pd, C);                       // NESOSIM.py:263
+        const double oc = -mul(pd, sub(1.0, C));             // NESOSIM.py:267
+        const double wt = wind_flag(W, mc.wpt);
+        const double lead = a.sw.leadloss ? lead_loss(wt, h0, W, C, mc, a.k) : 0.0;
+        const double atm = a.sw.atmloss ? atm_loss(wt, h0, W, mc, a.k) : 0.0;
+        double wpl = 0.0, wpg = 0.0, wpn = 0.0;
+        if (a.sw.windpack) wind_packing(wt, h0, mc, a.k, wpl, wpg, wpn);
+
+        auto prev = [&](int v) { return a.prev[v][(long long)m * a.prev_stride[v] + o]; };
+        auto store = [&](int v, double val) {
+            if (a.next[v]) a.next[v][(long long)m * a.next_stride[v] + o] = val;
+        };
+        store(V_ACC, add(prev(V_ACC), acc));
+        store(V_OCEAN, add(prev(V_OCEAN), oc));
+        store(V_ADV, add(add(prev(V_ADV), adv0), adv1));     // NESOSIM.py:290
+        store(V_DIV, add(add(prev(V_DIV), div0), div1));     // NESOSIM.py:291
+        store(V_LEAD, add(prev(V_LEAD), lead));
+        store(V_ATM, add(prev(V_ATM), atm));
+        store(V_WPL, add(prev(V_WPL), wpl));
+        store(V_WPG, add(prev(V_WPG), wpg));
+        store(V_WP, add(prev(V_WP), wpn));
+
+        // NESOSIM.py:327,329 (left to right), then fill_nan_no_negative (332-333)
+        double h0n = add(add(add(add(add(add(h0, acc), wpl), lead), atm), adv0), div0);
+        double h1n = add(add(add(h1, wpg), adv1), div1);
+        h0n = mask_nan(h0n, land, true);
+        h1n = mask_nan(h1n, land, true);
+        store(V_H0, h0n);
+        store(V_H1, h1n);
+        const double rho = a.sw.clim ? density_clim(a.rho_new.c, h0n, h1n, C, land, a.k)
+                                     : density_variable(h0n, h1n, land, a.k);
+        store(V_DENS, rho);
+    }
+}
+
+// Slot 0 of every array: zeros (genEmptyArrays, NESOSIM.py:350-376) and the initial-condition split of main
+// (NESOSIM.py:604-609): IC[conc<minConc]=0; h[0,0]=h[0,1]=IC*0.5.
+struct InitArgs {
+    long long plane;
+    const double *ic;         // NULL -> zero depth
+    long long ic_stride;      // 0 (shared) or plane (per member)
+    const double *conc0;      // first day's concentration
+    double minConc;
+    double *slot0[NVAR];
+    long long stride[NVAR];
+};
+
+__global__ void init_slot0_kernel(const __grid_constant__ InitArgs a) {
+    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= a.plane) return;
+    const int m = blockIdx.y;
+    double half = 0.0;
+    if (a.ic) {
+        double v = a.ic[(long long)m * a.ic_stride + o];
+        if (__ldg(a.conc0 + o) < a.minConc) v = 0.0;
+        half = mul(v, 0.5);
+    }
+#pragma unroll
+    for (int v = 0; v < NVAR; ++v)
+        if (a.slot0[v]) a.slot0[v][(long long)m * a.stride[v] + o] = (v == V_H0 || v == V_H1) ? half : 0.0;
+}
+
+// ------------------------------------------------------------------ smooth_snow, standalone (both branches)
+
+// flags: bit0 NaN present, bit1 +inf present, bit2 -inf present  (np.isnan(arr.sum()), see oracle)
+__global__ void scan_nonfinite_kernel(const double *in, long long n, int *flags) {
+    int f = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = in[i];
+        if (v != v) f |= 1;
+        else if (v == __longlong_as_double(0x7ff0000000000000LL)) f |= 2;
+        else if (v == __longlong_as_double(0xfff0000000000000LL)) f |= 4;
+    }
+    f = __reduce_or_sync(0xffffffffu, f);
+    if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
+}
+
+struct SmoothArgs {
+    const double *in;
+    double *out;
+    int ny, nx;
+    double w[9];
+    ConstDiv div;
+    const int *flags;
+};
+
+__global__ void smooth_kernel(const __grid_constant__ SmoothArgs a) {
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (gx >= a.nx || gy >= a.ny) return;
+    const int fl = *a.flags;
+    const bool interp = (fl & 1) || ((fl & 6) == 6);
+    auto fetch = [&](int ii, int jj) {
+        const int r = gy + ii - 1, c = gx + jj - 1;
+        return (r >= 0 && r < a.ny && c >= 0 && c < a.nx) ? a.in[(long long)r * a.nx + c] : 0.0;
+    };
+    double res;
+    if (!interp) {
+        res = div_const(conv3x3(a.w, fetch), a.div);
+    } else {
+        double top = 0.0, bot = 0.0;
+#pragma unroll
+        for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj) {
+                const double val = fetch(ii, jj);
+                const double ker = a.w[(2 - ii) * 3 + (2 - jj)];
+                if (val == val) {
+                    top = add(top, mul(val, ker));
+                    bot = add(bot, ker);
+                }
+            }
+        res = (bot == 0.0) ? a.in[(long long)gy * a.nx + gx] : __ddiv_rn(top, bot);
+    }
+    a.out[(long long)gy * a.nx + gx] = res;
+}
+
+// ------------------------------------------------------------------ per-function kernels (known-answer tests)
+
+__global__ void op_dynamics_kernel(const double *drift, const double *h, int ny, int nx, double deltaT,
+                                   GradConsts g, double *adv, double *dv) {
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (gx >= nx || gy >= ny) return;
+    const long long plane = (long long)ny * nx, o = (long long)gy * nx + gx;
+    const double *U = drift, *V = drift + plane;
+    auto ut = [&](int r, int c) { return mul(U[(long long)r * nx + c], deltaT); };
+    auto vt = [&](int r, int c) { return mul(V[(long long)r * nx + c], deltaT); };
+    const int xm = max(gx - 1, 0), xp = min(gx + 1, nx - 1), ym = max(gy - 1, 0), yp = min(gy + 1, ny - 1);
+    const double gxu = gradient1d(ut(gy, xm), ut(gy, gx), ut(gy, xp), gx, nx, g);
+    const double gyv = gradient1d(vt(ym, gx), vt(gy, gx), vt(yp, gx), gy, ny, g);
+    for (int l = 0; l < 2; ++l) {
+        const double *hl = h + l * plane;
+        const double hc = hl[o];
+        const double gxh = gradient1d(hl[(long long)gy * nx + xm], hc, hl[(long long)gy * nx + xp], gx, nx, g);
+        const double gyh = gradient1d(hl[(long long)ym * nx + gx], hc, hl[(long long)yp * nx + gx], gy, ny, g);
+        dv[l * plane + o] = zero_if_nonfinite(div_term(hc, gxu, gyv));
+        adv[l * plane + o] = zero_if_nonfinite(adv_term(ut(gy, gx), vt(gy, gx), gxh, gyh));
+    }
+}
+
+__global__ void op_wind_terms_kernel(const double *h0, const double *W, const double *C, long long n,
+                                     MemberCoef mc, ModelConsts k, double *lead, double *atm, double *wpl,
+                                     double *wpg, double *wpn) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double wt = wind_flag(W[i], mc.wpt);
+    if (lead) lead[i] = lead_loss(wt, h0[i], W[i], C[i], mc, k);
+    if (atm) atm[i] = atm_loss(wt, h0[i], W[i], mc, k);
+    double l, g_, nnet;
+    wind_packing(wt, h0[i], mc, k, l, g_, nnet);
+    if (wpl) wpl[i] = l;
+    if (wpg) wpg[i] = g_;
+    if (wpn) wpn[i] = nnet;
+}
+
+__global__ void op_fill_zero_kernel(double *a, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = zero_if_nonfinite(a[i]);
+}
+
+__global__ void op_fill_nan_kernel(double *a, const uint8_t *mask, long long n, int neg_to_zero) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = mask_nan(a[i], is_land(mask[i]), neg_to_zero != 0);
+}
+
+__global__ void op_density_kernel(const double *h, const uint8_t *mask, long long n, ModelConsts k, double *rho) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rho[i] = density_variable(h[i], h[n + i], is_land(mask[i]), k);
+}
+
+}  // namespace nesosim

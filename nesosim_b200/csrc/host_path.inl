@@ -1,0 +1,141 @@
+// host_path.inl -- nesosim_run_season_host: the end-to-end call with HOST buffers (included by nesosim_abi.cu).
+//
+// Forcing goes host->device once; members are processed in batches whose device outputs are double-buffered:
+// while batch b computes on the compute stream, batch b-1 drains device->host on the copy stream.  Device
+// buffers are cached in the context so repeated calls (bench.py) do not re-allocate.
+namespace {
+
+long long var_elems_per_member(const nesosim_ctx *ctx, int v) {   // v indexes the 11 arrays of nesosim_outputs
+    const long long T = ctx->cfg.num_days;
+    return (v == 0 ? 2 : 1) * T * ctx->plane;
+}
+
+double *const *host_arrays(const nesosim_outputs *o, double *tmp[11]) {
+    tmp[0] = o->snowDepths; tmp[1] = o->density; tmp[2] = o->snowAcc; tmp[3] = o->snowOcean; tmp[4] = o->snowAdv;
+    tmp[5] = o->snowDiv; tmp[6] = o->snowLead; tmp[7] = o->snowAtm; tmp[8] = o->snowWindPackLoss;
+    tmp[9] = o->snowWindPackGain; tmp[10] = o->snowWindPack;
+    return tmp;
+}
+
+}  // namespace
+
+extern "C" int nesosim_run_season_host(nesosim_ctx *ctx, const double *precip, const double *conc,
+                                       const double *wind, const double *drift, const double *rho_clim,
+                                       const nesosim_member_params *params, const double *ic, int ic_per_member,
+                                       const nesosim_outputs *out_host, int64_t *h2d_bytes, int64_t *d2h_bytes) {
+    if (!ctx || !precip || !conc || !wind || !drift || !params || !out_host) return fail(NESOSIM_ERR_ARG, "NULL argument");
+    if (ctx->cfg.density_clim && !rho_clim) return fail(NESOSIM_ERR_ARG, "density_clim=1 needs rho_clim");
+    CU(cudaSetDevice(ctx->cfg.device));
+    const int M = ctx->cfg.n_members;
+    const long long T = ctx->cfg.num_days, plane = ctx->plane;
+    HostPath *hp = &ctx->hp;
+    int64_t up = 0, down = 0;
+
+    double *harr[11];
+    host_arrays(out_host, harr);
+    long long per_member = 0;   // device elements per member for the wanted outputs
+    for (int v = 0; v < 11; ++v)
+        if (harr[v]) per_member += var_elems_per_member(ctx, v);
+    if (per_member == 0) return fail(NESOSIM_ERR_ARG, "no output requested");
+
+    if (!hp->compute) {
+        CU(cudaStreamCreateWithFlags(&hp->compute, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&hp->copy, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreateWithFlags(&hp->done[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&hp->drained[i], cudaEventDisableTiming));
+        }
+    }
+    const size_t forcing_elems = (size_t)5 * T * plane + T;
+    if (!hp->forcing) CU(cudaMalloc(&hp->forcing, forcing_elems * sizeof(double)));
+    double *dP = hp->forcing, *dC = dP + T * plane, *dW = dC + T * plane, *dUV = dW + T * plane,
+           *dRho = dUV + 2 * T * plane;
+    CU(cudaMemcpyAsync(dP, precip, T * plane * 8, cudaMemcpyHostToDevice, hp->compute));
+    CU(cudaMemcpyAsync(dC, conc, T * plane * 8, cudaMemcpyHostToDevice, hp->compute));
+    CU(cudaMemcpyAsync(dW, wind, T * plane * 8, cudaMemcpyHostToDevice, hp->compute));
+    CU(cudaMemcpyAsync(dUV, drift, 2 * T * plane * 8, cudaMemcpyHostToDevice, hp->compute));
+    up += 5 * T * plane * 8;
+    if (rho_clim) {
+        CU(cudaMemcpyAsync(dRho, rho_clim, T * 8, cudaMemcpyHostToDevice, hp->compute));
+        up += T * 8;
+    }
+    const size_t ic_elems = ic ? (size_t)(ic_per_member ? M : 1) * plane : 0;
+    if (ic) {
+        if (hp->ic_elems < ic_elems) {
+            cudaFree(hp->ic);
+            hp->ic = nullptr;
+            CU(cudaMalloc(&hp->ic, ic_elems * sizeof(double)));
+            hp->ic_elems = ic_elems;
+        }
+        CU(cudaMemcpyAsync(hp->ic, ic, ic_elems * 8, cudaMemcpyHostToDevice, hp->compute));
+        up += ic_elems * 8;
+    }
+    CU(cudaStreamSynchronize(hp->compute));   // set_forcing reads rho_clim back; sources may be pageable
+    int rc = nesosim_set_forcing(ctx, dP, dC, dW, dUV, rho_clim ? dRho : nullptr);
+    if (rc) return rc;
+    if ((rc = upload_coef(ctx, params, hp->compute))) return rc;
+    up += (int64_t)sizeof(MemberCoef) * M;
+
+    // batch size: two device buffers of <= NESOSIM_HOST_BATCH_GB (default 8 GiB) each
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    double cap_gb = 8.0;
+    if (const char *e = getenv("NESOSIM_HOST_BATCH_GB")) cap_gb = atof(e);
+    size_t cap = (size_t)(cap_gb * (1ull << 30));
+    if (!hp->outbuf[0] && cap * 2 > free_b / 10 * 8) cap = free_b / 10 * 4;
+    int batch = (int)std::max<long long>(1, std::min<long long>(M, (long long)(cap / (per_member * 8))));
+    if (hp->batch < batch || !hp->outbuf[0]) {
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(hp->outbuf[i]);
+            hp->outbuf[i] = nullptr;
+        }
+        for (int i = 0; i < 2; ++i) CU(cudaMalloc(&hp->outbuf[i], (size_t)batch * per_member * 8));
+        hp->batch = batch;
+    }
+    batch = std::min(batch, hp->batch);
+
+    int nb = 0;
+    for (int m0 = 0; m0 < M; m0 += batch, ++nb) {
+        const int cnt = std::min(batch, M - m0);
+        const int b = nb & 1;
+        if (nb >= 2) CU(cudaStreamWaitEvent(hp->compute, hp->drained[b], 0));
+        // device views of this batch, variable-major inside the buffer
+        nesosim_outputs dev{};
+        double *darr[11];
+        long long off = 0;
+        for (int v = 0; v < 11; ++v) {
+            darr[v] = nullptr;
+            if (!harr[v]) continue;
+            darr[v] = hp->outbuf[b] + off;
+            off += var_elems_per_member(ctx, v) * cnt;
+        }
+        dev.snowDepths = darr[0]; dev.density = darr[1]; dev.snowAcc = darr[2]; dev.snowOcean = darr[3];
+        dev.snowAdv = darr[4]; dev.snowDiv = darr[5]; dev.snowLead = darr[6]; dev.snowAtm = darr[7];
+        dev.snowWindPackLoss = darr[8]; dev.snowWindPackGain = darr[9]; dev.snowWindPack = darr[10];
+        dev.depth_member_stride = 2 * T * plane;
+        dev.plane_member_stride = T * plane;
+        rc = run_members(ctx, ic ? hp->ic : nullptr, ic_per_member, &dev, m0, cnt, 0, -1, hp->compute);
+        if (rc) return rc;
+        CU(cudaEventRecord(hp->done[b], hp->compute));
+        CU(cudaStreamWaitEvent(hp->copy, hp->done[b], 0));
+        for (int v = 0; v < 11; ++v) {
+            if (!harr[v]) continue;
+            const long long n = var_elems_per_member(ctx, v);
+            const long long hstride = (v == 0) ? out_host->depth_member_stride : out_host->plane_member_stride;
+            if (hstride == n) {
+                CU(cudaMemcpyAsync(harr[v] + (long long)m0 * hstride, darr[v], (size_t)n * cnt * 8, cudaMemcpyDeviceToHost, hp->copy));
+            } else {
+                for (int m = 0; m < cnt; ++m)
+                    CU(cudaMemcpyAsync(harr[v] + (long long)(m0 + m) * hstride, darr[v] + (long long)m * n, (size_t)n * 8,
+                                       cudaMemcpyDeviceToHost, hp->copy));
+            }
+            down += n * cnt * 8;
+        }
+        CU(cudaEventRecord(hp->drained[b], hp->copy));
+    }
+    CU(cudaStreamSynchronize(hp->compute));
+    CU(cudaStreamSynchronize(hp->copy));
+    if (h2d_bytes) *h2d_bytes = up;
+    if (d2h_bytes) *d2h_bytes = down;
+    return NESOSIM_OK;
+}

@@ -1,0 +1,505 @@
+// nesosim_abi.cu -- C ABI (include/nesosim_b200.h) over the sm_100a kernels.  No torch, no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/nesosim_b200.h"
+#include "day_kernels.cuh"
+#include "ensemble_kernel.cuh"
+
+using namespace nesosim;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char *what) {
+    return fail(NESOSIM_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                            \
+    do {                                                    \
+        cudaError_t e_ = (call);                            \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+
+// Decide whether div_const()'s 3-operation path is provably exact for divisor c (see cell_math.cuh).
+// With c = B*2^e, B a 53-bit integer significand, x/c can only come within 3*2^-107 (relative to its binade) of
+// a rounding midpoint if |A*2^k - M*B| is tiny for some dividend significand A and odd M (k = 53 or 54).  When
+// B has t trailing zero bits that quantity is a non-zero multiple of 2^t, so t >= 8 already rules it out with
+// a wide margin; this covers every grid spacing (dx, 2*dx are integers below 2^29 metres) and the fresh-snow
+// density.  Divisors with a full significand (the Gaussian kernel sum) go through check_full_divisor().
+bool check_full_divisor(double c);
+
+ConstDiv const_div_host(double c) {
+    ConstDiv d;
+    d.c = c;
+    d.rc = 1.0 / c;
+    d.fast = 0;
+    if (!(std::fabs(c) >= 1e-100 && std::fabs(c) <= 1e100)) return d;
+    if (c == 1.0) { d.fast = 1; return d; }
+    int e;
+    const double mant = std::frexp(std::fabs(c), &e);             // [0.5, 1)
+    const unsigned long long B = (unsigned long long)std::ldexp(mant, 53);
+    const int tz = __builtin_ctzll(B);
+    d.fast = (tz >= 8) ? 1 : (check_full_divisor(c) ? 1 : 0);
+    return d;
+}
+
+// Exhaustive check for a divisor with an arbitrary significand B (odd part up to 53 bits): the only dividends
+// whose quotient can lie within 2^-105 of a midpoint are those with |A*2^k - M*B| <= LIM for an odd M, i.e.
+// A = (N * inv(2^k) mod B') solutions for |N| <= LIM -- a handful of significands per binade relation.  Each
+// candidate (and its neighbours) is run through the same three operations on the host (fma is exact in glibc)
+// and compared with the IEEE quotient.  Any mismatch disables the fast path for this divisor.
+unsigned long long mulmod(unsigned long long a, unsigned long long b, unsigned long long m) {
+    return (unsigned long long)(((unsigned __int128)a * b) % m);
+}
+unsigned long long powmod(unsigned long long a, unsigned long long e, unsigned long long m) {
+    unsigned long long r = 1 % m;
+    a %= m;
+    while (e) {
+        if (e & 1) r = mulmod(r, a, m);
+        a = mulmod(a, a, m);
+        e >>= 1;
+    }
+    return r;
+}
+long long egcd_inv(long long a, long long m) {   // inverse of a mod m, gcd(a,m)=1
+    __int128 t = 0, nt = 1, r = m, nr = a % m;
+    while (nr != 0) {
+        __int128 q = r / nr;
+        __int128 tmp = t - q * nt; t = nt; nt = tmp;
+        tmp = r - q * nr; r = nr; nr = tmp;
+    }
+    if (t < 0) t += m;
+    return (long long)t;
+}
+bool fast_div_matches(double x, double c, double rc) {
+    const double q0 = x * rc;
+    const double r = std::fma(-c, q0, x);
+    const double q = std::fma(r, rc, q0);
+    return q == x / c;
+}
+bool check_full_divisor(double c) {
+    int e;
+    const double mant = std::frexp(std::fabs(c), &e);
+    unsigned long long B = (unsigned long long)std::ldexp(mant, 53);   // [2^52, 2^53)
+    const int tz = __builtin_ctzll(B);
+    const unsigned long long Bodd = B >> tz;
+    if (Bodd == 1) return true;
+    const double rc = 1.0 / c;
+    const int LIM = 64;
+    for (int k = 53; k <= 54; ++k) {
+        // A * 2^k == N (mod Bodd)  ->  A == N * inv(2^k) (mod Bodd)
+        const unsigned long long p2 = powmod(2, (unsigned long long)k, Bodd);
+        const unsigned long long inv = (unsigned long long)egcd_inv((long long)p2, (long long)Bodd);
+        for (int N = -LIM; N <= LIM; ++N) {
+            if (N == 0) continue;
+            const unsigned long long Nm = (N > 0) ? (unsigned long long)N % Bodd : Bodd - ((unsigned long long)(-N) % Bodd);
+            unsigned long long A0 = mulmod(Nm % Bodd, inv, Bodd);
+            // all A in [2^52, 2^53) congruent to A0 mod Bodd (Bodd may be much smaller than 2^52 only when
+            // tz is large, which const_div_host() already accepted; cap the walk)
+            unsigned long long first = A0 + ((((1ULL << 52) > A0) ? ((1ULL << 52) - A0 + Bodd - 1) / Bodd : 0) * Bodd);
+            int walked = 0;
+            for (unsigned long long A = first; A < (1ULL << 53) && walked < 4096; A += Bodd, ++walked) {
+                for (int d = -1; d <= 1; ++d) {
+                    const double x = (double)(A + d);
+                    for (int s = -2; s <= 2; ++s) {
+                        const double xs = std::ldexp(x, s);
+                        if (!fast_div_matches(xs, c, rc) || !fast_div_matches(-xs, c, rc)) return false;
+                    }
+                }
+            }
+        }
+    }
+    return true;
+}
+
+// device-side resources of nesosim_run_season_host (host_path.inl), cached across calls
+struct HostPath {
+    double *forcing = nullptr;      // [P|C|W][T][plane] + drift [T][2][plane] + rho_clim [T]
+    double *ic = nullptr;
+    double *outbuf[2] = {nullptr, nullptr};
+    int batch = 0;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaEvent_t done[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr};
+    size_t ic_elems = 0;
+};
+
+
+}  // namespace
+
+struct nesosim_ctx {
+    nesosim_config cfg;
+    long long plane;
+    uint8_t *mask_dev = nullptr;
+    MemberCoef *coef_dev = nullptr;
+    const double *P = nullptr, *C = nullptr, *W = nullptr, *UV = nullptr, *rho_clim = nullptr;
+    std::vector<double> rho_clim_host;
+    double *scratch = nullptr;      // lazily allocated state for outputs the caller did not ask for
+    HostPath hp;
+    int *flags_dev = nullptr;
+    long long launches = 0;
+    ModelConsts k;
+    GradConsts g;
+    ConstDiv conv_div, rho_fresh_div;
+    EnsembleState ens;              // season-resident ensemble path (ensemble_kernel.cuh)
+};
+
+namespace {
+
+int upload_coef(nesosim_ctx *ctx, const nesosim_member_params *p, cudaStream_t st) {
+    const int M = ctx->cfg.n_members;
+    std::vector<MemberCoef> h(M);
+    for (int m = 0; m < M; ++m) {
+        h[m].llf = p[m].leadLossFactor;
+        h[m].alf = p[m].atmLossFactor;
+        h[m].wpt = p[m].windPackThresh;
+        h[m].neg_wpf_dt = (-p[m].windPackFactor) * ctx->cfg.deltaT;
+        h[m].wpf_dt = p[m].windPackFactor * ctx->cfg.deltaT;
+    }
+    // pageable source: the copy is staged before the call returns, so the vector may die afterwards
+    CU(cudaMemcpyAsync(ctx->coef_dev, h.data(), sizeof(MemberCoef) * M, cudaMemcpyHostToDevice, st));
+    return NESOSIM_OK;
+}
+
+int ensure_scratch(nesosim_ctx *ctx) {
+    if (ctx->scratch) return NESOSIM_OK;
+    const size_t n = (size_t)NVAR * 2 * ctx->cfg.n_members * ctx->plane;
+    CU(cudaMalloc(&ctx->scratch, n * sizeof(double)));
+    CU(cudaMemset(ctx->scratch, 0, n * sizeof(double)));
+    return NESOSIM_OK;
+}
+
+double *out_base(const nesosim_outputs *o, int v) {
+    switch (v) {
+        case V_H0: case V_H1: return o->snowDepths;
+        case V_DENS: return o->density;
+        case V_ACC: return o->snowAcc;
+        case V_OCEAN: return o->snowOcean;
+        case V_ADV: return o->snowAdv;
+        case V_DIV: return o->snowDiv;
+        case V_LEAD: return o->snowLead;
+        case V_ATM: return o->snowAtm;
+        case V_WPL: return o->snowWindPackLoss;
+        case V_WPG: return o->snowWindPackGain;
+        case V_WP: return o->snowWindPack;
+    }
+    return nullptr;
+}
+
+// pointer to variable v, time slot t, member 0, plus the member stride
+// (`o` already points at the first member of the range being run; `m0` only offsets the internal scratch)
+void slot_ptr(const nesosim_ctx *ctx, const nesosim_outputs *o, int v, int t, int m0, double **ptr, long long *stride) {
+    double *base = out_base(o, v);
+    const long long plane = ctx->plane;
+    if (base) {
+        if (v == V_H0 || v == V_H1) {
+            *ptr = base + ((long long)t * 2 + (v == V_H1 ? 1 : 0)) * plane;
+            *stride = o->depth_member_stride;
+        } else {
+            *ptr = base + (long long)t * plane;
+            *stride = o->plane_member_stride;
+        }
+    } else {
+        *ptr = ctx->scratch ? ctx->scratch + (((long long)v * 2 + (t & 1)) * ctx->cfg.n_members + m0) * plane : nullptr;
+        *stride = plane;
+    }
+}
+
+bool any_missing(const nesosim_outputs *o) {
+    for (int v = 0; v < NVAR; ++v)
+        if (v != V_DENS && !out_base(o, v)) return true;
+    return false;
+}
+
+int check_outputs(const nesosim_ctx *ctx, const nesosim_outputs *o) {
+    if (!o) return fail(NESOSIM_ERR_ARG, "outputs struct is NULL");
+    const long long T = ctx->cfg.num_days, plane = ctx->plane;
+    if (ctx->cfg.n_members > 1) {
+        if (o->snowDepths && o->depth_member_stride < T * 2 * plane)
+            return fail(NESOSIM_ERR_ARG, "depth_member_stride smaller than T*2*ny*nx");
+        if (o->plane_member_stride < T * plane) {
+            for (int v = 2; v < NVAR; ++v)
+                if (out_base(o, v)) return fail(NESOSIM_ERR_ARG, "plane_member_stride smaller than T*ny*nx");
+        }
+    }
+    return NESOSIM_OK;
+}
+
+int launch_day(nesosim_ctx *ctx, int x, const double *P, const double *C, const double *W, const double *U,
+               const double *V, double rho_new, const nesosim_outputs *o, int m0, int mcount, cudaStream_t st) {
+    DayArgs a;
+    a.ny = ctx->cfg.ny;
+    a.nx = ctx->cfg.nx;
+    a.P = P; a.C = C; a.W = W; a.U = U; a.V = V;
+    a.mask = ctx->mask_dev;
+    for (int v = 0; v < NVAR; ++v) {
+        double *pp, *np_;
+        long long ps, ns;
+        slot_ptr(ctx, o, v, x, m0, &pp, &ps);
+        slot_ptr(ctx, o, v, x + 1, m0, &np_, &ns);
+        a.prev[v] = pp; a.prev_stride[v] = ps;
+        a.next[v] = np_; a.next_stride[v] = ns;
+    }
+    if (!o->density) a.next[V_DENS] = nullptr;
+    a.coef = ctx->coef_dev + m0;
+    a.k = ctx->k;
+    a.g = ctx->g;
+    a.conv_div = ctx->conv_div;
+    a.rho_new = ctx->cfg.density_clim ? const_div_host(rho_new) : ctx->rho_fresh_div;
+    std::memcpy(a.w, ctx->cfg.conv_weights, sizeof(a.w));
+    a.sw = Switches{ctx->cfg.dynamicsInc == 1, ctx->cfg.leadlossInc == 1, ctx->cfg.windpackInc == 1,
+                    ctx->cfg.atmlossInc == 1, ctx->cfg.density_clim != 0};
+    dim3 grid((a.nx + TX - 1) / TX, (a.ny + TY - 1) / TY, mcount);
+    day_step_kernel<<<grid, DAY_THREADS, 0, st>>>(a);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return NESOSIM_OK;
+}
+
+int launch_init(nesosim_ctx *ctx, const double *ic, int ic_per_member, const double *conc0,
+                const nesosim_outputs *o, int m0, int mcount, cudaStream_t st) {
+    InitArgs a;
+    a.plane = ctx->plane;
+    a.ic = (ic && ic_per_member) ? ic + (long long)m0 * ctx->plane : ic;
+    a.ic_stride = ic_per_member ? ctx->plane : 0;
+    a.conc0 = conc0;
+    a.minConc = ctx->cfg.minConc;
+    for (int v = 0; v < NVAR; ++v) {
+        double *p;
+        long long s;
+        slot_ptr(ctx, o, v, 0, m0, &p, &s);
+        a.slot0[v] = p;
+        a.stride[v] = s;
+    }
+    if (!o->density) a.slot0[V_DENS] = nullptr;
+    dim3 grid((unsigned)((ctx->plane + 255) / 256), mcount);
+    init_slot0_kernel<<<grid, 256, 0, st>>>(a);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return NESOSIM_OK;
+}
+
+// Steps first_step .. first_step+num_steps-1 for members [m0, m0+mcount); `out` addresses member m0.
+int run_members(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, const nesosim_outputs *out, int m0,
+                int mcount, int first_step, int num_steps, cudaStream_t st) {
+    const int T = ctx->cfg.num_days;
+    if (num_steps < 0) num_steps = T - 1 - first_step;
+    if (first_step < 0 || first_step + num_steps > T - 1) return fail(NESOSIM_ERR_ARG, "step range outside the season");
+    int rc;
+    if (any_missing(out) && (rc = ensure_scratch(ctx))) return rc;
+    if (first_step == 0 && (rc = launch_init(ctx, ic_dev, ic_per_member, ctx->C, out, m0, mcount, st))) return rc;
+    const long long plane = ctx->plane;
+    for (int x = first_step; x < first_step + num_steps; ++x) {
+        const double rho = ctx->cfg.density_clim ? ctx->rho_clim_host[x] : ctx->cfg.snowDensityFresh;
+        rc = launch_day(ctx, x, ctx->P + x * plane, ctx->C + x * plane, ctx->W + x * plane,
+                        ctx->UV + (long long)x * 2 * plane, ctx->UV + ((long long)x * 2 + 1) * plane, rho, out,
+                        m0, mcount, st);
+        if (rc) return rc;
+    }
+    return NESOSIM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nesosim_abi_version(void) { return NESOSIM_ABI_VERSION; }
+const char *nesosim_last_error(void) { return g_err.c_str(); }
+
+int nesosim_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int nesosim_create(const nesosim_config *cfg, const uint8_t *region_mask_host, nesosim_ctx **out) {
+    if (!cfg || !region_mask_host || !out) return fail(NESOSIM_ERR_ARG, "NULL argument");
+    if (cfg->ny < 2 || cfg->nx < 2) return fail(NESOSIM_ERR_ARG, "ny and nx must be >= 2 (np.gradient needs two points)");
+    if (cfg->num_days < 2) return fail(NESOSIM_ERR_ARG, "num_days must be >= 2");
+    if (cfg->n_members < 1 || cfg->n_members > 65535) return fail(NESOSIM_ERR_ARG, "n_members must be in [1, 65535]");
+    if (!(cfg->dx > 0) || !(cfg->deltaT > 0)) return fail(NESOSIM_ERR_ARG, "dx and deltaT must be positive");
+    if (!(cfg->conv_divisor != 0)) return fail(NESOSIM_ERR_ARG, "conv_divisor must be non-zero");
+    if (nesosim_device_count() <= cfg->device || cfg->device < 0)
+        return fail(NESOSIM_ERR_CUDA, "no such CUDA device (this library has no CPU path)");
+    CU(cudaSetDevice(cfg->device));
+    nesosim_ctx *ctx = new (std::nothrow) nesosim_ctx();
+    if (!ctx) return fail(NESOSIM_ERR_NOMEM, "out of host memory");
+    ctx->cfg = *cfg;
+    ctx->plane = (long long)cfg->ny * cfg->nx;
+    ctx->k = ModelConsts{cfg->deltaT, cfg->snowDensityFresh, cfg->snowDensityOld,
+                         cfg->snowDensityFresh / cfg->snowDensityOld, cfg->minSnowD, cfg->minConc};
+    ctx->g.dx = const_div_host(cfg->dx);
+    ctx->g.two_dx = const_div_host(2. * cfg->dx);
+    ctx->conv_div = const_div_host(cfg->conv_divisor);
+    ctx->rho_fresh_div = const_div_host(cfg->snowDensityFresh);
+    cudaError_t e = cudaMalloc(&ctx->mask_dev, ctx->plane);
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->mask_dev, region_mask_host, ctx->plane, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->coef_dev, sizeof(MemberCoef) * cfg->n_members);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->flags_dev, sizeof(int));
+    if (e != cudaSuccess) {
+        nesosim_destroy(ctx);
+        return cuda_fail(e, "nesosim_create allocation");
+    }
+    *out = ctx;
+    return NESOSIM_OK;
+}
+
+int nesosim_destroy(nesosim_ctx *ctx) {
+    if (!ctx) return NESOSIM_OK;
+    cudaSetDevice(ctx->cfg.device);
+    ensemble_release(ctx->ens);
+    cudaFree(ctx->mask_dev);
+    cudaFree(ctx->coef_dev);
+    cudaFree(ctx->scratch);
+    cudaFree(ctx->flags_dev);
+    cudaFree(ctx->hp.forcing);
+    cudaFree(ctx->hp.ic);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(ctx->hp.outbuf[i]);
+        if (ctx->hp.done[i]) cudaEventDestroy(ctx->hp.done[i]);
+        if (ctx->hp.drained[i]) cudaEventDestroy(ctx->hp.drained[i]);
+    }
+    if (ctx->hp.compute) cudaStreamDestroy(ctx->hp.compute);
+    if (ctx->hp.copy) cudaStreamDestroy(ctx->hp.copy);
+    delete ctx;
+    return NESOSIM_OK;
+}
+
+int nesosim_set_forcing(nesosim_ctx *ctx, const double *precip_dev, const double *conc_dev,
+                        const double *wind_dev, const double *drift_dev, const double *rho_clim_dev) {
+    if (!ctx || !precip_dev || !conc_dev || !wind_dev || !drift_dev) return fail(NESOSIM_ERR_ARG, "NULL forcing pointer");
+    if (ctx->cfg.density_clim && !rho_clim_dev) return fail(NESOSIM_ERR_ARG, "density_clim=1 needs rho_clim");
+    CU(cudaSetDevice(ctx->cfg.device));
+    ctx->P = precip_dev; ctx->C = conc_dev; ctx->W = wind_dev; ctx->UV = drift_dev; ctx->rho_clim = rho_clim_dev;
+    ctx->rho_clim_host.clear();
+    if (ctx->cfg.density_clim) {
+        ctx->rho_clim_host.resize(ctx->cfg.num_days);
+        CU(cudaMemcpy(ctx->rho_clim_host.data(), rho_clim_dev, sizeof(double) * ctx->cfg.num_days, cudaMemcpyDeviceToHost));
+    }
+    ctx->ens.derived_valid = false;
+    return NESOSIM_OK;
+}
+
+int nesosim_run_season(nesosim_ctx *ctx, const nesosim_member_params *params_host, const double *ic_dev,
+                       int ic_per_member, const nesosim_outputs *out, int first_step, int num_steps,
+                       void *stream) {
+    if (!ctx || !params_host) return fail(NESOSIM_ERR_ARG, "NULL argument");
+    if (!ctx->P) return fail(NESOSIM_ERR_STATE, "nesosim_set_forcing has not been called");
+    int rc = check_outputs(ctx, out);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = upload_coef(ctx, params_host, st))) return rc;
+    return run_members(ctx, ic_dev, ic_per_member, out, 0, ctx->cfg.n_members, first_step, num_steps, st);
+}
+
+int nesosim_step_day(nesosim_ctx *ctx, int x, const double *conc_dev, const double *precip_dev,
+                     const double *drift_dev, const double *wind_dev, double rho_new,
+                     const nesosim_member_params *params_host, const nesosim_outputs *out, void *stream) {
+    if (!ctx || !conc_dev || !precip_dev || !drift_dev || !wind_dev || !params_host)
+        return fail(NESOSIM_ERR_ARG, "NULL argument");
+    if (x < 0 || x + 1 >= ctx->cfg.num_days) return fail(NESOSIM_ERR_ARG, "x outside [0, num_days-2]");
+    int rc = check_outputs(ctx, out);
+    if (rc) return rc;
+    if (any_missing(out)) return fail(NESOSIM_ERR_ARG, "nesosim_step_day needs every accumulator and snowDepths (density optional)");
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = upload_coef(ctx, params_host, st))) return rc;
+    return launch_day(ctx, x, precip_dev, conc_dev, wind_dev, drift_dev, drift_dev + ctx->plane, rho_new, out, 0,
+                      ctx->cfg.n_members, st);
+}
+
+int nesosim_smooth(const double *in_dev, double *out_dev, int ny, int nx, const double weights_host[9],
+                   double divisor, void *stream) {
+    if (!in_dev || !out_dev || !weights_host || ny < 1 || nx < 1 || in_dev == out_dev)
+        return fail(NESOSIM_ERR_ARG, "bad argument to nesosim_smooth");
+    cudaStream_t st = (cudaStream_t)stream;
+    int *flags;
+    CU(cudaMallocAsync(&flags, sizeof(int), st));
+    CU(cudaMemsetAsync(flags, 0, sizeof(int), st));
+    const long long n = (long long)ny * nx;
+    scan_nonfinite_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 1184), 256, 0, st>>>(in_dev, n, flags);
+    SmoothArgs a;
+    a.in = in_dev; a.out = out_dev; a.ny = ny; a.nx = nx;
+    std::memcpy(a.w, weights_host, sizeof(a.w));
+    a.div = const_div_host(divisor);
+    a.flags = flags;
+    dim3 blk(32, 8), grid((nx + 31) / 32, (ny + 7) / 8);
+    smooth_kernel<<<grid, blk, 0, st>>>(a);
+    CU(cudaGetLastError());
+    CU(cudaFreeAsync(flags, st));
+    return NESOSIM_OK;
+}
+
+int nesosim_op_dynamics(const double *drift_dev, const double *depths_dev, double dx, double deltaT, int ny,
+                        int nx, double *adv_dev, double *div_dev, void *stream) {
+    if (!drift_dev || !depths_dev || !adv_dev || !div_dev || ny < 2 || nx < 2) return fail(NESOSIM_ERR_ARG, "bad argument");
+    GradConsts g;
+    g.dx = const_div_host(dx);
+    g.two_dx = const_div_host(2. * dx);
+    dim3 blk(32, 8), grid((nx + 31) / 32, (ny + 7) / 8);
+    op_dynamics_kernel<<<grid, blk, 0, (cudaStream_t)stream>>>(drift_dev, depths_dev, ny, nx, deltaT, g, adv_dev, div_dev);
+    CU(cudaGetLastError());
+    return NESOSIM_OK;
+}
+
+int nesosim_op_wind_terms(const double *h0_dev, const double *wind_dev, const double *conc_dev, int64_t n,
+                          const nesosim_member_params *p, double deltaT, double rhoFresh, double rhoOld,
+                          double *lead_dev, double *atm_dev, double *wp_loss_dev, double *wp_gain_dev,
+                          double *wp_net_dev, void *stream) {
+    if (!h0_dev || !wind_dev || !conc_dev || !p || n < 0) return fail(NESOSIM_ERR_ARG, "bad argument");
+    if (n == 0) return NESOSIM_OK;
+    MemberCoef mc{p->leadLossFactor, p->atmLossFactor, p->windPackThresh, (-p->windPackFactor) * deltaT,
+                  p->windPackFactor * deltaT};
+    ModelConsts k{deltaT, rhoFresh, rhoOld, rhoFresh / rhoOld, 0.0, 0.0};
+    op_wind_terms_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        h0_dev, wind_dev, conc_dev, n, mc, k, lead_dev, atm_dev, wp_loss_dev, wp_gain_dev, wp_net_dev);
+    CU(cudaGetLastError());
+    return NESOSIM_OK;
+}
+
+int nesosim_op_fill_zero(double *arr_dev, int64_t n, void *stream) {
+    if (!arr_dev || n < 0) return fail(NESOSIM_ERR_ARG, "bad argument");
+    if (n == 0) return NESOSIM_OK;
+    op_fill_zero_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(arr_dev, n);
+    CU(cudaGetLastError());
+    return NESOSIM_OK;
+}
+
+int nesosim_op_fill_nan_no_negative(double *arr_dev, const uint8_t *mask_dev, int64_t n, int negative_to_zero,
+                                    void *stream) {
+    if (!arr_dev || !mask_dev || n < 0) return fail(NESOSIM_ERR_ARG, "bad argument");
+    if (n == 0) return NESOSIM_OK;
+    op_fill_nan_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(arr_dev, mask_dev, n, negative_to_zero);
+    CU(cudaGetLastError());
+    return NESOSIM_OK;
+}
+
+int nesosim_op_density(const double *depths_dev, const uint8_t *mask_dev, int64_t n, double rhoFresh,
+                       double rhoOld, double minSnowD, double *density_dev, void *stream) {
+    if (!depths_dev || !mask_dev || !density_dev || n < 0) return fail(NESOSIM_ERR_ARG, "bad argument");
+    if (n == 0) return NESOSIM_OK;
+    ModelConsts k{0.0, rhoFresh, rhoOld, rhoFresh / rhoOld, minSnowD, 0.0};
+    op_density_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(depths_dev, mask_dev, n, k, density_dev);
+    CU(cudaGetLastError());
+    return NESOSIM_OK;
+}
+
+int64_t nesosim_launch_count(const nesosim_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"
+
+#include "host_path.inl"

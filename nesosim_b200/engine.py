@@ -1,0 +1,288 @@
+"""Python handle on the native snow-budget context.  PyTorch is used only to own device memory and streams;
+every number is computed by ``libnesosim_b200.so`` through the C ABI in ``include/nesosim_b200.h``.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+DEFAULTS = dict(snowDensityFresh=200., snowDensityOld=350., minSnowD=0.02, minConc=0.15, deltaT=60. * 60. * 24.)
+
+
+def gaussian_kernel_3x3(stddev=1.0, size=3):
+    """Host-side weights of ``Gaussian2DKernel(x_stddev=stddev, x_size=size, y_size=size)`` (smooth_snow,
+    NESOSIM.py:184).  astropy's own array is used when astropy is installed; otherwise the same closed form
+    (amplitude 1/(2*pi*s^2) times exp(-(0.5*x^2/s^2 + 0.5*y^2/s^2)) sampled at integer offsets)."""
+    try:   # pragma: no cover - astropy is absent from the build image
+        from astropy.convolution import Gaussian2DKernel
+        return np.array(Gaussian2DKernel(x_stddev=stddev, x_size=size, y_size=size).array, dtype=np.float64)
+    except Exception:
+        pass
+    s = float(stddev)
+    r = np.arange(-(int(size) // 2), int(size) // 2 + 1)
+    x, y = np.meshgrid(r, r)
+    x = x.astype(float)
+    y = y.astype(float)
+    a = 0.5 * ((1.0 / s ** 2) + (0.0 / s ** 2))
+    c = 0.5 * ((0.0 / s ** 2) + (1.0 / s ** 2))
+    return (1. / (2 * np.pi * s * s)) * np.exp(-((a * x ** 2) + (0.0 * x * y) + (c * y ** 2)))
+
+
+def conv_constants(variant="post_divide"):
+    """(weights[9], divisor) handed to the device.  ``post_divide`` = astropy 3.1-4.x order (raw kernel, then
+    ``result /= kernel.sum()``); ``pre_normalised`` = kernel divided by its sum first (divisor 1)."""
+    g = gaussian_kernel_3x3()
+    ksum = g.sum()
+    if variant == "post_divide":
+        return g.reshape(-1).copy(), float(ksum)
+    if variant == "pre_normalised":
+        return (g / ksum).reshape(-1).copy(), 1.0
+    raise ValueError("conv_variant must be 'post_divide' or 'pre_normalised'")
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def region_codes_u8(region_mask):
+    """Any numeric mask -> uint8 codes preserving the only two predicates the model tests (>10, <1)."""
+    m = np.asarray(region_mask)
+    out = np.full(m.shape, 5, dtype=np.uint8)
+    with np.errstate(invalid="ignore"):
+        out[m > 10] = 11
+        out[m < 1] = 0
+    return np.ascontiguousarray(out)
+
+
+class SnowBudgetEngine:
+    """One native context: grid + constants + switches for ``n_members`` parameter sets sharing one forcing."""
+
+    def __init__(self, region_mask, num_days, dx, n_members=1, dynamicsInc=1, leadlossInc=1, windpackInc=1,
+                 atmlossInc=0, densityType="variable", conv_variant="post_divide", device=0, **consts):
+        self.lib = _lib.load()
+        mask = region_codes_u8(region_mask)
+        self.ny, self.nx = mask.shape
+        self.T = int(num_days)
+        self.M = int(n_members)
+        self.device = int(device)
+        k = dict(DEFAULTS)
+        k.update(consts)
+        cfg = _lib.Config()
+        cfg.ny, cfg.nx, cfg.num_days, cfg.n_members = self.ny, self.nx, self.T, self.M
+        cfg.dx = float(dx)
+        for name in DEFAULTS:
+            setattr(cfg, name, float(k[name]))
+        w, div = conv_constants(conv_variant)
+        cfg.conv_weights = (C.c_double * 9)(*w.tolist())
+        cfg.conv_divisor = div
+        cfg.dynamicsInc, cfg.leadlossInc, cfg.windpackInc, cfg.atmlossInc = (int(dynamicsInc), int(leadlossInc),
+                                                                            int(windpackInc), int(atmlossInc))
+        cfg.density_clim = 1 if densityType == "clim" else 0
+        cfg.device = self.device
+        self.cfg = cfg
+        self._weights = w
+        self._divisor = div
+        handle = C.c_void_p()
+        _lib.check(self.lib.nesosim_create(C.byref(cfg), mask.ctypes.data_as(C.c_void_p), C.byref(handle)))
+        self.handle = handle
+        self._forcing = None
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.nesosim_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------ device API
+    def _dev(self, a):
+        torch = _torch()
+        if isinstance(a, torch.Tensor):
+            t = a
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+        return t.to(device="cuda:%d" % self.device, dtype=torch.float64).contiguous()
+
+    def set_forcing(self, precip, conc, wind, drift, rho_clim=None):
+        """Stage a season of forcing in HBM (arrays (T,ny,nx), drift (T,2,ny,nx); numpy or CUDA tensors)."""
+        f = [self._dev(precip), self._dev(conc), self._dev(wind), self._dev(drift)]
+        T, ny, nx = self.T, self.ny, self.nx
+        assert tuple(f[0].shape) == (T, ny, nx) and tuple(f[3].shape) == (T, 2, ny, nx), "forcing shape"
+        rc = None if rho_clim is None else self._dev(rho_clim)
+        self._forcing = f + [rc]
+        _lib.check(self.lib.nesosim_set_forcing(self.handle, f[0].data_ptr(), f[1].data_ptr(), f[2].data_ptr(),
+                                                f[3].data_ptr(), None if rc is None else rc.data_ptr()))
+
+    def alloc_outputs(self, names=_lib.OUTPUT_NAMES, zero=False):
+        """Device tensors shaped like genEmptyArrays (NESOSIM.py:350-376) with a leading member axis."""
+        torch = _torch()
+        mk = torch.zeros if zero else torch.empty
+        dev = "cuda:%d" % self.device
+        out = {}
+        for n in names:
+            shape = (self.M, self.T, 2, self.ny, self.nx) if n == "snowDepths" else (self.M, self.T, self.ny, self.nx)
+            out[n] = mk(shape, dtype=torch.float64, device=dev)
+        return out
+
+    def _outputs_struct(self, outputs):
+        o = _lib.Outputs()
+        plane = self.ny * self.nx
+        for n in _lib.OUTPUT_NAMES:
+            t = outputs.get(n)
+            if t is None:
+                setattr(o, n, None)
+                continue
+            assert t.is_contiguous() and t.dtype == _torch().float64
+            setattr(o, n, t.data_ptr())
+        o.depth_member_stride = self.T * 2 * plane
+        o.plane_member_stride = self.T * plane
+        return o
+
+    def _stream(self):
+        return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    def run_season(self, params, ic=None, outputs=None, first_step=0, num_steps=-1):
+        """All members, steps ``first_step .. first_step+num_steps-1``; returns the dict of device tensors."""
+        if outputs is None:
+            outputs = self.alloc_outputs()
+        p = _lib.member_params_array(params)
+        assert len(p) == self.M, "need one parameter row per member"
+        ic_t = None if ic is None else self._dev(ic)
+        per_member = 0
+        if ic_t is not None:
+            per_member = 1 if (ic_t.dim() == 3 and self.M > 1) else 0
+            assert tuple(ic_t.shape[-2:]) == (self.ny, self.nx)
+        o = self._outputs_struct(outputs)
+        _lib.check(self.lib.nesosim_run_season(self.handle, p, None if ic_t is None else ic_t.data_ptr(), per_member,
+                                               C.byref(o), int(first_step), int(num_steps), self._stream()))
+        self._keep = (ic_t, outputs)
+        return outputs
+
+    def step_day(self, x, conc, precip, drift, wind, params, outputs, rho_new=200.):
+        """One ``calcBudget`` (NESOSIM.py:224-347) on explicit day planes; mutates slot x+1 of ``outputs``."""
+        p = _lib.member_params_array(params)
+        planes = [self._dev(conc), self._dev(precip), self._dev(drift), self._dev(wind)]
+        o = self._outputs_struct(outputs)
+        _lib.check(self.lib.nesosim_step_day(self.handle, int(x), planes[0].data_ptr(), planes[1].data_ptr(),
+                                             planes[2].data_ptr(), planes[3].data_ptr(), float(rho_new), p,
+                                             C.byref(o), self._stream()))
+        self._keep = (planes, outputs)
+
+    def launch_count(self):
+        return int(self.lib.nesosim_launch_count(self.handle))
+
+    # -------------------------------------------------------------------------------------------- host API
+    def run_season_host(self, forcing, params, ic=None, outputs=None, names=_lib.OUTPUT_NAMES):
+        """End-to-end call on HOST numpy arrays (H2D + season + D2H inside).  Returns (outputs, h2d, d2h)."""
+        T, ny, nx, M = self.T, self.ny, self.nx, self.M
+        if outputs is None:
+            outputs = {}
+            for n in names:
+                shape = (M, T, 2, ny, nx) if n == "snowDepths" else (M, T, ny, nx)
+                outputs[n] = np.empty(shape, dtype=np.float64)
+
+        def hp(a):
+            if a is None:
+                return None
+            if hasattr(a, "data_ptr"):      # pinned torch CPU tensor
+                return C.c_void_p(a.data_ptr())
+            assert a.dtype == np.float64 and a.flags.c_contiguous
+            return a.ctypes.data_as(C.c_void_p)
+
+        o = _lib.Outputs()
+        for n in _lib.OUTPUT_NAMES:
+            setattr(o, n, hp(outputs.get(n)))
+        plane = ny * nx
+        o.depth_member_stride = T * 2 * plane
+        o.plane_member_stride = T * plane
+        p = _lib.member_params_array(params)
+        per_member = 0
+        if ic is not None and getattr(ic, "ndim", 2) == 3 and M > 1:
+            per_member = 1
+        up, down = C.c_int64(0), C.c_int64(0)
+        _lib.check(self.lib.nesosim_run_season_host(self.handle, hp(forcing["precip"]), hp(forcing["conc"]),
+                                                    hp(forcing["wind"]), hp(forcing["drift"]),
+                                                    hp(forcing.get("rho_clim")), p, hp(ic), per_member,
+                                                    C.byref(o), C.byref(up), C.byref(down)))
+        return outputs, up.value, down.value
+
+
+# -------------------------------------------------------------------------------- per-function device ops
+
+def _cuda(a, device=0, dtype=None):
+    torch = _torch()
+    t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+    return t.to(device="cuda:%d" % device, dtype=dtype or t.dtype).contiguous()
+
+
+def _cur_stream(device=0):
+    return C.c_void_p(_torch().cuda.current_stream(device).cuda_stream)
+
+
+def smooth(arr, conv_variant="post_divide", device=0):
+    """``smooth_snow`` (NESOSIM.py:170-187) on the GPU; numpy in, numpy out (new array, as the reference)."""
+    torch = _torch()
+    lib = _lib.load()
+    a = _cuda(np.asarray(arr, dtype=np.float64), device)
+    out = torch.empty_like(a)
+    w, div = conv_constants(conv_variant)
+    wc = (C.c_double * 9)(*w.tolist())
+    _lib.check(lib.nesosim_smooth(a.data_ptr(), out.data_ptr(), a.shape[0], a.shape[1], wc, div, _cur_stream(device)))
+    return out.cpu().numpy()
+
+
+def op_dynamics(drift, depths, dx, deltaT=86400., device=0):
+    torch = _torch()
+    lib = _lib.load()
+    d = _cuda(np.asarray(drift, dtype=np.float64), device)
+    h = _cuda(np.asarray(depths, dtype=np.float64), device)
+    adv = torch.empty_like(h)
+    div = torch.empty_like(h)
+    _lib.check(lib.nesosim_op_dynamics(d.data_ptr(), h.data_ptr(), float(dx), float(deltaT), h.shape[1], h.shape[2],
+                                       adv.data_ptr(), div.data_ptr(), _cur_stream(device)))
+    return adv.cpu().numpy(), div.cpu().numpy()
+
+
+def op_wind_terms(h0, wind, conc, params, deltaT=86400., rhoFresh=200., rhoOld=350., device=0):
+    torch = _torch()
+    lib = _lib.load()
+    a = [_cuda(np.asarray(v, dtype=np.float64), device) for v in (h0, wind, conc)]
+    outs = [torch.empty_like(a[0]) for _ in range(5)]
+    p = _lib.member_params_array(params)
+    _lib.check(lib.nesosim_op_wind_terms(a[0].data_ptr(), a[1].data_ptr(), a[2].data_ptr(), a[0].numel(), p,
+                                         float(deltaT), float(rhoFresh), float(rhoOld),
+                                         *[o.data_ptr() for o in outs], _cur_stream(device)))
+    return [o.cpu().numpy() for o in outs]
+
+
+def op_fill_zero(arr, device=0):
+    lib = _lib.load()
+    a = _cuda(np.array(arr, dtype=np.float64), device)
+    _lib.check(lib.nesosim_op_fill_zero(a.data_ptr(), a.numel(), _cur_stream(device)))
+    return a.cpu().numpy()
+
+
+def op_fill_nan_no_negative(arr, mask, negative_to_zero=True, device=0):
+    lib = _lib.load()
+    a = _cuda(np.array(arr, dtype=np.float64), device)
+    m = _cuda(region_codes_u8(mask), device)
+    _lib.check(lib.nesosim_op_fill_nan_no_negative(a.data_ptr(), m.data_ptr(), a.numel(), int(bool(negative_to_zero)),
+                                                   _cur_stream(device)))
+    return a.cpu().numpy()
+
+
+def op_density(depths, mask, rhoFresh=200., rhoOld=350., minSnowD=0.02, device=0):
+    torch = _torch()
+    lib = _lib.load()
+    h = _cuda(np.asarray(depths, dtype=np.float64), device)
+    m = _cuda(region_codes_u8(mask), device)
+    rho = torch.empty_like(h[0])
+    _lib.check(lib.nesosim_op_density(h.data_ptr(), m.data_ptr(), rho.numel(), float(rhoFresh), float(rhoOld),
+                                      float(minSnowD), rho.data_ptr(), _cur_stream(device)))
+    return rho.cpu().numpy()

@@ -1,0 +1,289 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): NaN/land/ice masks bit-exact (identical ``isnan`` patterns) and every value
+within 1e-10 relative -- the tests below assert the stronger property the design aims for: value-identical
+(``np.array_equal(..., equal_nan=True)``) on every array, and additionally state the 1e-10 tolerance check.
+"""
+import numpy as np
+import pytest
+
+from nesosim_b200 import synthetic as S
+from oracle import nesosim_oracle as O
+from oracle.astropy_restated import convolve_fill0, gaussian2d_kernel
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10   # tolerance stated by north_star for snow volume / depth / density / both layers
+ATOL = 1e-300
+
+
+def assert_parity(got, ref, name):
+    assert got.shape == ref.shape, name
+    assert np.array_equal(np.isnan(got), np.isnan(ref)), "NaN mask differs: " + name
+    fin = ~np.isnan(ref)
+    assert np.allclose(got[fin], ref[fin], rtol=RTOL, atol=ATOL), "outside 1e-10: " + name
+    assert np.array_equal(got, ref, equal_nan=True), "not value-identical: " + name
+
+
+def oracle_params(row, **kw):
+    return O.Params(windPackFactor=row[0], windPackThresh=row[1], leadLossFactor=row[2], atmLossFactor=row[3], **kw)
+
+
+def run_both(mask, T, dx, params, flags, seed=0, rho_clim=None, ic_scale=1.0, conv_variant="post_divide"):
+    from nesosim_b200.engine import SnowBudgetEngine
+    forcing = S.make_season(mask, T, seed=seed)
+    ic = S.make_ic(mask, seed=seed) * ic_scale
+    params = np.asarray(params, dtype=float).reshape(-1, 4)
+    eng = SnowBudgetEngine(mask, T, dx, n_members=len(params), conv_variant=conv_variant, **flags)
+    eng.set_forcing(forcing["precip"], forcing["conc"], forcing["wind"], forcing["drift"], rho_clim)
+    out = eng.run_season(params, ic)
+    got = {k: v.cpu().numpy() for k, v in out.items()}
+    eng.close()
+    refs = []
+    fl = O.Flags(dynamicsInc=flags.get("dynamicsInc", 1), leadlossInc=flags.get("leadlossInc", 1),
+                 windpackInc=flags.get("windpackInc", 1), atmlossInc=flags.get("atmlossInc", 0),
+                 densityType=flags.get("densityType", "variable"), conv_variant=conv_variant)
+    for row in params:
+        refs.append(O.run_season(forcing, ic, mask, dx, oracle_params(row), fl, rho_clim=rho_clim))
+    return got, refs
+
+
+def compare_all(got, refs):
+    for m, ref in enumerate(refs):
+        for name in got:
+            assert_parity(got[name][m], ref[name], "%s[member %d]" % (name, m))
+
+
+ONESEASON = [5.8e-7, 5., 2.9e-7, 2.2e-8]      # run_oneseason.py:40-48
+MULTISEASON = [5.8e-7, 5., 1.45e-7, 2.2e-8]   # run_multiseason.py:42-50
+
+
+def test_season_100km_oneseason_params(cuda):
+    mask = S.region_mask(dx=100000)
+    got, refs = run_both(mask, 62, 100000, [ONESEASON], dict(atmlossInc=0), seed=11)
+    compare_all(got, refs)
+    h = got["snowDepths"][0]
+    assert np.isfinite(h).sum() > 1000 and np.nanmax(h) > 0.01      # the comparison is not vacuous
+
+
+def test_season_100km_multiseason_params_ensemble(cuda):
+    mask = S.region_mask(dx=100000)
+    params = np.vstack([MULTISEASON, S.ensemble_params(4, seed=5)])
+    got, refs = run_both(mask, 40, 100000, params, dict(atmlossInc=1), seed=12)
+    compare_all(got, refs)
+    # members really differ
+    assert not np.array_equal(got["snowDepths"][1], got["snowDepths"][2], equal_nan=True)
+
+
+@pytest.mark.parametrize("flags", [dict(dynamicsInc=0), dict(leadlossInc=0, atmlossInc=1), dict(windpackInc=0),
+                                   dict(dynamicsInc=0, leadlossInc=0, windpackInc=0, atmlossInc=0)])
+def test_switches(cuda, flags):
+    mask = S.region_mask(dx=100000)
+    got, refs = run_both(mask, 12, 100000, [MULTISEASON], flags, seed=13)
+    compare_all(got, refs)
+
+
+def test_clim_density(cuda):
+    mask = S.region_mask(dx=100000)
+    T = 15
+    rho = 1000 * (0.29 + 0.0003 * np.arange(T))      # shape of W99_density.csv values (utils.py:1336-1343)
+    got, refs = run_both(mask, T, 100000, [ONESEASON], dict(densityType="clim"), seed=14, rho_clim=rho)
+    compare_all(got, refs)
+
+
+def test_ragged_grid_not_multiple_of_tile(cuda):
+    mask = S.region_mask(shape=(45, 70), kind="disc")
+    got, refs = run_both(mask, 10, 50000, [MULTISEASON, ONESEASON], dict(atmlossInc=1), seed=15, ic_scale=3.0)
+    compare_all(got, refs)
+
+
+def test_minimum_grid_2x2(cuda):
+    mask = np.full((2, 2), 8, dtype=np.uint8)
+    got, refs = run_both(mask, 5, 100000, [MULTISEASON], dict(atmlossInc=1), seed=16)
+    compare_all(got, refs)
+
+
+def test_prenormalised_kernel_variant(cuda):
+    mask = S.region_mask(dx=100000)
+    got, refs = run_both(mask, 8, 100000, [ONESEASON], dict(), seed=17, conv_variant="pre_normalised")
+    compare_all(got, refs)
+
+
+def test_25km_short_season(cuda):
+    mask = S.region_mask(dx=25000)
+    got, refs = run_both(mask, 6, 25000, [MULTISEASON], dict(atmlossInc=1), seed=18)
+    compare_all(got, refs)
+
+
+def test_step_day_matches_calc_budget(cuda):
+    """nesosim_step_day has calcBudget's in-place contract (NESOSIM.py:224-347)."""
+    from nesosim_b200.engine import SnowBudgetEngine
+    mask = S.region_mask(dx=100000)
+    T = 6
+    forcing = S.make_season(mask, T, seed=19)
+    ic = S.make_ic(mask, seed=19)
+    p = oracle_params(MULTISEASON)
+    fl = O.Flags(atmlossInc=1)
+    ref = O.run_season(forcing, ic, mask, 100000, p, fl)
+    eng = SnowBudgetEngine(mask, T, 100000, atmlossInc=1)
+    out = eng.alloc_outputs(zero=True)
+    half = O.initial_depths(ic, forcing["conc"][0], p)
+    out["snowDepths"][0, 0, 0] = cuda.from_numpy(half).cuda()
+    out["snowDepths"][0, 0, 1] = cuda.from_numpy(half).cuda()
+    for x in range(T - 1):
+        eng.step_day(x, forcing["conc"][x], forcing["precip"][x], forcing["drift"][x], forcing["wind"][x],
+                     [MULTISEASON], out)
+    for name, t in out.items():
+        assert_parity(t[0].cpu().numpy(), ref[name], name)
+
+
+def test_resume_in_two_halves(cuda):
+    """first_step/num_steps: running [0,k) then [k,T-1) equals one run."""
+    from nesosim_b200.engine import SnowBudgetEngine
+    mask = S.region_mask(dx=100000)
+    T = 14
+    forcing = S.make_season(mask, T, seed=20)
+    ic = S.make_ic(mask, seed=20)
+    eng = SnowBudgetEngine(mask, T, 100000)
+    eng.set_forcing(forcing["precip"], forcing["conc"], forcing["wind"], forcing["drift"])
+    a = eng.run_season([ONESEASON], ic)
+    b = eng.alloc_outputs()
+    eng.run_season([ONESEASON], ic, b, 0, 6)
+    eng.run_season([ONESEASON], ic, b, 6, -1)
+    for n in a:
+        assert cuda.equal(a[n].nan_to_num(nan=-7.0), b[n].nan_to_num(nan=-7.0)), n
+
+
+def test_outputs_subset_uses_internal_state(cuda):
+    """NULL outputs are carried in internal scratch; the requested ones are unchanged."""
+    from nesosim_b200.engine import SnowBudgetEngine
+    mask = S.region_mask(dx=100000)
+    T = 9
+    forcing = S.make_season(mask, T, seed=21)
+    ic = S.make_ic(mask, seed=21)
+    eng = SnowBudgetEngine(mask, T, 100000, n_members=2, atmlossInc=1)
+    eng.set_forcing(forcing["precip"], forcing["conc"], forcing["wind"], forcing["drift"])
+    params = S.ensemble_params(2, seed=2)
+    full = eng.run_season(params, ic)
+    part = eng.alloc_outputs(names=("snowDepths", "density"))
+    eng.run_season(params, ic, part)
+    for n in part:
+        assert cuda.equal(full[n].nan_to_num(nan=-7.0), part[n].nan_to_num(nan=-7.0)), n
+
+
+def test_host_path_end_to_end(cuda):
+    from nesosim_b200.engine import SnowBudgetEngine
+    mask = S.region_mask(dx=100000)
+    T = 10
+    forcing = S.make_season(mask, T, seed=22)
+    ic = S.make_ic(mask, seed=22)
+    params = S.ensemble_params(5, seed=3)
+    eng = SnowBudgetEngine(mask, T, 100000, n_members=5, atmlossInc=1)
+    import os
+    os.environ["NESOSIM_HOST_BATCH_GB"] = "0.02"       # force several member batches
+    try:
+        out, up, down = eng.run_season_host(forcing, params, ic)
+    finally:
+        del os.environ["NESOSIM_HOST_BATCH_GB"]
+    assert up >= 5 * T * mask.size * 8 and down == 12 * 5 * T * mask.size * 8
+    for m in range(5):
+        ref = O.run_season(forcing, ic, mask, 100000, oracle_params(params[m]), O.Flags(atmlossInc=1))
+        for name in out:
+            assert_parity(out[name][m], ref[name], name)
+
+
+# ------------------------------------------------------------------------------------ per-function KATs
+
+def test_smooth_plain_and_nan_branch(cuda):
+    from nesosim_b200 import engine as E
+    rng = np.random.default_rng(0)
+    g = gaussian2d_kernel()
+    a = rng.standard_normal((37, 53))
+    assert_parity(E.smooth(a), convolve_fill0(a, g), "plain")
+    b = a.copy()
+    b[5, 7] = np.nan                    # isolated NaN
+    b[20:24, 30:34] = np.nan            # block >= 3x3 -> bot == 0 -> NaN preserved in the middle
+    b[0, 0] = np.nan
+    b[-1, -1] = np.nan                  # corners / edges
+    b[0, 20] = np.nan
+    ref = convolve_fill0(b, g)
+    assert np.isnan(ref[21, 31]) and np.isfinite(ref[5, 7])
+    assert_parity(E.smooth(b), ref, "interpolate")
+    c = a.copy()
+    c[3, 3] = np.inf
+    c[9, 9] = -np.inf                   # +inf and -inf make arr.sum() NaN -> interpolate branch
+    assert_parity(E.smooth(c), convolve_fill0(c, g), "inf pair")
+    d = a.copy()
+    d[3, 3] = np.inf                    # a single inf keeps the plain branch
+    assert_parity(E.smooth(d), convolve_fill0(d, g), "single inf")
+    assert_parity(E.smooth(b, "pre_normalised"), convolve_fill0(b, g, "pre_normalised"), "pre-normalised")
+
+
+def test_op_dynamics(cuda):
+    from nesosim_b200 import engine as E
+    rng = np.random.default_rng(1)
+    ny, nx = 19, 45
+    h = np.abs(rng.standard_normal((2, ny, nx))) * 0.2
+    h[:, 4:7, 10:13] = np.nan
+    d = 0.1 * rng.standard_normal((2, ny, nx))
+    d[:, 12, :] = np.nan
+    d[0, 2, 2] = np.inf
+    for dx in (100000, 25000, 12345.678):
+        adv, div = E.op_dynamics(d, h, dx)
+        radv, rdiv = O.calc_dynamics(d, h, dx, O.Params())
+        assert_parity(adv, radv, "adv dx=%r" % dx)
+        assert_parity(div, rdiv, "div dx=%r" % dx)
+        assert np.isfinite(adv).all() and np.isfinite(div).all()
+
+
+def test_op_wind_terms(cuda):
+    from nesosim_b200 import engine as E
+    rng = np.random.default_rng(2)
+    n = 4096
+    h0 = np.abs(rng.standard_normal(n)) * 0.3
+    W = rng.gamma(4.0, 1.5, n)
+    C = rng.random(n)
+    W[:8] = 5.0                          # exactly the threshold: not packed
+    W[8:12] = np.nan                     # 0*NaN stays NaN (NESOSIM.py:69-71)
+    h0[12:16] = np.nan
+    W[16] = np.inf
+    h0[17] = 0.0
+    W[17] = np.inf                       # 0*inf = NaN
+    p = O.Params(windPackFactor=5.8e-7, windPackThresh=5., leadLossFactor=1.45e-7, atmLossFactor=2.2e-8)
+    lead, atm, wpl, wpg, wpn = E.op_wind_terms(h0, W, C, [MULTISEASON])
+    with np.errstate(all="ignore"):
+        rl, rg, rn = O.wind_packing(W, h0, p)
+        assert_parity(lead, O.lead_loss(h0, W, C, p), "lead")
+        assert_parity(atm, O.atm_loss(h0, W, p), "atm")
+    assert_parity(wpl, rl, "wpl")
+    assert_parity(wpg, rg, "wpg")
+    assert_parity(wpn, rn, "wpn")
+    assert np.isnan(lead[8]) and lead[0] == 0.0
+
+
+def test_op_fills_and_density(cuda):
+    from nesosim_b200 import engine as E
+    rng = np.random.default_rng(3)
+    n = 2000
+    a = rng.standard_normal(n)
+    a[::7] = np.nan
+    a[::11] = np.inf
+    a[::13] = -np.inf
+    a[5] = -0.0
+    mask = rng.integers(0, 13, n).astype(np.uint8)
+    z = a.copy()
+    O.fill_mask_nan_zero(z)
+    assert_parity(E.op_fill_zero(a), z, "fill zero")
+    for neg in (True, False):
+        r = a.copy()
+        O.fill_nan_no_negative(r, mask, negative_to_zero=neg)
+        assert_parity(E.op_fill_nan_no_negative(a, mask, neg), r, "fill nan %s" % neg)
+    h = np.abs(rng.standard_normal((2, n))) * 0.05
+    h[0, :50] = 0.0
+    h[1, :25] = 0.0                      # 0/0
+    h[0, 60:70] = 0.01
+    h[1, 60:70] = 0.01                   # sum straddles minSnowD
+    h[0, 70] = 0.02
+    h[1, 70] = 0.0
+    h[:, 80:90] = np.nan
+    assert_parity(E.op_density(h, mask), O.density_calc(h, None, mask, O.Params()), "density")
