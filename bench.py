@@ -277,6 +277,8 @@ def run_ours(args):
     # end to end through the host-buffer C-ABI call
     e2e = None
     try:
+        if args.no_e2e:
+            raise RuntimeError("skipped (--no-e2e)")
         e2e = run_e2e(args, eng, forcing, params, ic, rank, world, cells_per_step, barrier)
     except Exception as ex:   # keep the headline line even if the host path cannot allocate
         e2e = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
@@ -349,6 +351,7 @@ def main():
     ap.add_argument("--days", type=int, default=NUM_DAYS)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
