@@ -138,6 +138,12 @@ int nesosim_op_fill_nan_no_negative(double *arr_dev, const uint8_t *mask_dev, in
 int nesosim_op_density(const double *depths_dev, const uint8_t *mask_dev, int64_t n, double rhoFresh,
                        double rhoOld, double minSnowD, double *density_dev, void *stream);
 
+/* Diagnostics for the exact constant-division path used for /dx, /(2.*dx), /rho and /kernel.sum()
+ * (cell_math.cuh div_const): whether the 3-operation path was proven exact for divisor c, and a host
+ * replica of the device routine (same branches, std::fma) so CPU tests can compare it with x / c. */
+int    nesosim_const_div_is_fast(double c);
+double nesosim_const_div_eval_host(double x, double c);
+
 /* Number of kernel launches this context has issued since creation (bench.py reports it). */
 int64_t nesosim_launch_count(const nesosim_ctx *ctx);
 

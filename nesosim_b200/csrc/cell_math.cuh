@@ -16,24 +16,24 @@ __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 __device__ __forceinline__ bool finite(double x) { return fabs(x) <= 1.7976931348623157e308; }
 
-// x / c for a divisor that is fixed for the whole launch.  `rc` = RN(1/c) from the host.
+// x / c for a divisor that is fixed for the whole launch (c finite, non-zero, normal).  `rc` = RN(1/c) (host).
 // Fast path (Markstein / Brisebarre-Muller-Raina "division by a known constant"): q0 = RN(x*rc);
 // r = fma(-c, q0, x); q = RN(q0 + r*rc).  Before the last rounding the value is x/c*(1+eta), |eta| <= 3*2^-107
 // relative to the quotient's binade, so q is the correctly rounded quotient unless x/c lies that close to a
 // rounding midpoint.  The host only sets `fast` for divisors where that cannot happen (const_div_host() in
-// nesosim_abi.cu proves it per divisor); otherwise, and for operands outside the magnitude window (0, inf, NaN,
-// tiny, huge), the IEEE division instruction sequence is used.  Either way the result equals numpy's `x / c`.
+// nesosim_abi.cu proves it per divisor).  Zero, infinite and NaN dividends -- more than half of every plane is
+// NaN land -- are exactly x*rc (same sign rules as IEEE division by a finite non-zero constant) and never reach
+// the division subroutine; only finite dividends outside the magnitude window (or a divisor without the proof)
+// use the IEEE division sequence.  The result always equals numpy's `x / c`.
 struct ConstDiv {
     double c, rc;
     int fast;
 };
 __device__ __forceinline__ double div_const(double x, const ConstDiv &d) {
     const double ax = fabs(x);
-    if (d.fast && ax >= 1e-200 && ax <= 1e200) {   // the window is also false for NaN
-        const double q0 = __dmul_rn(x, d.rc);
-        const double r = __fma_rn(-d.c, q0, x);
-        return __fma_rn(r, d.rc, q0);
-    }
+    const double q0 = __dmul_rn(x, d.rc);
+    if (!(ax > 0.0 && ax <= 1.7976931348623157e308)) return q0;   // +-0, +-inf, NaN
+    if (d.fast && ax >= 1e-200 && ax <= 1e200) return __fma_rn(__fma_rn(-d.c, q0, x), d.rc, q0);
     return __ddiv_rn(x, d.c);
 }
 
@@ -43,10 +43,28 @@ struct GradConsts {
     ConstDiv dx, two_dx;
 };
 // `fm`, `fc`, `fp` are the values at index-1, index, index+1 (fm/fp ignored where they fall off the grid).
+// One subtraction and one division per call: the operands and the divisor are selected first.
 __device__ __forceinline__ double gradient1d(double fm, double fc, double fp, int idx, int n, const GradConsts &g) {
-    if (idx == 0) return div_const(sub(fp, fc), g.dx);
-    if (idx == n - 1) return div_const(sub(fc, fm), g.dx);
-    return div_const(sub(fp, fm), g.two_dx);
+    const bool first = (idx == 0), last = (idx == n - 1);
+    const double hi = last ? fc : fp;
+    const double lo = first ? fc : fm;
+    ConstDiv d;
+    d.c = (first || last) ? g.dx.c : g.two_dx.c;
+    d.rc = (first || last) ? g.dx.rc : g.two_dx.rc;
+    d.fast = g.dx.fast & g.two_dx.fast;
+    return div_const(sub(hi, lo), d);
+}
+
+// a / b for two variable operands with IEEE results, keeping NaN and zero operands (land, snow-free cells) off
+// the division subroutine's special-operand path.
+__device__ __forceinline__ double div_ieee(double a, double b) {
+    if (a != a || b != b) return qnan();
+    if (b == 0.0) {
+        if (a == 0.0) return qnan();
+        const bool neg = (__double2hiint(a) ^ __double2hiint(b)) < 0;
+        return __longlong_as_double(neg ? 0xfff0000000000000LL : 0x7ff0000000000000LL);
+    }
+    return __ddiv_rn(a, b);
 }
 
 // fillMaskAndNaNWithZero (NESOSIM.py:127-139): NaN -> 0, +-inf -> 0
@@ -104,7 +122,7 @@ __device__ __forceinline__ void wind_packing(double wt, double h0, const MemberC
 // densityCalc (NESOSIM.py:464-471) on the updated depths
 __device__ __forceinline__ double density_variable(double h0, double h1, bool land, const ModelConsts &k) {
     const double den = add(h0, h1);
-    double rho = __ddiv_rn(add(mul(h0, k.rhoFresh), mul(h1, k.rhoOld)), den);
+    double rho = div_ieee(add(mul(h0, k.rhoFresh), mul(h1, k.rhoOld)), den);
     if (rho > k.rhoOld) rho = k.rhoOld;
     if (rho < k.rhoFresh) rho = k.rhoFresh;
     if (land) rho = qnan();

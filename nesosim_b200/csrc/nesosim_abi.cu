@@ -500,6 +500,17 @@ int nesosim_op_density(const double *depths_dev, const uint8_t *mask_dev, int64_
 
 int64_t nesosim_launch_count(const nesosim_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int nesosim_const_div_is_fast(double c) { return const_div_host(c).fast; }
+
+double nesosim_const_div_eval_host(double x, double c) {
+    const ConstDiv d = const_div_host(c);
+    const double ax = std::fabs(x);
+    const double q0 = x * d.rc;
+    if (!(ax > 0.0 && ax <= 1.7976931348623157e308)) return q0;
+    if (d.fast && ax >= 1e-200 && ax <= 1e200) return std::fma(std::fma(-d.c, q0, x), d.rc, q0);
+    return x / d.c;
+}
+
 }  // extern "C"
 
 #include "host_path.inl"
