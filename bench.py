@@ -221,7 +221,10 @@ def run_ours(args):
     ic = S.make_ic(mask, seed=SEED)
     params = S.ensemble_params(M * world, seed=SEED)[rank * M:(rank + 1) * M]     # this rank's members
 
+    if args.variant:
+        os.environ["NESOSIM_ENS_VARIANT"] = args.variant
     eng = SnowBudgetEngine(mask, T, DX, n_members=M, atmlossInc=1, device=local)
+    eng.set_path(args.path)
     eng.set_forcing(forcing["precip"], forcing["conc"], forcing["wind"], forcing["drift"])
     out = eng.alloc_outputs()
     cells_per_step = M * ny * nx * (T - 1)
@@ -292,7 +295,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(M, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "config": workload_config(M, world, {"kernel_path": eng.last_path(), "variant": args.variant or "default"}), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     eng.close()
@@ -350,6 +353,8 @@ def main():
     ap.add_argument("--members", type=int, default=MEMBERS_PER_GPU)
     ap.add_argument("--days", type=int, default=NUM_DAYS)
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--path", default="auto", choices=["auto", "general", "ensemble"])
+    ap.add_argument("--variant", default="", help="season-resident kernel build variant (NESOSIM_ENS_VARIANT)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     args = ap.parse_args()

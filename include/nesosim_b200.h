@@ -138,6 +138,12 @@ int nesosim_op_fill_nan_no_negative(double *arr_dev, const uint8_t *mask_dev, in
 int nesosim_op_density(const double *depths_dev, const uint8_t *mask_dev, int64_t n, double rhoFresh,
                        double rhoOld, double minSnowD, double *density_dev, void *stream);
 
+/* Kernel path of nesosim_run_season: 0 = automatic (default), 1 = general per-day kernel (any grid),
+ * 2 = season-resident cluster kernel (grids up to 96x96, variable density, whole season; error otherwise).
+ * Both paths produce identical values.  nesosim_last_path reports which one the last season used. */
+int nesosim_set_path(nesosim_ctx *ctx, int path);
+int nesosim_last_path(const nesosim_ctx *ctx);
+
 /* Diagnostics for the exact constant-division path used for /dx, /(2.*dx), /rho and /kernel.sum()
  * (cell_math.cuh div_const): whether the 3-operation path was proven exact for divisor c, and a host
  * replica of the device routine (same branches, std::fma) so CPU tests can compare it with x / c. */

@@ -3,7 +3,9 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <new>
 #include <string>
 #include <vector>
@@ -152,6 +154,8 @@ struct nesosim_ctx {
     GradConsts g;
     ConstDiv conv_div, rho_fresh_div;
     EnsembleState ens;              // season-resident ensemble path (ensemble_kernel.cuh)
+    int path = 0;                   // 0 auto, 1 general per-day launches, 2 season-resident ensemble kernel
+    int last_path = 0;              // which path the last run_season used (1 or 2)
 };
 
 namespace {
@@ -289,6 +293,118 @@ int launch_init(nesosim_ctx *ctx, const double *ic, int ic_per_member, const dou
     return NESOSIM_OK;
 }
 
+
+// ------------------------------------------------------------------ season-resident ensemble path (host side)
+
+struct EnsVariant {
+    const char *name;
+    void (*kernel)(const EnsArgs);
+    size_t smem;
+    int threads;
+    int max_rows;   // rows one CTA can own
+};
+
+const EnsVariant *ens_variants(int *n) {
+    static const EnsVariant v[] = {
+        {"r6g4_psm", ensemble_season_kernel<6, 4, true>, EnsLayout<6, 4, true>::SMEM_BYTES, EnsLayout<6, 4, true>::NT, 24},
+        {"r6g4_reg", ensemble_season_kernel<6, 4, false>, EnsLayout<6, 4, false>::SMEM_BYTES, EnsLayout<6, 4, false>::NT, 24},
+        {"r4g6_psm", ensemble_season_kernel<4, 6, true>, EnsLayout<4, 6, true>::SMEM_BYTES, EnsLayout<4, 6, true>::NT, 24},
+        {"r5g5_reg", ensemble_season_kernel<5, 5, false>, EnsLayout<5, 5, false>::SMEM_BYTES, EnsLayout<5, 5, false>::NT, 25},
+        {"r3g8_psm", ensemble_season_kernel<3, 8, true>, EnsLayout<3, 8, true>::SMEM_BYTES, EnsLayout<3, 8, true>::NT, 24},
+    };
+    *n = (int)(sizeof(v) / sizeof(v[0]));
+    return v;
+}
+
+const EnsVariant *pick_variant() {
+    int n;
+    const EnsVariant *v = ens_variants(&n);
+    if (const char *e = getenv("NESOSIM_ENS_VARIANT"))
+        for (int i = 0; i < n; ++i)
+            if (!strcmp(e, v[i].name)) return &v[i];
+    return &v[0];
+}
+
+// The kernel keeps a whole member on one 4-CTA cluster: strips of ny/4 rows, rows of at most 96 columns.
+bool ensemble_eligible(const nesosim_ctx *ctx, int first_step, int num_steps, const char **why) {
+    const nesosim_config &c = ctx->cfg;
+    const EnsVariant *v = pick_variant();
+    if (c.nx > ENS_MAX_NX) { *why = "nx > 96"; return false; }
+    if ((c.ny + ENS_CLUSTER - 1) / ENS_CLUSTER > v->max_rows) { *why = "ny too large for one cluster"; return false; }
+    if (c.ny < 2 * ENS_CLUSTER) { *why = "ny < 8"; return false; }
+    if (c.density_clim) { *why = "densityType='clim'"; return false; }
+    if (first_step != 0 || num_steps != c.num_days - 1) { *why = "partial season"; return false; }
+    return true;
+}
+
+int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, const nesosim_outputs *out, int m0,
+                 int mcount, cudaStream_t st) {
+    const nesosim_config &c = ctx->cfg;
+    const long long plane = ctx->plane;
+    const int steps = c.num_days - 1;
+    EnsembleState &e = ctx->ens;
+    const size_t need = (size_t)steps * ND * plane;
+    if (e.derived_elems < need) {
+        cudaFree(e.derived);
+        e.derived = nullptr;
+        e.derived_elems = 0;
+        CU(cudaMalloc(&e.derived, need * sizeof(double)));
+        e.derived_elems = need;
+    }
+    // member-independent pre-pass: part of the season, recomputed on every call
+    DeriveArgs d;
+    d.ny = c.ny; d.nx = c.nx; d.steps = steps;
+    d.P = ctx->P; d.C = ctx->C; d.UV = ctx->UV; d.rho_clim = nullptr;
+    d.D = e.derived;
+    d.k = ctx->k; d.g = ctx->g; d.rho_new = ctx->rho_fresh_div;
+    dim3 blk(32, 8), grid((c.nx + 31) / 32, (c.ny + 7) / 8, steps);
+    derive_pointwise_kernel<<<grid, blk, 0, st>>>(d);
+    derive_scan_kernel<<<(unsigned)((plane + 127) / 128), 128, 0, st>>>(e.derived, plane, steps);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+
+    const EnsVariant *v = pick_variant();
+    CU(cudaFuncSetAttribute((const void *)v->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem));
+    int max_clusters = 0;
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(ENS_CLUSTER * 64);
+        cfg.blockDim = dim3(v->threads);
+        cfg.dynamicSmemBytes = v->smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = ENS_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CU(cudaOccupancyMaxActiveClusters(&max_clusters, (const void *)v->kernel, &cfg));
+    }
+    if (max_clusters < 1) return fail(NESOSIM_ERR_CUDA, "no 4-CTA cluster fits on this device");
+    if (const char *envc = getenv("NESOSIM_ENS_CLUSTERS")) max_clusters = std::max(1, std::min(max_clusters, atoi(envc)));
+    e.max_clusters = max_clusters;
+    const int ncl = std::min(max_clusters, mcount);
+
+    EnsArgs a;
+    a.ny = c.ny; a.nx = c.nx; a.T = c.num_days; a.M = mcount;
+    a.D = e.derived;
+    a.W = ctx->W;
+    a.mask = ctx->mask_dev;
+    a.ic = (ic_dev && ic_per_member) ? ic_dev + (long long)m0 * plane : ic_dev;
+    a.ic_stride = ic_per_member ? plane : 0;
+    a.conc0 = ctx->C;
+    for (int vv = 0; vv < NVAR; ++vv) {
+        double *base = out_base(out, vv);
+        a.out[vv] = base ? base + (vv == V_H1 ? plane : 0) : nullptr;
+        a.mstride[vv] = (vv == V_H0 || vv == V_H1) ? out->depth_member_stride : out->plane_member_stride;
+    }
+    a.coef = ctx->coef_dev + m0;
+    a.k = ctx->k; a.g = ctx->g; a.conv_div = ctx->conv_div;
+    std::memcpy(a.w, c.conv_weights, sizeof(a.w));
+    a.sw = Switches{c.dynamicsInc == 1, c.leadlossInc == 1, c.windpackInc == 1, c.atmlossInc == 1, 0};
+    v->kernel<<<ncl * ENS_CLUSTER, v->threads, v->smem, st>>>(a);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return NESOSIM_OK;
+}
+
 // Steps first_step .. first_step+num_steps-1 for members [m0, m0+mcount); `out` addresses member m0.
 int run_members(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, const nesosim_outputs *out, int m0,
                 int mcount, int first_step, int num_steps, cudaStream_t st) {
@@ -296,6 +412,15 @@ int run_members(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, const
     if (num_steps < 0) num_steps = T - 1 - first_step;
     if (first_step < 0 || first_step + num_steps > T - 1) return fail(NESOSIM_ERR_ARG, "step range outside the season");
     int rc;
+    const char *why = "";
+    const bool can_ens = ensemble_eligible(ctx, first_step, num_steps, &why);
+    if (ctx->path == 2 && !can_ens)
+        return fail(NESOSIM_ERR_ARG, std::string("season-resident ensemble path not applicable: ") + why);
+    if (ctx->path != 1 && can_ens) {
+        ctx->last_path = 2;
+        return run_ensemble(ctx, ic_dev, ic_per_member, out, m0, mcount, st);
+    }
+    ctx->last_path = 1;
     if (any_missing(out) && (rc = ensure_scratch(ctx))) return rc;
     if (first_step == 0 && (rc = launch_init(ctx, ic_dev, ic_per_member, ctx->C, out, m0, mcount, st))) return rc;
     const long long plane = ctx->plane;
@@ -499,6 +624,14 @@ int nesosim_op_density(const double *depths_dev, const uint8_t *mask_dev, int64_
 }
 
 int64_t nesosim_launch_count(const nesosim_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int nesosim_set_path(nesosim_ctx *ctx, int path) {
+    if (!ctx || path < 0 || path > 2) return fail(NESOSIM_ERR_ARG, "path must be 0 (auto), 1 (per-day kernel) or 2 (season-resident)");
+    ctx->path = path;
+    return NESOSIM_OK;
+}
+
+int nesosim_last_path(const nesosim_ctx *ctx) { return ctx ? ctx->last_path : 0; }
 
 int nesosim_const_div_is_fast(double c) { return const_div_host(c).fast; }
 

@@ -177,6 +177,18 @@ class SnowBudgetEngine:
     def launch_count(self):
         return int(self.lib.nesosim_launch_count(self.handle))
 
+    PATHS = {"auto": 0, "general": 1, "ensemble": 2}
+
+    def set_path(self, path):
+        """'auto' | 'general' (per-day kernel) | 'ensemble' (season-resident cluster kernel)."""
+        _lib.check(self.lib.nesosim_set_path(self.handle, self.PATHS[path]))
+
+    def last_path(self):
+        return {0: None, 1: "general", 2: "ensemble"}[int(self.lib.nesosim_last_path(self.handle))]
+
+    def dominant_kernel(self):
+        return {"general": "day_step_kernel", "ensemble": "ensemble_season_kernel"}.get(self.last_path(), "?")
+
     # -------------------------------------------------------------------------------------------- host API
     def run_season_host(self, forcing, params, ic=None, outputs=None, names=_lib.OUTPUT_NAMES):
         """End-to-end call on HOST numpy arrays (H2D + season + D2H inside).  Returns (outputs, h2d, d2h)."""

@@ -29,15 +29,21 @@ def oracle_params(row, **kw):
     return O.Params(windPackFactor=row[0], windPackThresh=row[1], leadLossFactor=row[2], atmLossFactor=row[3], **kw)
 
 
-def run_both(mask, T, dx, params, flags, seed=0, rho_clim=None, ic_scale=1.0, conv_variant="post_divide"):
+PATHS = ["general", "ensemble"]
+
+
+def run_both(mask, T, dx, params, flags, seed=0, rho_clim=None, ic_scale=1.0, conv_variant="post_divide",
+             path="auto", expect_path=None):
     from nesosim_b200.engine import SnowBudgetEngine
     forcing = S.make_season(mask, T, seed=seed)
     ic = S.make_ic(mask, seed=seed) * ic_scale
     params = np.asarray(params, dtype=float).reshape(-1, 4)
     eng = SnowBudgetEngine(mask, T, dx, n_members=len(params), conv_variant=conv_variant, **flags)
+    eng.set_path(path)
     eng.set_forcing(forcing["precip"], forcing["conc"], forcing["wind"], forcing["drift"], rho_clim)
     out = eng.run_season(params, ic)
     got = {k: v.cpu().numpy() for k, v in out.items()}
+    assert eng.last_path() == (expect_path or (path if path != "auto" else eng.last_path()))
     eng.close()
     refs = []
     fl = O.Flags(dynamicsInc=flags.get("dynamicsInc", 1), leadlossInc=flags.get("leadlossInc", 1),
@@ -58,28 +64,31 @@ ONESEASON = [5.8e-7, 5., 2.9e-7, 2.2e-8]      # run_oneseason.py:40-48
 MULTISEASON = [5.8e-7, 5., 1.45e-7, 2.2e-8]   # run_multiseason.py:42-50
 
 
-def test_season_100km_oneseason_params(cuda):
+@pytest.mark.parametrize("path", PATHS)
+def test_season_100km_oneseason_params(cuda, path):
     mask = S.region_mask(dx=100000)
-    got, refs = run_both(mask, 62, 100000, [ONESEASON], dict(atmlossInc=0), seed=11)
+    got, refs = run_both(mask, 62, 100000, [ONESEASON], dict(atmlossInc=0), seed=11, path=path)
     compare_all(got, refs)
     h = got["snowDepths"][0]
     assert np.isfinite(h).sum() > 1000 and np.nanmax(h) > 0.01      # the comparison is not vacuous
 
 
-def test_season_100km_multiseason_params_ensemble(cuda):
+@pytest.mark.parametrize("path", PATHS)
+def test_season_100km_multiseason_params_ensemble(cuda, path):
     mask = S.region_mask(dx=100000)
     params = np.vstack([MULTISEASON, S.ensemble_params(4, seed=5)])
-    got, refs = run_both(mask, 40, 100000, params, dict(atmlossInc=1), seed=12)
+    got, refs = run_both(mask, 40, 100000, params, dict(atmlossInc=1), seed=12, path=path)
     compare_all(got, refs)
     # members really differ
     assert not np.array_equal(got["snowDepths"][1], got["snowDepths"][2], equal_nan=True)
 
 
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("flags", [dict(dynamicsInc=0), dict(leadlossInc=0, atmlossInc=1), dict(windpackInc=0),
                                    dict(dynamicsInc=0, leadlossInc=0, windpackInc=0, atmlossInc=0)])
-def test_switches(cuda, flags):
+def test_switches(cuda, flags, path):
     mask = S.region_mask(dx=100000)
-    got, refs = run_both(mask, 12, 100000, [MULTISEASON], flags, seed=13)
+    got, refs = run_both(mask, 12, 100000, [MULTISEASON], flags, seed=13, path=path)
     compare_all(got, refs)
 
 
@@ -87,32 +96,59 @@ def test_clim_density(cuda):
     mask = S.region_mask(dx=100000)
     T = 15
     rho = 1000 * (0.29 + 0.0003 * np.arange(T))      # shape of W99_density.csv values (utils.py:1336-1343)
-    got, refs = run_both(mask, T, 100000, [ONESEASON], dict(densityType="clim"), seed=14, rho_clim=rho)
+    got, refs = run_both(mask, T, 100000, [ONESEASON], dict(densityType="clim"), seed=14, rho_clim=rho,
+                         expect_path="general")     # the season-resident kernel is variable-density only
     compare_all(got, refs)
 
 
-def test_ragged_grid_not_multiple_of_tile(cuda):
-    mask = S.region_mask(shape=(45, 70), kind="disc")
-    got, refs = run_both(mask, 10, 50000, [MULTISEASON, ONESEASON], dict(atmlossInc=1), seed=15, ic_scale=3.0)
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("shape", [(45, 70), (9, 96), (95, 33)])
+def test_ragged_grid_not_multiple_of_tile(cuda, path, shape):
+    mask = S.region_mask(shape=shape, kind="disc")
+    got, refs = run_both(mask, 10, 50000, [MULTISEASON, ONESEASON], dict(atmlossInc=1), seed=15, ic_scale=3.0,
+                         path=path)
     compare_all(got, refs)
 
 
 def test_minimum_grid_2x2(cuda):
     mask = np.full((2, 2), 8, dtype=np.uint8)
-    got, refs = run_both(mask, 5, 100000, [MULTISEASON], dict(atmlossInc=1), seed=16)
+    got, refs = run_both(mask, 5, 100000, [MULTISEASON], dict(atmlossInc=1), seed=16, expect_path="general")
     compare_all(got, refs)
 
 
-def test_prenormalised_kernel_variant(cuda):
+@pytest.mark.parametrize("path", PATHS)
+def test_prenormalised_kernel_variant(cuda, path):
     mask = S.region_mask(dx=100000)
-    got, refs = run_both(mask, 8, 100000, [ONESEASON], dict(), seed=17, conv_variant="pre_normalised")
+    got, refs = run_both(mask, 8, 100000, [ONESEASON], dict(), seed=17, conv_variant="pre_normalised", path=path)
     compare_all(got, refs)
 
 
 def test_25km_short_season(cuda):
     mask = S.region_mask(dx=25000)
-    got, refs = run_both(mask, 6, 25000, [MULTISEASON], dict(atmlossInc=1), seed=18)
+    got, refs = run_both(mask, 6, 25000, [MULTISEASON], dict(atmlossInc=1), seed=18, expect_path="general")
     compare_all(got, refs)
+
+
+@pytest.mark.parametrize("variant", ["r6g4_psm", "r6g4_reg", "r4g6_psm", "r5g5_reg", "r3g8_psm"])
+def test_ensemble_kernel_variants_many_members_per_cluster(cuda, variant, monkeypatch):
+    """Every build variant of the season-resident kernel; 3 clusters share 11 members with per-member ICs."""
+    from nesosim_b200.engine import SnowBudgetEngine
+    monkeypatch.setenv("NESOSIM_ENS_VARIANT", variant)
+    monkeypatch.setenv("NESOSIM_ENS_CLUSTERS", "3")
+    mask = S.region_mask(dx=100000)
+    T, M = 9, 11
+    forcing = S.make_season(mask, T, seed=23)
+    rng = np.random.default_rng(23)
+    ic = S.make_ic(mask, seed=23)[None] * rng.uniform(0.5, 3.0, (M, 1, 1))
+    params = S.ensemble_params(M, seed=23)
+    eng = SnowBudgetEngine(mask, T, 100000, n_members=M, atmlossInc=1)
+    eng.set_path("ensemble")
+    eng.set_forcing(forcing["precip"], forcing["conc"], forcing["wind"], forcing["drift"])
+    out = {k: v.cpu().numpy() for k, v in eng.run_season(params, ic).items()}
+    for m in range(M):
+        ref = O.run_season(forcing, ic[m], mask, 100000, oracle_params(params[m]), O.Flags(atmlossInc=1))
+        for name in out:
+            assert_parity(out[name][m], ref[name], "%s[%d] %s" % (name, m, variant))
 
 
 def test_step_day_matches_calc_budget(cuda):
