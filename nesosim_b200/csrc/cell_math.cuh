@@ -14,7 +14,9 @@ __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, 
 __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
-__device__ __forceinline__ bool finite(double x) { return fabs(x) <= 1.7976931348623157e308; }
+// exponent-field tests run on the integer pipe, leaving the fp64 pipe to the arithmetic
+__device__ __forceinline__ unsigned biased_exp(double x) { return ((unsigned)__double2hiint(x) >> 20) & 0x7ffu; }
+__device__ __forceinline__ bool finite(double x) { return biased_exp(x) != 0x7ffu; }
 
 // x / c for a divisor that is fixed for the whole launch (c finite, non-zero, normal).  `rc` = RN(1/c) (host).
 // Fast path (Markstein / Brisebarre-Muller-Raina "division by a known constant"): q0 = RN(x*rc);
@@ -24,16 +26,17 @@ __device__ __forceinline__ bool finite(double x) { return fabs(x) <= 1.797693134
 // nesosim_abi.cu proves it per divisor).  Zero, infinite and NaN dividends -- more than half of every plane is
 // NaN land -- are exactly x*rc (same sign rules as IEEE division by a finite non-zero constant) and never reach
 // the division subroutine; only finite dividends outside the magnitude window (or a divisor without the proof)
-// use the IEEE division sequence.  The result always equals numpy's `x / c`.
+// (outside 2^-623..2^624) use the IEEE division sequence.  The result always equals numpy's `x / c`.
 struct ConstDiv {
     double c, rc;
     int fast;
 };
 __device__ __forceinline__ double div_const(double x, const ConstDiv &d) {
-    const double ax = fabs(x);
+    const unsigned e = biased_exp(x);
     const double q0 = __dmul_rn(x, d.rc);
-    if (!(ax > 0.0 && ax <= 1.7976931348623157e308)) return q0;   // +-0, +-inf, NaN
-    if (d.fast && ax >= 1e-200 && ax <= 1e200) return __fma_rn(__fma_rn(-d.c, q0, x), d.rc, q0);
+    if (d.fast && (e - 400u) <= 1246u)           // 2^-623 <= |x| < 2^624: x, q0 and the residual are normal
+        return __fma_rn(__fma_rn(-d.c, q0, x), d.rc, q0);
+    if (e == 0x7ffu || x == 0.0) return q0;      // +-inf, NaN, +-0
     return __ddiv_rn(x, d.c);
 }
 

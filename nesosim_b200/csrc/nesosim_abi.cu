@@ -143,6 +143,7 @@ struct nesosim_ctx {
     nesosim_config cfg;
     long long plane;
     uint8_t *mask_dev = nullptr;
+    std::vector<uint8_t> mask_host;
     MemberCoef *coef_dev = nullptr;
     const double *P = nullptr, *C = nullptr, *W = nullptr, *UV = nullptr, *rho_clim = nullptr;
     std::vector<double> rho_clim_host;
@@ -298,42 +299,113 @@ int launch_init(nesosim_ctx *ctx, const double *ic, int ic_per_member, const dou
 
 struct EnsVariant {
     const char *name;
-    void (*kernel)(const EnsArgs);
-    size_t smem;
-    int threads;
-    int max_rows;   // rows one CTA can own
+    int ko;
+    void (*kernel_all)(const EnsArgs);    // all twelve outputs requested
+    void (*kernel_some)(const EnsArgs);   // NULL outputs are skipped
 };
 
 const EnsVariant *ens_variants(int *n) {
     static const EnsVariant v[] = {
-        {"r6g4_psm", ensemble_season_kernel<6, 4, true>, EnsLayout<6, 4, true>::SMEM_BYTES, EnsLayout<6, 4, true>::NT, 24},
-        {"r6g4_reg", ensemble_season_kernel<6, 4, false>, EnsLayout<6, 4, false>::SMEM_BYTES, EnsLayout<6, 4, false>::NT, 24},
-        {"r4g6_psm", ensemble_season_kernel<4, 6, true>, EnsLayout<4, 6, true>::SMEM_BYTES, EnsLayout<4, 6, true>::NT, 24},
-        {"r5g5_reg", ensemble_season_kernel<5, 5, false>, EnsLayout<5, 5, false>::SMEM_BYTES, EnsLayout<5, 5, false>::NT, 25},
-        {"r3g8_psm", ensemble_season_kernel<3, 8, true>, EnsLayout<3, 8, true>::SMEM_BYTES, EnsLayout<3, 8, true>::NT, 24},
+        {"ko2", 2, ensemble_season_kernel<2, true>, ensemble_season_kernel<2, false>},
+        {"ko3", 3, ensemble_season_kernel<3, true>, ensemble_season_kernel<3, false>},
+        {"ko5", 5, ensemble_season_kernel<5, true>, ensemble_season_kernel<5, false>},
     };
     *n = (int)(sizeof(v) / sizeof(v[0]));
     return v;
 }
 
-const EnsVariant *pick_variant() {
-    int n;
-    const EnsVariant *v = ens_variants(&n);
-    if (const char *e = getenv("NESOSIM_ENS_VARIANT"))
-        for (int i = 0; i < n; ++i)
-            if (!strcmp(e, v[i].name)) return &v[i];
-    return &v[0];
+// Cut the grid into ENS_CLUSTER row strips with balanced work (ocean cells dominate; land cells and rows carry a
+// small cost) and compile the mask into the per-strip cell lists the kernel walks.
+int build_strip_tables(nesosim_ctx *ctx) {
+    EnsembleState &e = ctx->ens;
+    if (e.tables_ready) return NESOSIM_OK;
+    const int ny = ctx->cfg.ny, nx = ctx->cfg.nx;
+    const std::vector<uint8_t> &mask = ctx->mask_host;
+    auto land = [&](int r, int c) { const uint8_t m = mask[(size_t)r * nx + c]; return m > 10 || m < 1; };
+    std::vector<double> cum(ny + 1, 0.0);
+    for (int r = 0; r < ny; ++r) {
+        int oc = 0;
+        for (int c = 0; c < nx; ++c) oc += !land(r, c);
+        cum[r + 1] = cum[r] + oc * 1.0 + (nx - oc) * 0.12 + 0.05 * nx;
+    }
+    int best[3] = {0, 0, 0};
+    double best_cost = 1e300;
+    const int minr = 2;
+    for (int b1 = minr; b1 <= ny - 3 * minr; ++b1) {
+        if (b1 > ENS_MAXR) break;
+        for (int b2 = b1 + minr; b2 <= ny - 2 * minr; ++b2) {
+            if (b2 - b1 > ENS_MAXR) break;
+            for (int b3 = b2 + minr; b3 <= ny - minr; ++b3) {
+                if (b3 - b2 > ENS_MAXR) break;
+                if (ny - b3 > ENS_MAXR) continue;
+                const double c0 = cum[b1], c1 = cum[b2] - cum[b1], c2 = cum[b3] - cum[b2], c3 = cum[ny] - cum[b3];
+                const double mx = std::max(std::max(c0, c1), std::max(c2, c3));
+                if (mx < best_cost) { best_cost = mx; best[0] = b1; best[1] = b2; best[2] = b3; }
+            }
+        }
+    }
+    if (best_cost >= 1e300) return fail(NESOSIM_ERR_ARG, "grid cannot be cut into 4 strips of 2..28 rows");
+    StripTables &t = e.tables;
+    t.row0[0] = 0; t.row0[1] = best[0]; t.row0[2] = best[1]; t.row0[3] = best[2]; t.row0[4] = ny;
+    std::vector<unsigned short> codes;
+    int max_ocean = 0;
+    for (int k = 0; k < ENS_CLUSTER; ++k) {
+        const int ra = t.row0[k], rb = t.row0[k + 1];
+        std::vector<unsigned short> ri, re, oc, la;
+        for (int r = std::max(ra - 1, 0); r <= std::min(rb, ny - 1); ++r)
+            for (int c = 0; c < nx; ++c) {
+                bool needed = false;   // some ocean cell of this strip has (r,c) in its 3x3 neighbourhood
+                for (int rr = std::max(r - 1, ra); rr <= std::min(r + 1, rb - 1) && !needed; ++rr)
+                    for (int cc = std::max(c - 1, 0); cc <= std::min(c + 1, nx - 1); ++cc)
+                        if (!land(rr, cc)) { needed = true; break; }
+                if (!needed) continue;
+                const bool edge = (r == 0 || r == ny - 1 || c == 0 || c == nx - 1);
+                (edge ? re : ri).push_back((unsigned short)(r * 128 + c));
+            }
+        for (int r = ra; r < rb; ++r)
+            for (int c = 0; c < nx; ++c) (land(r, c) ? la : oc).push_back((unsigned short)((r - ra) * 128 + c));
+        auto append = [&](const std::vector<unsigned short> &v, int &off, int &n) {
+            while (codes.size() % 8) codes.push_back(0);
+            off = (int)codes.size();
+            n = (int)v.size();
+            codes.insert(codes.end(), v.begin(), v.end());
+        };
+        append(ri, t.raw_int_off[k], t.raw_int_n[k]);
+        append(re, t.raw_edge_off[k], t.raw_edge_n[k]);
+        append(oc, t.ocean_off[k], t.ocean_n[k]);
+        append(la, t.land_off[k], t.land_n[k]);
+        max_ocean = std::max(max_ocean, (int)oc.size());
+    }
+    codes.push_back(0);
+    CU(cudaMalloc(&e.codes_dev, codes.size() * sizeof(unsigned short)));
+    CU(cudaMemcpy(e.codes_dev, codes.data(), codes.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    t.codes = e.codes_dev;
+    e.ko_needed = std::max(1, (max_ocean + ENS_NT - 1) / ENS_NT);
+    e.tables_ready = true;
+    return NESOSIM_OK;
 }
 
-// The kernel keeps a whole member on one 4-CTA cluster: strips of ny/4 rows, rows of at most 96 columns.
-bool ensemble_eligible(const nesosim_ctx *ctx, int first_step, int num_steps, const char **why) {
+const EnsVariant *pick_variant(int ko_needed) {
+    int n;
+    const EnsVariant *v = ens_variants(&n);
+    if (const char *env = getenv("NESOSIM_ENS_VARIANT"))
+        for (int i = 0; i < n; ++i)
+            if (!strcmp(env, v[i].name) && v[i].ko >= ko_needed) return &v[i];
+    for (int i = 0; i < n; ++i)
+        if (v[i].ko >= ko_needed) return &v[i];
+    return nullptr;
+}
+
+// The kernel keeps a whole member on one 4-CTA cluster: strips of up to 28 rows, rows of at most 96 columns.
+bool ensemble_eligible(nesosim_ctx *ctx, int first_step, int num_steps, const char **why) {
     const nesosim_config &c = ctx->cfg;
-    const EnsVariant *v = pick_variant();
     if (c.nx > ENS_MAX_NX) { *why = "nx > 96"; return false; }
-    if ((c.ny + ENS_CLUSTER - 1) / ENS_CLUSTER > v->max_rows) { *why = "ny too large for one cluster"; return false; }
+    if (c.ny > ENS_CLUSTER * ENS_MAXR) { *why = "ny > 112"; return false; }
     if (c.ny < 2 * ENS_CLUSTER) { *why = "ny < 8"; return false; }
     if (c.density_clim) { *why = "densityType='clim'"; return false; }
     if (first_step != 0 || num_steps != c.num_days - 1) { *why = "partial season"; return false; }
+    if (build_strip_tables(ctx) != NESOSIM_OK) { *why = "strip tables"; return false; }
+    if (!pick_variant(ctx->ens.ko_needed)) { *why = "too many ocean cells per strip"; return false; }
     return true;
 }
 
@@ -343,39 +415,44 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     const long long plane = ctx->plane;
     const int steps = c.num_days - 1;
     EnsembleState &e = ctx->ens;
-    const size_t need = (size_t)steps * ND * plane;
-    if (e.derived_elems < need) {
+    const size_t cells = (size_t)steps * plane;
+    const size_t need = cells * (2 + 1 + 1) * sizeof(double2);
+    if (e.derived_bytes < need) {
         cudaFree(e.derived);
         e.derived = nullptr;
-        e.derived_elems = 0;
-        CU(cudaMalloc(&e.derived, need * sizeof(double)));
-        e.derived_elems = need;
+        e.derived_bytes = 0;
+        CU(cudaMalloc(&e.derived, need));
+        e.derived_bytes = need;
     }
+    double2 *DA = (double2 *)e.derived, *DB = DA + 2 * cells, *DC = DB + cells;
     // member-independent pre-pass: part of the season, recomputed on every call
     DeriveArgs d;
     d.ny = c.ny; d.nx = c.nx; d.steps = steps;
-    d.P = ctx->P; d.C = ctx->C; d.UV = ctx->UV; d.rho_clim = nullptr;
-    d.D = e.derived;
+    d.P = ctx->P; d.C = ctx->C; d.UV = ctx->UV;
+    d.DA = DA; d.DB = DB; d.DC = DC;
     d.k = ctx->k; d.g = ctx->g; d.rho_new = ctx->rho_fresh_div;
     dim3 blk(32, 8), grid((c.nx + 31) / 32, (c.ny + 7) / 8, steps);
     derive_pointwise_kernel<<<grid, blk, 0, st>>>(d);
-    derive_scan_kernel<<<(unsigned)((plane + 127) / 128), 128, 0, st>>>(e.derived, plane, steps);
+    derive_scan_kernel<<<(unsigned)((plane + 63) / 64), 64, 0, st>>>(DB, DC, plane, steps);
     ctx->launches += 2;
     CU(cudaGetLastError());
 
-    const EnsVariant *v = pick_variant();
-    CU(cudaFuncSetAttribute((const void *)v->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem));
+    const EnsVariant *v = pick_variant(e.ko_needed);
+    bool all = true;
+    for (int vv = 0; vv < NVAR; ++vv) all = all && (out_base(out, vv) != nullptr);
+    void (*kernel)(const EnsArgs) = all ? v->kernel_all : v->kernel_some;
+    CU(cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENS_SMEM_BYTES));
     int max_clusters = 0;
     {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(ENS_CLUSTER * 64);
-        cfg.blockDim = dim3(v->threads);
-        cfg.dynamicSmemBytes = v->smem;
+        cfg.blockDim = dim3(ENS_NT);
+        cfg.dynamicSmemBytes = ENS_SMEM_BYTES;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = ENS_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        CU(cudaOccupancyMaxActiveClusters(&max_clusters, (const void *)v->kernel, &cfg));
+        CU(cudaOccupancyMaxActiveClusters(&max_clusters, (const void *)kernel, &cfg));
     }
     if (max_clusters < 1) return fail(NESOSIM_ERR_CUDA, "no 4-CTA cluster fits on this device");
     if (const char *envc = getenv("NESOSIM_ENS_CLUSTERS")) max_clusters = std::max(1, std::min(max_clusters, atoi(envc)));
@@ -384,9 +461,8 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
 
     EnsArgs a;
     a.ny = c.ny; a.nx = c.nx; a.T = c.num_days; a.M = mcount;
-    a.D = e.derived;
+    a.DA = DA; a.DB = DB; a.DC = DC;
     a.W = ctx->W;
-    a.mask = ctx->mask_dev;
     a.ic = (ic_dev && ic_per_member) ? ic_dev + (long long)m0 * plane : ic_dev;
     a.ic_stride = ic_per_member ? plane : 0;
     a.conc0 = ctx->C;
@@ -399,7 +475,8 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     a.k = ctx->k; a.g = ctx->g; a.conv_div = ctx->conv_div;
     std::memcpy(a.w, c.conv_weights, sizeof(a.w));
     a.sw = Switches{c.dynamicsInc == 1, c.leadlossInc == 1, c.windpackInc == 1, c.atmlossInc == 1, 0};
-    v->kernel<<<ncl * ENS_CLUSTER, v->threads, v->smem, st>>>(a);
+    a.st = e.tables;
+    kernel<<<ncl * ENS_CLUSTER, ENS_NT, ENS_SMEM_BYTES, st>>>(a);
     ctx->launches++;
     CU(cudaGetLastError());
     return NESOSIM_OK;
@@ -464,6 +541,7 @@ int nesosim_create(const nesosim_config *cfg, const uint8_t *region_mask_host, n
     if (!ctx) return fail(NESOSIM_ERR_NOMEM, "out of host memory");
     ctx->cfg = *cfg;
     ctx->plane = (long long)cfg->ny * cfg->nx;
+    ctx->mask_host.assign(region_mask_host, region_mask_host + (size_t)cfg->ny * cfg->nx);
     ctx->k = ModelConsts{cfg->deltaT, cfg->snowDensityFresh, cfg->snowDensityOld,
                          cfg->snowDensityFresh / cfg->snowDensityOld, cfg->minSnowD, cfg->minConc};
     ctx->g.dx = const_div_host(cfg->dx);
@@ -637,10 +715,12 @@ int nesosim_const_div_is_fast(double c) { return const_div_host(c).fast; }
 
 double nesosim_const_div_eval_host(double x, double c) {
     const ConstDiv d = const_div_host(c);
-    const double ax = std::fabs(x);
+    unsigned long long bits;
+    std::memcpy(&bits, &x, 8);
+    const unsigned e = (unsigned)(bits >> 52) & 0x7ffu;
     const double q0 = x * d.rc;
-    if (!(ax > 0.0 && ax <= 1.7976931348623157e308)) return q0;
-    if (d.fast && ax >= 1e-200 && ax <= 1e200) return std::fma(std::fma(-d.c, q0, x), d.rc, q0);
+    if (d.fast && (e - 400u) <= 1246u) return std::fma(std::fma(-d.c, q0, x), d.rc, q0);
+    if (e == 0x7ffu || x == 0.0) return q0;
     return x / d.c;
 }
 

@@ -129,7 +129,7 @@ def test_25km_short_season(cuda):
     compare_all(got, refs)
 
 
-@pytest.mark.parametrize("variant", ["r6g4_psm", "r6g4_reg", "r4g6_psm", "r5g5_reg", "r3g8_psm"])
+@pytest.mark.parametrize("variant", ["ko2", "ko3", "ko5"])
 def test_ensemble_kernel_variants_many_members_per_cluster(cuda, variant, monkeypatch):
     """Every build variant of the season-resident kernel; 3 clusters share 11 members with per-member ICs."""
     from nesosim_b200.engine import SnowBudgetEngine
