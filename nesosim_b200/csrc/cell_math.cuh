@@ -31,13 +31,17 @@ struct ConstDiv {
     double c, rc;
     int fast;
 };
+// The IEEE division sequence is kept behind a real call: inlined, the compiler predicates it and every warp
+// that holds a NaN or zero lane (every warp near land) would run the division subroutine's special-operand path.
+__device__ __noinline__ double div_generic(double a, double b) { return __ddiv_rn(a, b); }
+
 __device__ __forceinline__ double div_const(double x, const ConstDiv &d) {
     const unsigned e = biased_exp(x);
     const double q0 = __dmul_rn(x, d.rc);
     if (d.fast && (e - 400u) <= 1246u)           // 2^-623 <= |x| < 2^624: x, q0 and the residual are normal
         return __fma_rn(__fma_rn(-d.c, q0, x), d.rc, q0);
-    if (e == 0x7ffu || x == 0.0) return q0;      // +-inf, NaN, +-0
-    return __ddiv_rn(x, d.c);
+    if (e == 0x7ffu || (e == 0u && ((__double2hiint(x) & 0x000fffff) | __double2loint(x)) == 0)) return q0;   // inf, NaN, +-0
+    return div_generic(x, d.c);
 }
 
 // np.gradient(f, dx, axis) with edge_order=1 and uniform spacing (numpy; call sites NESOSIM.py:204-211):
@@ -58,16 +62,21 @@ __device__ __forceinline__ double gradient1d(double fm, double fc, double fp, in
     return div_const(sub(hi, lo), d);
 }
 
-// a / b for two variable operands with IEEE results, keeping NaN and zero operands (land, snow-free cells) off
-// the division subroutine's special-operand path.
+// a / b for two variable operands with IEEE results.  Lanes whose operands are not both normal numbers (NaN
+// land, 0/0 on snow-free cells, ...) never reach the division sequence: the common special cases are written out
+// and the sequence itself runs on substituted normal operands, so its special-operand subroutine is never called.
 __device__ __forceinline__ double div_ieee(double a, double b) {
+    const unsigned ea = biased_exp(a), eb = biased_exp(b);
+    const bool normal = (ea - 1u) <= 0x7fdu && (eb - 1u) <= 0x7fdu;
+    const double q = __ddiv_rn(normal ? a : 1.0, normal ? b : 1.0);
+    if (normal) return q;
     if (a != a || b != b) return qnan();
-    if (b == 0.0) {
-        if (a == 0.0) return qnan();
-        const bool neg = (__double2hiint(a) ^ __double2hiint(b)) < 0;
-        return __longlong_as_double(neg ? 0xfff0000000000000LL : 0x7ff0000000000000LL);
-    }
-    return __ddiv_rn(a, b);
+    const bool neg = (__double2hiint(a) ^ __double2hiint(b)) < 0;
+    const bool a0 = (a == 0.0), b0 = (b == 0.0), ai = (ea == 0x7ffu), bi = (eb == 0x7ffu);
+    if ((a0 && b0) || (ai && bi)) return qnan();
+    if (b0 || ai) return __longlong_as_double(neg ? 0xfff0000000000000LL : 0x7ff0000000000000LL);
+    if (a0 || bi) return __longlong_as_double(neg ? 0x8000000000000000LL : 0LL);
+    return div_generic(a, b);   // a denormal operand
 }
 
 // fillMaskAndNaNWithZero (NESOSIM.py:127-139): NaN -> 0, +-inf -> 0
