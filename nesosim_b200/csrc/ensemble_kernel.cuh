@@ -94,21 +94,28 @@ __global__ void derive_scan_kernel(const double2 *DB, double2 *DC, long long pla
 constexpr int ENS_CLUSTER = 4;
 constexpr int ENS_NT = 512;            // 16 warps, up to 128 registers per thread
 constexpr int ENS_MAXR = 28;           // rows one CTA can own
-constexpr int ENS_TR = ENS_MAXR + 4;   // h tile rows: own rows + 2 halo rows each side
 constexpr int ENS_SX = 96;             // h tile row stride (double2 elements); columns 0..nx-1
-constexpr int ENS_RR = ENS_MAXR + 2;   // raw tile rows: own rows +- 1
 constexpr int ENS_SXR = 98;            // raw tile row stride; column c lives at c+1 (zero pad each side)
 constexpr int ENS_MAX_NX = 96;
-constexpr size_t ENS_SMEM_BYTES = (size_t)(2 * ENS_TR * ENS_SX + 2 * ENS_RR * ENS_SXR) * sizeof(double2);
+constexpr int ENS_KLB = 3;             // land cells handled per thread per batch
+
+// Shared memory (double2 units), sized by the host for the tallest strip (`rows`) and the longest raw list:
+//   h tiles  [2 parity][rows+4][SX]   own rows + 2 halo rows each side
+//   raw adv  [rows+2][SXR], raw div [rows+2][SXR]
+//   staged drift terms [2][n_raw]     next day's (ut,vt),(gxu,gyv) per raw-list entry (cp.async), optional
+inline size_t ens_smem_bytes(int rows, int n_stage) {
+    return (size_t)(2 * (rows + 4) * ENS_SX + 2 * (rows + 2) * ENS_SXR + 2 * n_stage) * sizeof(double2);
+}
 
 // Per-strip cell lists (uint16 code = row*128 + col; row is global for raw lists, strip-local for owned cells).
 struct StripTables {
     const unsigned short *codes;       // all lists concatenated (device)
     int row0[ENS_CLUSTER + 1];         // strip k owns rows row0[k] .. row0[k+1]-1
-    int raw_int_off[ENS_CLUSTER], raw_int_n[ENS_CLUSTER];     // raw cells with all four neighbours in the grid
-    int raw_edge_off[ENS_CLUSTER], raw_edge_n[ENS_CLUSTER];   // raw cells on the first/last row or column
+    int raw_off[ENS_CLUSTER], raw_int_n[ENS_CLUSTER], raw_n[ENS_CLUSTER];   // interior entries first, then edge entries
     int ocean_off[ENS_CLUSTER], ocean_n[ENS_CLUSTER];
     int land_off[ENS_CLUSTER], land_n[ENS_CLUSTER];
+    int rows_alloc;                    // tallest strip
+    int stage_alloc;                   // staged entries per CTA (0: read the drift terms straight from L2)
 };
 
 struct EnsArgs {
@@ -129,15 +136,27 @@ struct EnsArgs {
     StripTables st;
 };
 
-// KO = owned ocean cells per thread (capacity KO*512 per strip); ALLOUT = all twelve outputs requested.
-template <int KO, bool ALLOUT>
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// streaming store: every output element is written exactly once and never read back by this kernel
+__device__ __forceinline__ void st_out(double *p, double v) { __stcs(p, v); }
+
+// KO = owned ocean cells per thread (capacity KO*512 per strip); ALLOUT = all twelve outputs requested;
+// STAGE = next day's drift terms are staged in shared memory with cp.async during the current day.
+template <int KO, bool ALLOUT, bool STAGE>
 __global__ void __cluster_dims__(ENS_CLUSTER, 1, 1) __launch_bounds__(ENS_NT, 1)
 ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
-    constexpr int NT = ENS_NT, SX = ENS_SX, SXR = ENS_SXR;
+    constexpr int NT = ENS_NT, SX = ENS_SX, SXR = ENS_SXR, KLB = ENS_KLB;
     extern __shared__ __align__(16) double2 smem2[];
+    const int TR = a.st.rows_alloc + 4, RR = a.st.rows_alloc + 2;
     double2 *s_h = smem2;                              // [2 parity][TR][SX]   (h0,h1)
-    double2 *s_adv = s_h + 2 * ENS_TR * SX;            // [RR][SXR]            (adv0,adv1) after NaN->0
-    double2 *s_div = s_adv + ENS_RR * SXR;             // [RR][SXR]            (div0,div1) after NaN->0
+    double2 *s_adv = s_h + 2 * TR * SX;                // [RR][SXR]            (adv0,adv1) after NaN->0
+    double2 *s_div = s_adv + RR * SXR;                 // [RR][SXR]            (div0,div1) after NaN->0
+    double2 *s_da = s_div + RR * SXR;                  // [n_raw][2]           staged (ut,vt),(gxu,gyv)
 
     cg::cluster_group cluster = cg::this_cluster();
     const int k = (int)cluster.block_rank();
@@ -154,11 +173,10 @@ ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
     const int up_shift = (k > 0) ? (ra - a.st.row0[k - 1]) : 0;   // my local row lr -> their tile row lr + 2 + up_shift
     const int dn_shift = nrow;                                     // my local row lr -> their tile row lr + 2 - dn_shift
 
-    const unsigned short *raw_int = a.st.codes + a.st.raw_int_off[k];
-    const unsigned short *raw_edge = a.st.codes + a.st.raw_edge_off[k];
+    const unsigned short *raw = a.st.codes + a.st.raw_off[k];
     const unsigned short *ocean = a.st.codes + a.st.ocean_off[k];
     const unsigned short *land = a.st.codes + a.st.land_off[k];
-    const int n_raw_int = a.st.raw_int_n[k], n_raw_edge = a.st.raw_edge_n[k];
+    const int n_raw_int = a.st.raw_int_n[k], n_raw = a.st.raw_n[k];
     const int n_ocean = a.st.ocean_n[k], n_land = a.st.land_n[k];
 
     // cells this thread owns for the whole season: ocean[tid + j*NT]
@@ -176,7 +194,7 @@ ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
         }
     }
 
-    for (int i = tid; i < ENS_RR * SXR; i += NT) {     // zero padding of convolve(boundary='fill')
+    for (int i = tid; i < RR * SXR; i += NT) {         // zero padding of convolve(boundary='fill')
         s_adv[i] = make_double2(0.0, 0.0);
         s_div[i] = make_double2(0.0, 0.0);
     }
@@ -185,13 +203,23 @@ ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
     const double landAdv = a.sw.dynamics ? nan : 0.0, landLead = a.sw.leadloss ? nan : 0.0;
     const double landAtm = a.sw.atmloss ? nan : 0.0, landWp = a.sw.windpack ? nan : 0.0;
 
-    // write (h0,h1) of local row lr, column c for the day whose tiles have parity `par`
+    // write (h0,h1) of local row lr, column c into the tiles of parity `par` (own copy + neighbours' halos)
     auto put_h = [&](int par, int lr, int c, double2 v) {
-        s_h[(par * ENS_TR + lr + 2) * SX + c] = v;
-        if (lr < 2 && nb_up) nb_up[(par * ENS_TR + lr + 2 + up_shift) * SX + c] = v;
-        if (lr >= nrow - 2 && nb_dn) nb_dn[(par * ENS_TR + lr + 2 - dn_shift) * SX + c] = v;
+        s_h[(par * TR + lr + 2) * SX + c] = v;
+        if (lr < 2 && nb_up) nb_up[(par * TR + lr + 2 + up_shift) * SX + c] = v;
+        if (lr >= nrow - 2 && nb_dn) nb_dn[(par * TR + lr + 2 - dn_shift) * SX + c] = v;
     };
     auto want = [&](int v) { return ALLOUT || a.out[v] != nullptr; };
+    // stage day x's drift terms for this thread's raw-list entries
+    auto stage_day = [&](int x) {
+        const double2 *DAx = a.DA + (long long)x * plane * 2;
+        for (int i = tid; i < n_raw; i += NT) {
+            const int code = raw[i], r = code >> 7, c = code & 127;
+            const double2 *src = DAx + (r * nx + c) * 2;
+            cp_async16(s_da + 2 * i, src);
+            cp_async16(s_da + 2 * i + 1, src + 1);
+        }
+    };
 
     cluster.sync();   // every CTA of the cluster is running before anyone writes into a neighbour's shared memory
 
@@ -201,12 +229,15 @@ ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
 #pragma unroll
         for (int j = 0; j < KO; ++j) accAdv[j] = accDiv[j] = accLead[j] = accAtm[j] = accWpl[j] = accWpg[j] = accWp[j] = 0.0;
 
-        double *po[NVAR];   // member m, slot under construction
-#pragma unroll
-        for (int v = 0; v < NVAR; ++v) po[v] = want(v) ? a.out[v] + (long long)m * a.mstride[v] : nullptr;
+        // output address of variable v, cell o, time slot `slot` of member m
+        auto outp = [&](int v, int slot) -> double * {
+            const long long per_slot = (v == V_H0 || v == V_H1) ? 2 * plane : plane;
+            return a.out[v] + ((long long)m * a.mstride[v] + (long long)slot * per_slot);
+        };
 
         // ---- slot 0: genEmptyArrays zeros + the IC split of main (NESOSIM.py:604-609), every cell of the strip.
         // (No barrier against the previous member: its last day ended with a cluster barrier after all reads.)
+        if (STAGE && a.sw.dynamics) stage_day(0);
         for (int i = tid; i < nrow * nx; i += NT) {
             const int lr = i / nx, c = i - lr * nx;
             const long long o = (long long)(ra + lr) * nx + c;
@@ -219,30 +250,29 @@ ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
             put_h(0, lr, c, make_double2(half, half));
 #pragma unroll
             for (int v = 0; v < NVAR; ++v)
-                if (want(v)) po[v][o] = (v == V_H0 || v == V_H1) ? half : 0.0;
+                if (want(v)) st_out(outp(v, 0) + o, (v == V_H0 || v == V_H1) ? half : 0.0);
         }
+        if (STAGE) cp_async_wait_all();
         cluster.sync();
 
         for (int x = 0; x < steps; ++x) {
             const int par = x & 1;
-            const double2 *hcur = s_h + par * ENS_TR * SX;
+            const double2 *hcur = s_h + par * TR * SX;
             const double2 *DAx = a.DA + (long long)x * plane * 2;
             const double2 *DBx = a.DB + (long long)x * plane;
             const double2 *DCx = a.DC + (long long)x * plane;
             const double *Wx = a.W + (long long)x * plane;
-#pragma unroll
-            for (int v = 0; v < NVAR; ++v)
-                if (want(v)) po[v] += (v == V_H0 || v == V_H1) ? 2 * plane : plane;
 
             // member-independent inputs of the owned cells, requested before phase A so L2 latency overlaps it
-            double2 f_b[KO];
+            double2 f_b[KO], f_c[KO];
             double f_W[KO];
 #pragma unroll
             for (int j = 0; j < KO; ++j) {
-                f_b[j] = make_double2(0.0, 0.0);
+                f_b[j] = f_c[j] = make_double2(0.0, 0.0);
                 f_W[j] = 0.0;
                 if (own_t[j] >= 0) {
                     f_b[j] = __ldg(DBx + own_o[j]);
+                    f_c[j] = __ldg(DCx + own_o[j]);
                     f_W[j] = __ldg(Wx + own_o[j]);
                 }
             }
@@ -250,28 +280,33 @@ ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
             // ---------------- phase A: raw advection / divergence (calcDynamics, NESOSIM.py:189-222) where an
             // ocean cell of this strip will read it
             if (a.sw.dynamics) {
-                for (int i = tid; i < n_raw_int; i += NT) {
-                    const int code = raw_int[i], r = code >> 7, c = code & 127;
-                    const double2 d01 = __ldg(DAx + (r * nx + c) * 2), d23 = __ldg(DAx + (r * nx + c) * 2 + 1);
-                    const double2 *hp = hcur + (r - ra + 2) * SX + c;
-                    const double2 hc = hp[0], hl = hp[-1], hr = hp[1], hu = hp[-SX], hd = hp[SX];
-                    const double gx0 = div_const(sub(hr.x, hl.x), a.g.two_dx), gy0 = div_const(sub(hd.x, hu.x), a.g.two_dx);
-                    const double gx1 = div_const(sub(hr.y, hl.y), a.g.two_dx), gy1 = div_const(sub(hd.y, hu.y), a.g.two_dx);
-                    const int ro = (r - ra + 1) * SXR + c + 1;
-                    s_adv[ro] = make_double2(zero_if_nonfinite(adv_term(d01.x, d01.y, gx0, gy0)),
-                                             zero_if_nonfinite(adv_term(d01.x, d01.y, gx1, gy1)));
-                    s_div[ro] = make_double2(zero_if_nonfinite(div_term(hc.x, d23.x, d23.y)),
-                                             zero_if_nonfinite(div_term(hc.y, d23.x, d23.y)));
-                }
-                for (int i = tid; i < n_raw_edge; i += NT) {
-                    const int code = raw_edge[i], r = code >> 7, c = code & 127;
-                    const double2 d01 = __ldg(DAx + (r * nx + c) * 2), d23 = __ldg(DAx + (r * nx + c) * 2 + 1);
+                for (int i = tid; i < n_raw; i += NT) {
+                    const int code = raw[i], r = code >> 7, c = code & 127;
+                    double2 d01, d23;
+                    if (STAGE) {
+                        d01 = s_da[2 * i];
+                        d23 = s_da[2 * i + 1];
+                    } else {
+                        d01 = __ldg(DAx + (r * nx + c) * 2);
+                        d23 = __ldg(DAx + (r * nx + c) * 2 + 1);
+                    }
                     const double2 *hp = hcur + (r - ra + 2) * SX + c;
                     const double2 hc = hp[0];
-                    const double2 hl = hp[c > 0 ? -1 : 0], hr = hp[c < nx - 1 ? 1 : 0];
-                    const double2 hu = hp[r > 0 ? -SX : 0], hd = hp[r < ny - 1 ? SX : 0];
-                    const double gx0 = gradient1d(hl.x, hc.x, hr.x, c, nx, a.g), gy0 = gradient1d(hu.x, hc.x, hd.x, r, ny, a.g);
-                    const double gx1 = gradient1d(hl.y, hc.y, hr.y, c, nx, a.g), gy1 = gradient1d(hu.y, hc.y, hd.y, r, ny, a.g);
+                    double gx0, gy0, gx1, gy1;
+                    if (i < n_raw_int) {
+                        const double2 hl = hp[-1], hr = hp[1], hu = hp[-SX], hd = hp[SX];
+                        gx0 = div_const(sub(hr.x, hl.x), a.g.two_dx);
+                        gy0 = div_const(sub(hd.x, hu.x), a.g.two_dx);
+                        gx1 = div_const(sub(hr.y, hl.y), a.g.two_dx);
+                        gy1 = div_const(sub(hd.y, hu.y), a.g.two_dx);
+                    } else {   // first/last row or column: one-sided differences (np.gradient edge_order=1)
+                        const double2 hl = hp[c > 0 ? -1 : 0], hr = hp[c < nx - 1 ? 1 : 0];
+                        const double2 hu = hp[r > 0 ? -SX : 0], hd = hp[r < ny - 1 ? SX : 0];
+                        gx0 = gradient1d(hl.x, hc.x, hr.x, c, nx, a.g);
+                        gy0 = gradient1d(hu.x, hc.x, hd.x, r, ny, a.g);
+                        gx1 = gradient1d(hl.y, hc.y, hr.y, c, nx, a.g);
+                        gy1 = gradient1d(hu.y, hc.y, hd.y, r, ny, a.g);
+                    }
                     const int ro = (r - ra + 1) * SXR + c + 1;
                     s_adv[ro] = make_double2(zero_if_nonfinite(adv_term(d01.x, d01.y, gx0, gy0)),
                                              zero_if_nonfinite(adv_term(d01.x, d01.y, gx1, gy1)));
@@ -281,11 +316,13 @@ ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
             }
             __syncthreads();
 
-            // ---------------- phase B: owned ocean cells -- point-wise terms, 3x3 smoothing, update, outputs
+            // ---------------- phase B: owned ocean cells -- point-wise terms, 3x3 smoothing, update
+            double h0n[KO], h1n[KO];
 #pragma unroll
             for (int j = 0; j < KO; ++j) {
+                h0n[j] = h1n[j] = 0.0;
                 if (own_t[j] < 0) continue;
-                const int to = own_t[j], o = own_o[j];
+                const int to = own_t[j];
                 const int lr = to / SX - 2, c = to - (lr + 2) * SX;
                 const double2 h = hcur[to];
                 const double W = f_W[j];
@@ -331,58 +368,92 @@ ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
                     t0 = add(add(t0, 0.0), 0.0);
                     t1 = add(add(t1, 0.0), 0.0);
                 }
-                const double h0n = mask_nan(t0, false, true), h1n = mask_nan(t1, false, true);   // NESOSIM.py:332-333
-                put_h(par ^ 1, lr, c, make_double2(h0n, h1n));
-                const double2 cum = __ldg(DCx + o);
-                if (want(V_ACC)) po[V_ACC][o] = cum.x;
-                if (want(V_OCEAN)) po[V_OCEAN][o] = cum.y;
-                if (want(V_LEAD)) po[V_LEAD][o] = accLead[j];
-                if (want(V_ATM)) po[V_ATM][o] = accAtm[j];
-                if (want(V_WPL)) po[V_WPL][o] = accWpl[j];
-                if (want(V_WPG)) po[V_WPG][o] = accWpg[j];
-                if (want(V_WP)) po[V_WP][o] = accWp[j];
-                if (want(V_ADV)) po[V_ADV][o] = accAdv[j];
-                if (want(V_DIV)) po[V_DIV][o] = accDiv[j];
-                if (want(V_H0)) po[V_H0][o] = h0n;
-                if (want(V_H1)) po[V_H1][o] = h1n;
-                if (want(V_DENS)) po[V_DENS][o] = density_variable(h0n, h1n, false, a.k);
+                h0n[j] = mask_nan(t0, false, true);              // NESOSIM.py:332-333
+                h1n[j] = mask_nan(t1, false, true);
+                put_h(par ^ 1, lr, c, make_double2(h0n[j], h1n[j]));
+            }
+            if (x <= 1) {   // land: h is NaN from slot 1 on; two steps put it into both tile parities
+                for (int i = tid; i < n_land; i += NT) {
+                    const int code = land[i];
+                    put_h(par ^ 1, code >> 7, code & 127, make_double2(nan, nan));
+                }
+            }
+            // Tiles of day x+1 are written: arrive now, wait after the global stores have been issued, so the
+            // barrier's release fence never has this day's HBM stores to drain.
+            cluster_arrive_release();
+            if (STAGE && a.sw.dynamics && x + 1 < steps) stage_day(x + 1);
+
+            // ---------------- outputs of the owned cells (slot x+1)
+#pragma unroll
+            for (int j = 0; j < KO; ++j) {
+                if (own_t[j] < 0) continue;
+                const int o = own_o[j];
+                if (want(V_ACC)) st_out(outp(V_ACC, x + 1) + o, f_c[j].x);
+                if (want(V_OCEAN)) st_out(outp(V_OCEAN, x + 1) + o, f_c[j].y);
+                if (want(V_LEAD)) st_out(outp(V_LEAD, x + 1) + o, accLead[j]);
+                if (want(V_ATM)) st_out(outp(V_ATM, x + 1) + o, accAtm[j]);
+                if (want(V_WPL)) st_out(outp(V_WPL, x + 1) + o, accWpl[j]);
+                if (want(V_WPG)) st_out(outp(V_WPG, x + 1) + o, accWpg[j]);
+                if (want(V_WP)) st_out(outp(V_WP, x + 1) + o, accWp[j]);
+                if (want(V_ADV)) st_out(outp(V_ADV, x + 1) + o, accAdv[j]);
+                if (want(V_DIV)) st_out(outp(V_DIV, x + 1) + o, accDiv[j]);
+                if (want(V_H0)) st_out(outp(V_H0, x + 1) + o, h0n[j]);
+                if (want(V_H1)) st_out(outp(V_H1, x + 1) + o, h1n[j]);
+                if (want(V_DENS)) st_out(outp(V_DENS, x + 1) + o, density_variable(h0n[j], h1n[j], false, a.k));
             }
 
             // ---------------- land cells: no state.  Step 0 sees the initial depths; afterwards h is NaN, so every
             // switched-on term is NaN and every switched-off term adds 0 (NESOSIM.py:287-322): closed form.
-            for (int i = tid; i < n_land; i += NT) {
-                const int code = land[i], lr = code >> 7, c = code & 127;
-                const int o = (ra + lr) * nx + c;
-                const double2 cum = __ldg(DCx + o);
-                double vLead = landLead, vAtm = landAtm, vWpl = landWp, vWpg = landWp, vWp = landWp;
-                if (x == 0) {
-                    const double2 h = hcur[(lr + 2) * SX + c];
-                    const double W = __ldg(Wx + o);
-                    const double omc = __ldg(DBx + o).y;
-                    const double wt = wind_flag(W, mc.wpt);
-                    vLead = add(0.0, a.sw.leadloss ? -mul(mul(mul(mul(mul(wt, mc.llf), a.k.deltaT), h.x), W), omc) : 0.0);
-                    vAtm = add(0.0, a.sw.atmloss ? atm_loss(wt, h.x, W, mc, a.k) : 0.0);
-                    double wpl = 0.0, wpg = 0.0, wpn = 0.0;
-                    if (a.sw.windpack) wind_packing(wt, h.x, mc, a.k, wpl, wpg, wpn);
-                    vWpl = add(0.0, wpl);
-                    vWpg = add(0.0, wpg);
-                    vWp = add(0.0, wpn);
+            for (int base = 0; base < n_land; base += KLB * NT) {
+                int lo[KLB], lt[KLB];
+                double2 cum[KLB];
+#pragma unroll
+                for (int q = 0; q < KLB; ++q) {
+                    const int idx = base + q * NT + tid;
+                    lo[q] = -1;
+                    lt[q] = 0;
+                    if (idx < n_land) {
+                        const int code = land[idx], lr = code >> 7, c = code & 127;
+                        lo[q] = (ra + lr) * nx + c;
+                        lt[q] = (lr + 2) * SX + c;
+                    }
                 }
-                if (x <= 1) put_h(par ^ 1, lr, c, make_double2(nan, nan));   // both tile parities hold NaN afterwards
-                if (want(V_ACC)) po[V_ACC][o] = cum.x;
-                if (want(V_OCEAN)) po[V_OCEAN][o] = cum.y;
-                if (want(V_LEAD)) po[V_LEAD][o] = vLead;
-                if (want(V_ATM)) po[V_ATM][o] = vAtm;
-                if (want(V_WPL)) po[V_WPL][o] = vWpl;
-                if (want(V_WPG)) po[V_WPG][o] = vWpg;
-                if (want(V_WP)) po[V_WP][o] = vWp;
-                if (want(V_ADV)) po[V_ADV][o] = landAdv;
-                if (want(V_DIV)) po[V_DIV][o] = landAdv;
-                if (want(V_H0)) po[V_H0][o] = nan;
-                if (want(V_H1)) po[V_H1][o] = nan;
-                if (want(V_DENS)) po[V_DENS][o] = nan;
+#pragma unroll
+                for (int q = 0; q < KLB; ++q) cum[q] = (lo[q] >= 0) ? __ldg(DCx + lo[q]) : make_double2(0.0, 0.0);
+#pragma unroll
+                for (int q = 0; q < KLB; ++q) {
+                    if (lo[q] < 0) continue;
+                    const int o = lo[q];
+                    double vLead = landLead, vAtm = landAtm, vWpl = landWp, vWpg = landWp, vWp = landWp;
+                    if (x == 0) {
+                        const double2 h = hcur[lt[q]];
+                        const double W = __ldg(Wx + o);
+                        const double omc = __ldg(DBx + o).y;
+                        const double wt = wind_flag(W, mc.wpt);
+                        vLead = add(0.0, a.sw.leadloss ? -mul(mul(mul(mul(mul(wt, mc.llf), a.k.deltaT), h.x), W), omc) : 0.0);
+                        vAtm = add(0.0, a.sw.atmloss ? atm_loss(wt, h.x, W, mc, a.k) : 0.0);
+                        double wpl = 0.0, wpg = 0.0, wpn = 0.0;
+                        if (a.sw.windpack) wind_packing(wt, h.x, mc, a.k, wpl, wpg, wpn);
+                        vWpl = add(0.0, wpl);
+                        vWpg = add(0.0, wpg);
+                        vWp = add(0.0, wpn);
+                    }
+                    if (want(V_ACC)) st_out(outp(V_ACC, x + 1) + o, cum[q].x);
+                    if (want(V_OCEAN)) st_out(outp(V_OCEAN, x + 1) + o, cum[q].y);
+                    if (want(V_LEAD)) st_out(outp(V_LEAD, x + 1) + o, vLead);
+                    if (want(V_ATM)) st_out(outp(V_ATM, x + 1) + o, vAtm);
+                    if (want(V_WPL)) st_out(outp(V_WPL, x + 1) + o, vWpl);
+                    if (want(V_WPG)) st_out(outp(V_WPG, x + 1) + o, vWpg);
+                    if (want(V_WP)) st_out(outp(V_WP, x + 1) + o, vWp);
+                    if (want(V_ADV)) st_out(outp(V_ADV, x + 1) + o, landAdv);
+                    if (want(V_DIV)) st_out(outp(V_DIV, x + 1) + o, landAdv);
+                    if (want(V_H0)) st_out(outp(V_H0, x + 1) + o, nan);
+                    if (want(V_H1)) st_out(outp(V_H1, x + 1) + o, nan);
+                    if (want(V_DENS)) st_out(outp(V_DENS, x + 1) + o, nan);
+                }
             }
-            cluster.sync();   // day x+1 tiles (own rows and pushed halos) are complete; raw tiles are free again
+            if (STAGE) cp_async_wait_all();
+            cluster_wait_acquire();   // day x+1 tiles (own rows and pushed halos) are complete; raw tiles are free
         }
     }
 }

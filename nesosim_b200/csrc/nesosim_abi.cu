@@ -300,15 +300,17 @@ int launch_init(nesosim_ctx *ctx, const double *ic, int ic_per_member, const dou
 struct EnsVariant {
     const char *name;
     int ko;
-    void (*kernel_all)(const EnsArgs);    // all twelve outputs requested
-    void (*kernel_some)(const EnsArgs);   // NULL outputs are skipped
+    void (*kernel[2][2])(const EnsArgs);  // [all twelve outputs requested][drift terms staged in shared memory]
 };
 
 const EnsVariant *ens_variants(int *n) {
     static const EnsVariant v[] = {
-        {"ko2", 2, ensemble_season_kernel<2, true>, ensemble_season_kernel<2, false>},
-        {"ko3", 3, ensemble_season_kernel<3, true>, ensemble_season_kernel<3, false>},
-        {"ko5", 5, ensemble_season_kernel<5, true>, ensemble_season_kernel<5, false>},
+#define ENS_V(K) {{ensemble_season_kernel<K, false, false>, ensemble_season_kernel<K, false, true>}, \
+                  {ensemble_season_kernel<K, true, false>, ensemble_season_kernel<K, true, true>}}
+        {"ko2", 2, ENS_V(2)},
+        {"ko3", 3, ENS_V(3)},
+        {"ko5", 5, ENS_V(5)},
+#undef ENS_V
     };
     *n = (int)(sizeof(v) / sizeof(v[0]));
     return v;
@@ -348,7 +350,7 @@ int build_strip_tables(nesosim_ctx *ctx) {
     StripTables &t = e.tables;
     t.row0[0] = 0; t.row0[1] = best[0]; t.row0[2] = best[1]; t.row0[3] = best[2]; t.row0[4] = ny;
     std::vector<unsigned short> codes;
-    int max_ocean = 0;
+    int max_ocean = 0, max_raw = 0, max_rows = 0;
     for (int k = 0; k < ENS_CLUSTER; ++k) {
         const int ra = t.row0[k], rb = t.row0[k + 1];
         std::vector<unsigned short> ri, re, oc, la;
@@ -370,8 +372,11 @@ int build_strip_tables(nesosim_ctx *ctx) {
             n = (int)v.size();
             codes.insert(codes.end(), v.begin(), v.end());
         };
-        append(ri, t.raw_int_off[k], t.raw_int_n[k]);
-        append(re, t.raw_edge_off[k], t.raw_edge_n[k]);
+        t.raw_int_n[k] = (int)ri.size();
+        ri.insert(ri.end(), re.begin(), re.end());           // interior entries first, then the edge entries
+        append(ri, t.raw_off[k], t.raw_n[k]);
+        max_raw = std::max(max_raw, t.raw_n[k]);
+        max_rows = std::max(max_rows, rb - ra);
         append(oc, t.ocean_off[k], t.ocean_n[k]);
         append(la, t.land_off[k], t.land_n[k]);
         max_ocean = std::max(max_ocean, (int)oc.size());
@@ -380,6 +385,10 @@ int build_strip_tables(nesosim_ctx *ctx) {
     CU(cudaMalloc(&e.codes_dev, codes.size() * sizeof(unsigned short)));
     CU(cudaMemcpy(e.codes_dev, codes.data(), codes.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
     t.codes = e.codes_dev;
+    t.rows_alloc = max_rows;
+    // stage the drift terms in shared memory when the tiles leave room for the longest raw list
+    const size_t smem_cap = 227 * 1024;
+    t.stage_alloc = (ens_smem_bytes(max_rows, max_raw) <= smem_cap && !getenv("NESOSIM_ENS_NOSTAGE")) ? max_raw : 0;
     e.ko_needed = std::max(1, (max_ocean + ENS_NT - 1) / ENS_NT);
     e.tables_ready = true;
     return NESOSIM_OK;
@@ -440,14 +449,15 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     const EnsVariant *v = pick_variant(e.ko_needed);
     bool all = true;
     for (int vv = 0; vv < NVAR; ++vv) all = all && (out_base(out, vv) != nullptr);
-    void (*kernel)(const EnsArgs) = all ? v->kernel_all : v->kernel_some;
-    CU(cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENS_SMEM_BYTES));
+    void (*kernel)(const EnsArgs) = v->kernel[all ? 1 : 0][e.tables.stage_alloc > 0 ? 1 : 0];
+    const size_t smem_bytes = ens_smem_bytes(e.tables.rows_alloc, e.tables.stage_alloc);
+    CU(cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     int max_clusters = 0;
     {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(ENS_CLUSTER * 64);
         cfg.blockDim = dim3(ENS_NT);
-        cfg.dynamicSmemBytes = ENS_SMEM_BYTES;
+        cfg.dynamicSmemBytes = smem_bytes;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = ENS_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -476,7 +486,7 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     std::memcpy(a.w, c.conv_weights, sizeof(a.w));
     a.sw = Switches{c.dynamicsInc == 1, c.leadlossInc == 1, c.windpackInc == 1, c.atmlossInc == 1, 0};
     a.st = e.tables;
-    kernel<<<ncl * ENS_CLUSTER, ENS_NT, ENS_SMEM_BYTES, st>>>(a);
+    kernel<<<ncl * ENS_CLUSTER, ENS_NT, smem_bytes, st>>>(a);
     ctx->launches++;
     CU(cudaGetLastError());
     return NESOSIM_OK;
