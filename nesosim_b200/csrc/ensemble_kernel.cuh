@@ -103,8 +103,10 @@ constexpr int ENS_KLB = 3;             // land cells handled per thread per batc
 //   h tiles  [2 parity][rows+4][SX]   own rows + 2 halo rows each side
 //   raw adv  [rows+2][SXR], raw div [rows+2][SXR]
 //   staged drift terms [2][n_raw]     next day's (ut,vt),(gxu,gyv) per raw-list entry (cp.async), optional
-inline size_t ens_smem_bytes(int rows, int n_stage) {
-    return (size_t)(2 * (rows + 4) * ENS_SX + 2 * (rows + 2) * ENS_SXR + 2 * n_stage) * sizeof(double2);
+//   raw and land code lists (uint16)  (L1 is invalidated by every cluster barrier, so they must not live there)
+inline size_t ens_smem_bytes(int rows, int n_stage, int n_codes) {
+    return (size_t)(2 * (rows + 4) * ENS_SX + 2 * (rows + 2) * ENS_SXR + 2 * n_stage) * sizeof(double2) +
+           (size_t)((n_codes + 7) / 8 * 8) * sizeof(unsigned short);
 }
 
 // Per-strip cell lists (uint16 code = row*128 + col; row is global for raw lists, strip-local for owned cells).
@@ -116,6 +118,7 @@ struct StripTables {
     int land_off[ENS_CLUSTER], land_n[ENS_CLUSTER];
     int rows_alloc;                    // tallest strip
     int stage_alloc;                   // staged entries per CTA (0: read the drift terms straight from L2)
+    int raw_alloc, land_alloc;         // longest raw / land list (shared-memory copies)
 };
 
 struct EnsArgs {
@@ -134,6 +137,7 @@ struct EnsArgs {
     double w[9];
     Switches sw;
     StripTables st;
+    long long *timing;                 // debug: [gridDim.x][8] phase cycle totals of thread 0 (NULL = off)
 };
 
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
@@ -157,6 +161,8 @@ ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
     double2 *s_adv = s_h + 2 * TR * SX;                // [RR][SXR]            (adv0,adv1) after NaN->0
     double2 *s_div = s_adv + RR * SXR;                 // [RR][SXR]            (div0,div1) after NaN->0
     double2 *s_da = s_div + RR * SXR;                  // [n_raw][2]           staged (ut,vt),(gxu,gyv)
+    unsigned short *s_raw_code = reinterpret_cast<unsigned short *>(s_da + 2 * a.st.stage_alloc);
+    unsigned short *s_land_code = s_raw_code + (a.st.raw_alloc + 7) / 8 * 8;
 
     cg::cluster_group cluster = cg::this_cluster();
     const int k = (int)cluster.block_rank();
@@ -173,11 +179,12 @@ ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
     const int up_shift = (k > 0) ? (ra - a.st.row0[k - 1]) : 0;   // my local row lr -> their tile row lr + 2 + up_shift
     const int dn_shift = nrow;                                     // my local row lr -> their tile row lr + 2 - dn_shift
 
-    const unsigned short *raw = a.st.codes + a.st.raw_off[k];
     const unsigned short *ocean = a.st.codes + a.st.ocean_off[k];
-    const unsigned short *land = a.st.codes + a.st.land_off[k];
     const int n_raw_int = a.st.raw_int_n[k], n_raw = a.st.raw_n[k];
     const int n_ocean = a.st.ocean_n[k], n_land = a.st.land_n[k];
+    for (int i = tid; i < n_raw; i += NT) s_raw_code[i] = a.st.codes[a.st.raw_off[k] + i];
+    for (int i = tid; i < n_land; i += NT) s_land_code[i] = a.st.codes[a.st.land_off[k] + i];
+    const unsigned short *raw = s_raw_code, *land = s_land_code;
 
     // cells this thread owns for the whole season: ocean[tid + j*NT]
     int own_t[KO];       // tile offset (lr+2)*SX + col, or -1
@@ -223,16 +230,27 @@ ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
 
     cluster.sync();   // every CTA of the cluster is running before anyone writes into a neighbour's shared memory
 
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool timing = a.timing != nullptr && tid == 0;
+    long long tlast = 0;
+#define ENS_TICK(slot)                                   \
+    if (timing) {                                        \
+        const long long now_ = clock64();                \
+        tacc[slot] += now_ - tlast;                      \
+        tlast = now_;                                    \
+    }
+
     for (int m = cid; m < a.M; m += ncl) {
         const MemberCoef mc = a.coef[m];
         double accAdv[KO], accDiv[KO], accLead[KO], accAtm[KO], accWpl[KO], accWpg[KO], accWp[KO];
 #pragma unroll
         for (int j = 0; j < KO; ++j) accAdv[j] = accDiv[j] = accLead[j] = accAtm[j] = accWpl[j] = accWpg[j] = accWp[j] = 0.0;
 
-        // output address of variable v, cell o, time slot `slot` of member m
+        // output address of variable v, time slot `slot` of member m (add the cell offset)
+        const long long mo_plane = (long long)m * a.mstride[V_DENS], mo_depth = (long long)m * a.mstride[V_H0];
         auto outp = [&](int v, int slot) -> double * {
-            const long long per_slot = (v == V_H0 || v == V_H1) ? 2 * plane : plane;
-            return a.out[v] + ((long long)m * a.mstride[v] + (long long)slot * per_slot);
+            return (v == V_H0 || v == V_H1) ? a.out[v] + (mo_depth + (long long)slot * 2 * plane)
+                                            : a.out[v] + (mo_plane + (long long)slot * plane);
         };
 
         // ---- slot 0: genEmptyArrays zeros + the IC split of main (NESOSIM.py:604-609), every cell of the strip.
@@ -255,6 +273,7 @@ ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
         if (STAGE) cp_async_wait_all();
         cluster.sync();
 
+        if (timing) tlast = clock64();
         for (int x = 0; x < steps; ++x) {
             const int par = x & 1;
             const double2 *hcur = s_h + par * TR * SX;
@@ -274,6 +293,17 @@ ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
                     f_b[j] = __ldg(DBx + own_o[j]);
                     f_c[j] = __ldg(DCx + own_o[j]);
                     f_W[j] = __ldg(Wx + own_o[j]);
+                }
+            }
+
+            double2 l_c[KLB];   // running sums for the first batch of land cells (copied to the outputs)
+#pragma unroll
+            for (int q = 0; q < KLB; ++q) {
+                const int idx = q * NT + tid;
+                l_c[q] = make_double2(0.0, 0.0);
+                if (idx < n_land) {
+                    const int code = land[idx];
+                    l_c[q] = __ldg(DCx + (ra + (code >> 7)) * nx + (code & 127));
                 }
             }
 
@@ -314,7 +344,61 @@ ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
                                              zero_if_nonfinite(div_term(hc.y, d23.x, d23.y)));
                 }
             }
+            ENS_TICK(0)   // prefetch issue + phase A
             __syncthreads();
+            ENS_TICK(1)   // wait for the CTA
+            // ---------------- land cells: no state.  Step 0 sees the initial depths; afterwards h is NaN, so every
+            // switched-on term is NaN and every switched-off term adds 0 (NESOSIM.py:287-322): closed form.
+            for (int base = 0; base < n_land; base += KLB * NT) {
+                int lo[KLB], lt[KLB];
+                double2 cum[KLB];
+#pragma unroll
+                for (int q = 0; q < KLB; ++q) {
+                    const int idx = base + q * NT + tid;
+                    lo[q] = -1;
+                    lt[q] = 0;
+                    if (idx < n_land) {
+                        const int code = land[idx], lr = code >> 7, c = code & 127;
+                        lo[q] = (ra + lr) * nx + c;
+                        lt[q] = (lr + 2) * SX + c;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < KLB; ++q)   // the first batch was requested at the top of the day
+                    cum[q] = (base == 0) ? l_c[q] : ((lo[q] >= 0) ? __ldg(DCx + lo[q]) : make_double2(0.0, 0.0));
+#pragma unroll
+                for (int q = 0; q < KLB; ++q) {
+                    if (lo[q] < 0) continue;
+                    const int o = lo[q];
+                    double vLead = landLead, vAtm = landAtm, vWpl = landWp, vWpg = landWp, vWp = landWp;
+                    if (x == 0) {
+                        const double2 h = hcur[lt[q]];
+                        const double W = __ldg(Wx + o);
+                        const double omc = __ldg(DBx + o).y;
+                        const double wt = wind_flag(W, mc.wpt);
+                        vLead = add(0.0, a.sw.leadloss ? -mul(mul(mul(mul(mul(wt, mc.llf), a.k.deltaT), h.x), W), omc) : 0.0);
+                        vAtm = add(0.0, a.sw.atmloss ? atm_loss(wt, h.x, W, mc, a.k) : 0.0);
+                        double wpl = 0.0, wpg = 0.0, wpn = 0.0;
+                        if (a.sw.windpack) wind_packing(wt, h.x, mc, a.k, wpl, wpg, wpn);
+                        vWpl = add(0.0, wpl);
+                        vWpg = add(0.0, wpg);
+                        vWp = add(0.0, wpn);
+                    }
+                    if (want(V_ACC)) st_out(outp(V_ACC, x + 1) + o, cum[q].x);
+                    if (want(V_OCEAN)) st_out(outp(V_OCEAN, x + 1) + o, cum[q].y);
+                    if (want(V_LEAD)) st_out(outp(V_LEAD, x + 1) + o, vLead);
+                    if (want(V_ATM)) st_out(outp(V_ATM, x + 1) + o, vAtm);
+                    if (want(V_WPL)) st_out(outp(V_WPL, x + 1) + o, vWpl);
+                    if (want(V_WPG)) st_out(outp(V_WPG, x + 1) + o, vWpg);
+                    if (want(V_WP)) st_out(outp(V_WP, x + 1) + o, vWp);
+                    if (want(V_ADV)) st_out(outp(V_ADV, x + 1) + o, landAdv);
+                    if (want(V_DIV)) st_out(outp(V_DIV, x + 1) + o, landAdv);
+                    if (want(V_H0)) st_out(outp(V_H0, x + 1) + o, nan);
+                    if (want(V_H1)) st_out(outp(V_H1, x + 1) + o, nan);
+                    if (want(V_DENS)) st_out(outp(V_DENS, x + 1) + o, nan);
+                }
+            }
+            ENS_TICK(5)   // land stores
 
             // ---------------- phase B: owned ocean cells -- point-wise terms, 3x3 smoothing, update
             double h0n[KO], h1n[KO];
@@ -380,7 +464,9 @@ ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
             }
             // Tiles of day x+1 are written: arrive now, wait after the global stores have been issued, so the
             // barrier's release fence never has this day's HBM stores to drain.
+            ENS_TICK(2)   // phase B compute
             cluster_arrive_release();
+            ENS_TICK(3)   // arrive (release fence)
             if (STAGE && a.sw.dynamics && x + 1 < steps) stage_day(x + 1);
 
             // ---------------- outputs of the owned cells (slot x+1)
@@ -402,60 +488,16 @@ ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
                 if (want(V_DENS)) st_out(outp(V_DENS, x + 1) + o, density_variable(h0n[j], h1n[j], false, a.k));
             }
 
-            // ---------------- land cells: no state.  Step 0 sees the initial depths; afterwards h is NaN, so every
-            // switched-on term is NaN and every switched-off term adds 0 (NESOSIM.py:287-322): closed form.
-            for (int base = 0; base < n_land; base += KLB * NT) {
-                int lo[KLB], lt[KLB];
-                double2 cum[KLB];
-#pragma unroll
-                for (int q = 0; q < KLB; ++q) {
-                    const int idx = base + q * NT + tid;
-                    lo[q] = -1;
-                    lt[q] = 0;
-                    if (idx < n_land) {
-                        const int code = land[idx], lr = code >> 7, c = code & 127;
-                        lo[q] = (ra + lr) * nx + c;
-                        lt[q] = (lr + 2) * SX + c;
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < KLB; ++q) cum[q] = (lo[q] >= 0) ? __ldg(DCx + lo[q]) : make_double2(0.0, 0.0);
-#pragma unroll
-                for (int q = 0; q < KLB; ++q) {
-                    if (lo[q] < 0) continue;
-                    const int o = lo[q];
-                    double vLead = landLead, vAtm = landAtm, vWpl = landWp, vWpg = landWp, vWp = landWp;
-                    if (x == 0) {
-                        const double2 h = hcur[lt[q]];
-                        const double W = __ldg(Wx + o);
-                        const double omc = __ldg(DBx + o).y;
-                        const double wt = wind_flag(W, mc.wpt);
-                        vLead = add(0.0, a.sw.leadloss ? -mul(mul(mul(mul(mul(wt, mc.llf), a.k.deltaT), h.x), W), omc) : 0.0);
-                        vAtm = add(0.0, a.sw.atmloss ? atm_loss(wt, h.x, W, mc, a.k) : 0.0);
-                        double wpl = 0.0, wpg = 0.0, wpn = 0.0;
-                        if (a.sw.windpack) wind_packing(wt, h.x, mc, a.k, wpl, wpg, wpn);
-                        vWpl = add(0.0, wpl);
-                        vWpg = add(0.0, wpg);
-                        vWp = add(0.0, wpn);
-                    }
-                    if (want(V_ACC)) st_out(outp(V_ACC, x + 1) + o, cum[q].x);
-                    if (want(V_OCEAN)) st_out(outp(V_OCEAN, x + 1) + o, cum[q].y);
-                    if (want(V_LEAD)) st_out(outp(V_LEAD, x + 1) + o, vLead);
-                    if (want(V_ATM)) st_out(outp(V_ATM, x + 1) + o, vAtm);
-                    if (want(V_WPL)) st_out(outp(V_WPL, x + 1) + o, vWpl);
-                    if (want(V_WPG)) st_out(outp(V_WPG, x + 1) + o, vWpg);
-                    if (want(V_WP)) st_out(outp(V_WP, x + 1) + o, vWp);
-                    if (want(V_ADV)) st_out(outp(V_ADV, x + 1) + o, landAdv);
-                    if (want(V_DIV)) st_out(outp(V_DIV, x + 1) + o, landAdv);
-                    if (want(V_H0)) st_out(outp(V_H0, x + 1) + o, nan);
-                    if (want(V_H1)) st_out(outp(V_H1, x + 1) + o, nan);
-                    if (want(V_DENS)) st_out(outp(V_DENS, x + 1) + o, nan);
-                }
-            }
+            ENS_TICK(4)   // staging issue + owned-cell stores
             if (STAGE) cp_async_wait_all();
+            ENS_TICK(6)   // staged copies landed
             cluster_wait_acquire();   // day x+1 tiles (own rows and pushed halos) are complete; raw tiles are free
+            ENS_TICK(7)   // wait for the cluster
         }
     }
+#undef ENS_TICK
+    if (timing)
+        for (int q = 0; q < 8; ++q) a.timing[(long long)blockIdx.x * 8 + q] = tacc[q];
 }
 
 // host-side state of this path

@@ -328,7 +328,7 @@ int build_strip_tables(nesosim_ctx *ctx) {
     for (int r = 0; r < ny; ++r) {
         int oc = 0;
         for (int c = 0; c < nx; ++c) oc += !land(r, c);
-        cum[r + 1] = cum[r] + oc * 1.0 + (nx - oc) * 0.12 + 0.05 * nx;
+        cum[r + 1] = cum[r] + oc * 1.0 + (nx - oc) * 0.3 + 0.05 * nx;
     }
     int best[3] = {0, 0, 0};
     double best_cost = 1e300;
@@ -350,7 +350,7 @@ int build_strip_tables(nesosim_ctx *ctx) {
     StripTables &t = e.tables;
     t.row0[0] = 0; t.row0[1] = best[0]; t.row0[2] = best[1]; t.row0[3] = best[2]; t.row0[4] = ny;
     std::vector<unsigned short> codes;
-    int max_ocean = 0, max_raw = 0, max_rows = 0;
+    int max_ocean = 0, max_raw = 0, max_rows = 0, max_land = 0;
     for (int k = 0; k < ENS_CLUSTER; ++k) {
         const int ra = t.row0[k], rb = t.row0[k + 1];
         std::vector<unsigned short> ri, re, oc, la;
@@ -379,6 +379,7 @@ int build_strip_tables(nesosim_ctx *ctx) {
         max_rows = std::max(max_rows, rb - ra);
         append(oc, t.ocean_off[k], t.ocean_n[k]);
         append(la, t.land_off[k], t.land_n[k]);
+        max_land = std::max(max_land, (int)la.size());
         max_ocean = std::max(max_ocean, (int)oc.size());
     }
     codes.push_back(0);
@@ -388,7 +389,11 @@ int build_strip_tables(nesosim_ctx *ctx) {
     t.rows_alloc = max_rows;
     // stage the drift terms in shared memory when the tiles leave room for the longest raw list
     const size_t smem_cap = 227 * 1024;
-    t.stage_alloc = (ens_smem_bytes(max_rows, max_raw) <= smem_cap && !getenv("NESOSIM_ENS_NOSTAGE")) ? max_raw : 0;
+    t.raw_alloc = max_raw;
+    t.land_alloc = max_land;
+    const int n_codes = (max_raw + 7) / 8 * 8 + max_land;
+    t.stage_alloc = (ens_smem_bytes(max_rows, max_raw, n_codes) <= smem_cap && !getenv("NESOSIM_ENS_NOSTAGE")) ? max_raw : 0;
+    if (ens_smem_bytes(max_rows, t.stage_alloc, n_codes) > smem_cap) return fail(NESOSIM_ERR_ARG, "strip tiles exceed shared memory");
     e.ko_needed = std::max(1, (max_ocean + ENS_NT - 1) / ENS_NT);
     e.tables_ready = true;
     return NESOSIM_OK;
@@ -450,7 +455,8 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     bool all = true;
     for (int vv = 0; vv < NVAR; ++vv) all = all && (out_base(out, vv) != nullptr);
     void (*kernel)(const EnsArgs) = v->kernel[all ? 1 : 0][e.tables.stage_alloc > 0 ? 1 : 0];
-    const size_t smem_bytes = ens_smem_bytes(e.tables.rows_alloc, e.tables.stage_alloc);
+    const size_t smem_bytes = ens_smem_bytes(e.tables.rows_alloc, e.tables.stage_alloc,
+                                             (e.tables.raw_alloc + 7) / 8 * 8 + e.tables.land_alloc);
     CU(cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     int max_clusters = 0;
     {
@@ -486,9 +492,28 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     std::memcpy(a.w, c.conv_weights, sizeof(a.w));
     a.sw = Switches{c.dynamicsInc == 1, c.leadlossInc == 1, c.windpackInc == 1, c.atmlossInc == 1, 0};
     a.st = e.tables;
+    a.timing = nullptr;
+    const bool dbg_timing = getenv("NESOSIM_ENS_TIMING") != nullptr;   // debug aid: per-phase cycle totals to stderr
+    if (dbg_timing) {
+        CU(cudaMalloc(&a.timing, sizeof(long long) * 8 * ncl * ENS_CLUSTER));
+        CU(cudaMemset(a.timing, 0, sizeof(long long) * 8 * ncl * ENS_CLUSTER));
+    }
     kernel<<<ncl * ENS_CLUSTER, ENS_NT, smem_bytes, st>>>(a);
     ctx->launches++;
     CU(cudaGetLastError());
+    if (dbg_timing) {
+        std::vector<long long> h(8 * ncl * ENS_CLUSTER);
+        CU(cudaMemcpy(h.data(), a.timing, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(a.timing);
+        static const char *names[8] = {"phaseA", "cta_sync", "phaseB", "arrive", "own_stores", "land_stores", "cp_wait", "cluster_wait"};
+        const double days = (double)(c.num_days - 1) * ((mcount + ncl - 1) / ncl);
+        for (int kk = 0; kk < ENS_CLUSTER; ++kk) {
+            fprintf(stderr, "[ens timing] clusters=%d strip %d rows %d ocean %d land %d raw %d | cycles/day:", ncl, kk,
+                    e.tables.row0[kk + 1] - e.tables.row0[kk], e.tables.ocean_n[kk], e.tables.land_n[kk], e.tables.raw_n[kk]);
+            for (int q = 0; q < 8; ++q) fprintf(stderr, " %s=%.0f", names[q], h[kk * 8 + q] / days);
+            fprintf(stderr, "\n");
+        }
+    }
     return NESOSIM_OK;
 }
 
