@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -300,103 +301,18 @@ int launch_init(nesosim_ctx *ctx, const double *ic, int ic_per_member, const dou
 struct EnsVariant {
     const char *name;
     int ko;
-    void (*kernel[2][2])(const EnsArgs);  // [all twelve outputs requested][drift terms staged in shared memory]
+    void (*kernel)(const EnsArgs);
 };
 
 const EnsVariant *ens_variants(int *n) {
     static const EnsVariant v[] = {
-#define ENS_V(K) {{ensemble_season_kernel<K, false, false>, ensemble_season_kernel<K, false, true>}, \
-                  {ensemble_season_kernel<K, true, false>, ensemble_season_kernel<K, true, true>}}
-        {"ko2", 2, ENS_V(2)},
-        {"ko3", 3, ENS_V(3)},
-        {"ko5", 5, ENS_V(5)},
-#undef ENS_V
+        {"ko1", 1, ensemble_season_kernel<1>},
+        {"ko2", 2, ensemble_season_kernel<2>},
+        {"ko3", 3, ensemble_season_kernel<3>},
+        {"ko5", 5, ensemble_season_kernel<5>},
     };
     *n = (int)(sizeof(v) / sizeof(v[0]));
     return v;
-}
-
-// Cut the grid into ENS_CLUSTER row strips with balanced work (ocean cells dominate; land cells and rows carry a
-// small cost) and compile the mask into the per-strip cell lists the kernel walks.
-int build_strip_tables(nesosim_ctx *ctx) {
-    EnsembleState &e = ctx->ens;
-    if (e.tables_ready) return NESOSIM_OK;
-    const int ny = ctx->cfg.ny, nx = ctx->cfg.nx;
-    const std::vector<uint8_t> &mask = ctx->mask_host;
-    auto land = [&](int r, int c) { const uint8_t m = mask[(size_t)r * nx + c]; return m > 10 || m < 1; };
-    std::vector<double> cum(ny + 1, 0.0);
-    for (int r = 0; r < ny; ++r) {
-        int oc = 0;
-        for (int c = 0; c < nx; ++c) oc += !land(r, c);
-        cum[r + 1] = cum[r] + oc * 1.0 + (nx - oc) * 0.3 + 0.05 * nx;
-    }
-    int best[3] = {0, 0, 0};
-    double best_cost = 1e300;
-    const int minr = 2;
-    for (int b1 = minr; b1 <= ny - 3 * minr; ++b1) {
-        if (b1 > ENS_MAXR) break;
-        for (int b2 = b1 + minr; b2 <= ny - 2 * minr; ++b2) {
-            if (b2 - b1 > ENS_MAXR) break;
-            for (int b3 = b2 + minr; b3 <= ny - minr; ++b3) {
-                if (b3 - b2 > ENS_MAXR) break;
-                if (ny - b3 > ENS_MAXR) continue;
-                const double c0 = cum[b1], c1 = cum[b2] - cum[b1], c2 = cum[b3] - cum[b2], c3 = cum[ny] - cum[b3];
-                const double mx = std::max(std::max(c0, c1), std::max(c2, c3));
-                if (mx < best_cost) { best_cost = mx; best[0] = b1; best[1] = b2; best[2] = b3; }
-            }
-        }
-    }
-    if (best_cost >= 1e300) return fail(NESOSIM_ERR_ARG, "grid cannot be cut into 4 strips of 2..28 rows");
-    StripTables &t = e.tables;
-    t.row0[0] = 0; t.row0[1] = best[0]; t.row0[2] = best[1]; t.row0[3] = best[2]; t.row0[4] = ny;
-    std::vector<unsigned short> codes;
-    int max_ocean = 0, max_raw = 0, max_rows = 0, max_land = 0;
-    for (int k = 0; k < ENS_CLUSTER; ++k) {
-        const int ra = t.row0[k], rb = t.row0[k + 1];
-        std::vector<unsigned short> ri, re, oc, la;
-        for (int r = std::max(ra - 1, 0); r <= std::min(rb, ny - 1); ++r)
-            for (int c = 0; c < nx; ++c) {
-                bool needed = false;   // some ocean cell of this strip has (r,c) in its 3x3 neighbourhood
-                for (int rr = std::max(r - 1, ra); rr <= std::min(r + 1, rb - 1) && !needed; ++rr)
-                    for (int cc = std::max(c - 1, 0); cc <= std::min(c + 1, nx - 1); ++cc)
-                        if (!land(rr, cc)) { needed = true; break; }
-                if (!needed) continue;
-                const bool edge = (r == 0 || r == ny - 1 || c == 0 || c == nx - 1);
-                (edge ? re : ri).push_back((unsigned short)(r * 128 + c));
-            }
-        for (int r = ra; r < rb; ++r)
-            for (int c = 0; c < nx; ++c) (land(r, c) ? la : oc).push_back((unsigned short)((r - ra) * 128 + c));
-        auto append = [&](const std::vector<unsigned short> &v, int &off, int &n) {
-            while (codes.size() % 8) codes.push_back(0);
-            off = (int)codes.size();
-            n = (int)v.size();
-            codes.insert(codes.end(), v.begin(), v.end());
-        };
-        t.raw_int_n[k] = (int)ri.size();
-        ri.insert(ri.end(), re.begin(), re.end());           // interior entries first, then the edge entries
-        append(ri, t.raw_off[k], t.raw_n[k]);
-        max_raw = std::max(max_raw, t.raw_n[k]);
-        max_rows = std::max(max_rows, rb - ra);
-        append(oc, t.ocean_off[k], t.ocean_n[k]);
-        append(la, t.land_off[k], t.land_n[k]);
-        max_land = std::max(max_land, (int)la.size());
-        max_ocean = std::max(max_ocean, (int)oc.size());
-    }
-    codes.push_back(0);
-    CU(cudaMalloc(&e.codes_dev, codes.size() * sizeof(unsigned short)));
-    CU(cudaMemcpy(e.codes_dev, codes.data(), codes.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
-    t.codes = e.codes_dev;
-    t.rows_alloc = max_rows;
-    // stage the drift terms in shared memory when the tiles leave room for the longest raw list
-    const size_t smem_cap = 227 * 1024;
-    t.raw_alloc = max_raw;
-    t.land_alloc = max_land;
-    const int n_codes = (max_raw + 7) / 8 * 8 + max_land;
-    t.stage_alloc = (ens_smem_bytes(max_rows, max_raw, n_codes) <= smem_cap && !getenv("NESOSIM_ENS_NOSTAGE")) ? max_raw : 0;
-    if (ens_smem_bytes(max_rows, t.stage_alloc, n_codes) > smem_cap) return fail(NESOSIM_ERR_ARG, "strip tiles exceed shared memory");
-    e.ko_needed = std::max(1, (max_ocean + ENS_NT - 1) / ENS_NT);
-    e.tables_ready = true;
-    return NESOSIM_OK;
 }
 
 const EnsVariant *pick_variant(int ko_needed) {
@@ -410,16 +326,140 @@ const EnsVariant *pick_variant(int ko_needed) {
     return nullptr;
 }
 
-// The kernel keeps a whole member on one 4-CTA cluster: strips of up to 28 rows, rows of at most 96 columns.
-bool ensemble_eligible(nesosim_ctx *ctx, int first_step, int num_steps, const char **why) {
+constexpr size_t ENS_SMEM_CAP = 227 * 1024;
+
+// Cut the grid into `cl` row strips with balanced work and compile the mask into the per-strip cell lists the
+// kernel walks.  A strip must satisfy the bulk-copy rules (16-byte aligned start, 16-byte multiple size), hold
+// at least the two rows its neighbours need as halo, and fit the per-thread list capacities.
+// Returns false if no such cut exists for this cluster size.
+bool try_strip_tables(nesosim_ctx *ctx, int cl, StripTables &t, std::vector<unsigned short> &codes, int &ko_needed,
+                      size_t &smem_bytes) {
+    const int ny = ctx->cfg.ny, nx = ctx->cfg.nx;
+    const std::vector<uint8_t> &mask = ctx->mask_host;
+    auto land = [&](int r, int c) { const uint8_t m = mask[(size_t)r * nx + c]; return m > 10 || m < 1; };
+    if (ny < 2 * cl) return false;
+    // per-row ocean count and count of cells with an ocean cell in their 3x3 neighbourhood
+    std::vector<int> oc(ny, 0), dil(ny, 0);
+    for (int r = 0; r < ny; ++r)
+        for (int c = 0; c < nx; ++c) {
+            oc[r] += !land(r, c);
+            bool near = false;
+            for (int rr = std::max(r - 1, 0); rr <= std::min(r + 1, ny - 1) && !near; ++rr)
+                for (int cc = std::max(c - 1, 0); cc <= std::min(c + 1, nx - 1); ++cc)
+                    if (!land(rr, cc)) { near = true; break; }
+            dil[r] += near;
+        }
+    std::vector<long long> coc(ny + 1, 0), cdil(ny + 1, 0);
+    for (int r = 0; r < ny; ++r) { coc[r + 1] = coc[r] + oc[r]; cdil[r + 1] = cdil[r] + dil[r]; }
+    const int max_rows_smem = [&] {   // tallest strip whose tiles fit in shared memory (lists sized generously)
+        int best = 0;
+        for (int rows = 2; rows <= ny; ++rows)
+            if (ens_smem_bytes(rows, nx, (rows + 2) * nx + rows * nx + 16) <= ENS_SMEM_CAP) best = rows;
+        return best;
+    }();
+    auto strip_cost = [&](int ra, int rb) -> double {   // < 0: not allowed
+        const int rows = rb - ra;
+        if (rows < 2 || rows > max_rows_smem) return -1.0;
+        if (((long long)rows * nx) % 2 || ((long long)ra * nx) % 2) return -1.0;
+        const long long ocean = coc[rb] - coc[ra];
+        const long long raw = cdil[std::min(rb + 1, ny)] - cdil[std::max(ra - 1, 0)];
+        if (ocean > 5 * ENS_NT || raw > ENS_KR * ENS_NT) return -1.0;
+        return 11.0 * ocean + 4.5 * raw + 0.6 * rows * nx;   // cycles per day measured on B200 (phase timers)
+    };
+    const double INF = 1e300;
+    std::vector<std::vector<double>> best(cl + 1, std::vector<double>(ny + 1, INF));
+    std::vector<std::vector<int>> from(cl + 1, std::vector<int>(ny + 1, -1));
+    best[0][0] = 0.0;
+    for (int k = 1; k <= cl; ++k)
+        for (int r = 2 * k; r <= ny; ++r)
+            for (int q = 2 * (k - 1); q <= r - 2; ++q) {
+                if (best[k - 1][q] >= INF) continue;
+                const double c = strip_cost(q, r);
+                if (c < 0) continue;
+                const double v = std::max(best[k - 1][q], c);
+                if (v < best[k][r]) { best[k][r] = v; from[k][r] = q; }
+            }
+    if (best[cl][ny] >= INF) return false;
+    t = StripTables{};
+    t.cluster = cl;
+    for (int k = cl, r = ny; k >= 1; --k) { t.row0[k] = r; r = from[k][r]; }
+    t.row0[0] = 0;
+    codes.clear();
+    int max_ocean = 0, max_raw = 0, max_rows = 0, max_land = 0;
+    for (int k = 0; k < cl; ++k) {
+        const int ra = t.row0[k], rb = t.row0[k + 1];
+        std::vector<unsigned short> ri, re, ocl, la;
+        for (int r = std::max(ra - 1, 0); r <= std::min(rb, ny - 1); ++r)
+            for (int c = 0; c < nx; ++c) {
+                bool needed = false;   // some ocean cell of this strip has (r,c) in its 3x3 neighbourhood
+                for (int rr = std::max(r - 1, ra); rr <= std::min(r + 1, rb - 1) && !needed; ++rr)
+                    for (int cc = std::max(c - 1, 0); cc <= std::min(c + 1, nx - 1); ++cc)
+                        if (!land(rr, cc)) { needed = true; break; }
+                if (!needed) continue;
+                const bool edge = (r == 0 || r == ny - 1 || c == 0 || c == nx - 1);
+                (edge ? re : ri).push_back((unsigned short)(r * 128 + c));
+            }
+        for (int r = ra; r < rb; ++r)
+            for (int c = 0; c < nx; ++c) (land(r, c) ? la : ocl).push_back((unsigned short)((r - ra) * 128 + c));
+        auto append = [&](const std::vector<unsigned short> &v, int &off, int &n) {
+            while (codes.size() % 8) codes.push_back(0);
+            off = (int)codes.size();
+            n = (int)v.size();
+            codes.insert(codes.end(), v.begin(), v.end());
+        };
+        t.raw_int_n[k] = (int)ri.size();
+        ri.insert(ri.end(), re.begin(), re.end());           // interior entries first, then the edge entries
+        append(ri, t.raw_off[k], t.raw_n[k]);
+        append(ocl, t.ocean_off[k], t.ocean_n[k]);
+        append(la, t.land_off[k], t.land_n[k]);
+        max_raw = std::max(max_raw, t.raw_n[k]);
+        max_rows = std::max(max_rows, rb - ra);
+        max_land = std::max(max_land, (int)la.size());
+        max_ocean = std::max(max_ocean, (int)ocl.size());
+    }
+    codes.push_back(0);
+    if (max_raw > ENS_KR * ENS_NT) return false;
+    t.rows_alloc = max_rows;
+    t.raw_alloc = max_raw;
+    t.land_alloc = max_land;
+    smem_bytes = ens_smem_bytes(max_rows, nx, (max_raw + 7) / 8 * 8 + max_land);
+    if (smem_bytes > ENS_SMEM_CAP) return false;
+    ko_needed = std::max(1, (max_ocean + ENS_NT - 1) / ENS_NT);
+    return pick_variant(ko_needed) != nullptr;
+}
+
+int build_strip_tables(nesosim_ctx *ctx) {
+    EnsembleState &e = ctx->ens;
+    if (e.tables_ready) return NESOSIM_OK;
+    int forced = 0;
+    if (const char *env = getenv("NESOSIM_ENS_CLUSTER")) forced = atoi(env);
+    std::vector<unsigned short> codes;
+    bool ok = false;
+    for (int cl : {4, 8}) {
+        if (forced && cl != forced) continue;
+        if (try_strip_tables(ctx, cl, e.tables, codes, e.ko_needed, e.smem_bytes)) { ok = true; break; }
+    }
+    if (!ok) return fail(NESOSIM_ERR_ARG, "grid does not fit the season-resident kernel's shared-memory strips");
+    CU(cudaMalloc(&e.codes_dev, codes.size() * sizeof(unsigned short)));
+    CU(cudaMemcpy(e.codes_dev, codes.data(), codes.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    e.tables.codes = e.codes_dev;
+    e.tables_ready = true;
+    return NESOSIM_OK;
+}
+
+// The kernel keeps a whole member on one 4- or 8-CTA cluster: rows of at most 96 columns, strips that fit in
+// shared memory, 16-byte aligned planes for the bulk stores.
+bool ensemble_eligible(nesosim_ctx *ctx, int first_step, int num_steps, const nesosim_outputs *out, const char **why) {
     const nesosim_config &c = ctx->cfg;
     if (c.nx > ENS_MAX_NX) { *why = "nx > 96"; return false; }
-    if (c.ny > ENS_CLUSTER * ENS_MAXR) { *why = "ny > 112"; return false; }
-    if (c.ny < 2 * ENS_CLUSTER) { *why = "ny < 8"; return false; }
+    if (c.ny < 8) { *why = "ny < 8"; return false; }
+    if (((long long)c.ny * c.nx) % 2) { *why = "odd number of cells (bulk stores need 16-byte aligned planes)"; return false; }
     if (c.density_clim) { *why = "densityType='clim'"; return false; }
     if (first_step != 0 || num_steps != c.num_days - 1) { *why = "partial season"; return false; }
-    if (build_strip_tables(ctx) != NESOSIM_OK) { *why = "strip tables"; return false; }
-    if (!pick_variant(ctx->ens.ko_needed)) { *why = "too many ocean cells per strip"; return false; }
+    for (int v = 0; v < NVAR; ++v)
+        if (out_base(out, v) && ((uintptr_t)out_base(out, v) % 16)) { *why = "output array not 16-byte aligned"; return false; }
+    if ((out->depth_member_stride % 2) || (out->plane_member_stride % 2)) { *why = "odd member stride"; return false; }
+    if (build_strip_tables(ctx) != NESOSIM_OK) { *why = "no strip decomposition fits"; return false; }
     return true;
 }
 
@@ -452,25 +492,21 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     CU(cudaGetLastError());
 
     const EnsVariant *v = pick_variant(e.ko_needed);
-    bool all = true;
-    for (int vv = 0; vv < NVAR; ++vv) all = all && (out_base(out, vv) != nullptr);
-    void (*kernel)(const EnsArgs) = v->kernel[all ? 1 : 0][e.tables.stage_alloc > 0 ? 1 : 0];
-    const size_t smem_bytes = ens_smem_bytes(e.tables.rows_alloc, e.tables.stage_alloc,
-                                             (e.tables.raw_alloc + 7) / 8 * 8 + e.tables.land_alloc);
-    CU(cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    const int cl = e.tables.cluster;
+    void (*kernel)(const EnsArgs) = v->kernel;
+    CU(cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem_bytes));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.blockDim = dim3(ENS_NT);
+    cfg.dynamicSmemBytes = e.smem_bytes;
+    cfg.stream = st;
     int max_clusters = 0;
-    {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(ENS_CLUSTER * 64);
-        cfg.blockDim = dim3(ENS_NT);
-        cfg.dynamicSmemBytes = smem_bytes;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = ENS_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        CU(cudaOccupancyMaxActiveClusters(&max_clusters, (const void *)kernel, &cfg));
-    }
-    if (max_clusters < 1) return fail(NESOSIM_ERR_CUDA, "no 4-CTA cluster fits on this device");
+    cfg.gridDim = dim3(cl * 64);
+    CU(cudaOccupancyMaxActiveClusters(&max_clusters, (const void *)kernel, &cfg));
+    if (max_clusters < 1) return fail(NESOSIM_ERR_CUDA, "no cluster of this size fits on the device");
     if (const char *envc = getenv("NESOSIM_ENS_CLUSTERS")) max_clusters = std::max(1, std::min(max_clusters, atoi(envc)));
     e.max_clusters = max_clusters;
     const int ncl = std::min(max_clusters, mcount);
@@ -495,22 +531,24 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     a.timing = nullptr;
     const bool dbg_timing = getenv("NESOSIM_ENS_TIMING") != nullptr;   // debug aid: per-phase cycle totals to stderr
     if (dbg_timing) {
-        CU(cudaMalloc(&a.timing, sizeof(long long) * 8 * ncl * ENS_CLUSTER));
-        CU(cudaMemset(a.timing, 0, sizeof(long long) * 8 * ncl * ENS_CLUSTER));
+        CU(cudaMalloc(&a.timing, sizeof(long long) * 8 * ncl * cl));
+        CU(cudaMemset(a.timing, 0, sizeof(long long) * 8 * ncl * cl));
     }
-    kernel<<<ncl * ENS_CLUSTER, ENS_NT, smem_bytes, st>>>(a);
+    cfg.gridDim = dim3(ncl * cl);
+    CU(cudaLaunchKernelEx(&cfg, kernel, a));
     ctx->launches++;
     CU(cudaGetLastError());
     if (dbg_timing) {
-        std::vector<long long> h(8 * ncl * ENS_CLUSTER);
+        std::vector<long long> h(8 * ncl * cl);
         CU(cudaMemcpy(h.data(), a.timing, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(a.timing);
-        static const char *names[8] = {"phaseA", "cta_sync", "phaseB", "arrive", "own_stores", "land_stores", "cp_wait", "cluster_wait"};
+        static const char *names[8] = {"phaseA", "bulk_drain", "cta_sync", "phaseB", "arrive_sync", "issue_copy", "cluster_wait", "-"};
         const double days = (double)(c.num_days - 1) * ((mcount + ncl - 1) / ncl);
-        for (int kk = 0; kk < ENS_CLUSTER; ++kk) {
-            fprintf(stderr, "[ens timing] clusters=%d strip %d rows %d ocean %d land %d raw %d | cycles/day:", ncl, kk,
-                    e.tables.row0[kk + 1] - e.tables.row0[kk], e.tables.ocean_n[kk], e.tables.land_n[kk], e.tables.raw_n[kk]);
-            for (int q = 0; q < 8; ++q) fprintf(stderr, " %s=%.0f", names[q], h[kk * 8 + q] / days);
+        for (int kk = 0; kk < cl; ++kk) {
+            fprintf(stderr, "[ens timing] %s cluster=%d x %d smem=%zu strip %d rows %d ocean %d land %d raw %d | cycles/day:", v->name, cl,
+                    ncl, e.smem_bytes, kk, e.tables.row0[kk + 1] - e.tables.row0[kk], e.tables.ocean_n[kk], e.tables.land_n[kk],
+                    e.tables.raw_n[kk]);
+            for (int q = 0; q < 7; ++q) fprintf(stderr, " %s=%.0f", names[q], h[kk * 8 + q] / days);
             fprintf(stderr, "\n");
         }
     }
@@ -525,7 +563,7 @@ int run_members(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, const
     if (first_step < 0 || first_step + num_steps > T - 1) return fail(NESOSIM_ERR_ARG, "step range outside the season");
     int rc;
     const char *why = "";
-    const bool can_ens = ensemble_eligible(ctx, first_step, num_steps, &why);
+    const bool can_ens = ensemble_eligible(ctx, first_step, num_steps, out, &why);
     if (ctx->path == 2 && !can_ens)
         return fail(NESOSIM_ERR_ARG, std::string("season-resident ensemble path not applicable: ") + why);
     if (ctx->path != 1 && can_ens) {

@@ -129,13 +129,16 @@ def test_25km_short_season(cuda):
     compare_all(got, refs)
 
 
-@pytest.mark.parametrize("variant", ["ko2", "ko3", "ko5"])
-def test_ensemble_kernel_variants_many_members_per_cluster(cuda, variant, monkeypatch):
+@pytest.mark.parametrize("cluster", ["4", "8"])
+@pytest.mark.parametrize("variant", ["ko1", "ko2", "ko3", "ko5"])
+def test_ensemble_kernel_variants_many_members_per_cluster(cuda, variant, cluster, monkeypatch):
     """Every build variant of the season-resident kernel; 3 clusters share 11 members with per-member ICs."""
     from nesosim_b200.engine import SnowBudgetEngine
     monkeypatch.setenv("NESOSIM_ENS_VARIANT", variant)
     monkeypatch.setenv("NESOSIM_ENS_CLUSTERS", "3")
-    mask = S.region_mask(dx=100000)
+    monkeypatch.setenv("NESOSIM_ENS_CLUSTER", cluster)
+    # 100 km needs 8-CTA clusters (shared memory); a 48x90 cut of it also fits 4-CTA clusters
+    mask = S.region_mask(dx=100000) if cluster == "8" else np.ascontiguousarray(S.region_mask(dx=100000)[20:68])
     T, M = 9, 11
     forcing = S.make_season(mask, T, seed=23)
     rng = np.random.default_rng(23)
