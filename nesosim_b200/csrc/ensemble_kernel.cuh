@@ -95,10 +95,11 @@ __global__ void derive_scan_kernel(const double2 *DB, double2 *DC, long long pla
 // ------------------------------------------------------------------------------------ the season kernel
 
 constexpr int ENS_MAX_CLUSTER = 8;
-constexpr int ENS_NT = 512;            // 16 warps
+constexpr int ENS_NT = 512;            // default CTA size (16 warps); the kernel is templated on it
 constexpr int ENS_SXR = 98;            // raw tile row stride; column c lives at c+1 (zero pad each side)
 constexpr int ENS_MAX_NX = 96;
-constexpr int ENS_KR = 3;              // raw-list entries per thread (capacity 3*512 per strip)
+constexpr int ENS_MAX_OCEAN = 1024;    // per-strip capacities of the largest kernel variant
+constexpr int ENS_MAX_RAW = 1536;
 constexpr int ENS_NPLANE = 10;         // staged output planes: h0, h1, density, adv, div, lead, atm, wpl, wpg, wp
 
 // plane index -> output variable
@@ -161,10 +162,10 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // generic-proxy writes to shared memory must be fenced before the async proxy (TMA) reads them
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// KO = owned ocean cells per thread (capacity KO*512 per strip).
-template <int KO>
-__global__ void __launch_bounds__(ENS_NT, 1) ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
-    constexpr int NT = ENS_NT, SXR = ENS_SXR, KR = ENS_KR;
+// NT threads per CTA; KO owned ocean cells and KR raw-list entries per thread (capacities KO*NT, KR*NT per strip).
+template <int NT, int KO, int KR>
+__global__ void __launch_bounds__(NT, 1) ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
+    constexpr int SXR = ENS_SXR;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int ny = a.ny, nx = a.nx, CL = a.st.cluster;
     const int RA = a.st.rows_alloc;
@@ -482,10 +483,21 @@ __global__ void __launch_bounds__(ENS_NT, 1) ensemble_season_kernel(const __grid
                 const double2 *DCx = a.DC + (long long)x * plane + (long long)ra * nx;
                 double *pa_ = a.out[V_ACC] ? outp(V_ACC, x + 1) : nullptr;
                 double *po_ = a.out[V_OCEAN] ? outp(V_OCEAN, x + 1) : nullptr;
-                for (int i = tid; i < ncell; i += NT) {
-                    const double2 cum = __ldg(DCx + i);
-                    if (pa_) __stcs(pa_ + i, cum.x);
-                    if (po_) __stcs(po_ + i, cum.y);
+                for (int base = 0; base < ncell; base += 4 * NT) {   // all loads of a batch in flight before the stores
+                    double2 cum[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int i = base + q * NT + tid;
+                        cum[q] = (i < ncell) ? __ldg(DCx + i) : make_double2(0.0, 0.0);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int i = base + q * NT + tid;
+                        if (i < ncell) {
+                            if (pa_) __stcs(pa_ + i, cum[q].x);
+                            if (po_) __stcs(po_ + i, cum[q].y);
+                        }
+                    }
                 }
             }
             if (x + 1 < steps) load_cell_inputs(x + 1);
@@ -508,7 +520,7 @@ struct EnsembleState {
     unsigned short *codes_dev = nullptr;
     StripTables tables;
     bool tables_ready = false;
-    int ko_needed = 0;                 // ceil(max ocean cells per strip / ENS_NT)
+    int max_ocean = 0, max_raw = 0;    // longest ocean / raw list of any strip (selects the kernel variant)
     size_t smem_bytes = 0;
     int max_clusters = 0;
 };

@@ -300,29 +300,32 @@ int launch_init(nesosim_ctx *ctx, const double *ic, int ic_per_member, const dou
 
 struct EnsVariant {
     const char *name;
-    int ko;
+    int nt, ko, kr;                       // threads per CTA, owned ocean cells and raw-list entries per thread
     void (*kernel)(const EnsArgs);
 };
 
+// every entry compiles without register spills (checked with -Xptxas -v); more threads first
 const EnsVariant *ens_variants(int *n) {
     static const EnsVariant v[] = {
-        {"ko1", 1, ensemble_season_kernel<1>},
-        {"ko2", 2, ensemble_season_kernel<2>},
-        {"ko3", 3, ensemble_season_kernel<3>},
-        {"ko5", 5, ensemble_season_kernel<5>},
+        {"t512k1", 512, 1, 2, ensemble_season_kernel<512, 1, 2>},
+        {"t384k2", 384, 2, 3, ensemble_season_kernel<384, 2, 3>},
+        {"t256k2", 256, 2, 3, ensemble_season_kernel<256, 2, 3>},
+        {"t256k3", 256, 3, 4, ensemble_season_kernel<256, 3, 4>},
+        {"t256k4", 256, 4, 6, ensemble_season_kernel<256, 4, 6>},
     };
     *n = (int)(sizeof(v) / sizeof(v[0]));
     return v;
 }
 
-const EnsVariant *pick_variant(int ko_needed) {
+const EnsVariant *pick_variant(int max_ocean, int max_raw) {
     int n;
     const EnsVariant *v = ens_variants(&n);
+    auto fits = [&](const EnsVariant &e) { return e.ko * e.nt >= max_ocean && e.kr * e.nt >= max_raw; };
     if (const char *env = getenv("NESOSIM_ENS_VARIANT"))
         for (int i = 0; i < n; ++i)
-            if (!strcmp(env, v[i].name) && v[i].ko >= ko_needed) return &v[i];
+            if (!strcmp(env, v[i].name) && fits(v[i])) return &v[i];
     for (int i = 0; i < n; ++i)
-        if (v[i].ko >= ko_needed) return &v[i];
+        if (fits(v[i])) return &v[i];
     return nullptr;
 }
 
@@ -332,8 +335,8 @@ constexpr size_t ENS_SMEM_CAP = 227 * 1024;
 // kernel walks.  A strip must satisfy the bulk-copy rules (16-byte aligned start, 16-byte multiple size), hold
 // at least the two rows its neighbours need as halo, and fit the per-thread list capacities.
 // Returns false if no such cut exists for this cluster size.
-bool try_strip_tables(nesosim_ctx *ctx, int cl, StripTables &t, std::vector<unsigned short> &codes, int &ko_needed,
-                      size_t &smem_bytes) {
+bool try_strip_tables(nesosim_ctx *ctx, int cl, StripTables &t, std::vector<unsigned short> &codes, int &max_ocean_out,
+                      int &max_raw_out, size_t &smem_bytes, double &day_cost) {
     const int ny = ctx->cfg.ny, nx = ctx->cfg.nx;
     const std::vector<uint8_t> &mask = ctx->mask_host;
     auto land = [&](int r, int c) { const uint8_t m = mask[(size_t)r * nx + c]; return m > 10 || m < 1; };
@@ -363,7 +366,7 @@ bool try_strip_tables(nesosim_ctx *ctx, int cl, StripTables &t, std::vector<unsi
         if (((long long)rows * nx) % 2 || ((long long)ra * nx) % 2) return -1.0;
         const long long ocean = coc[rb] - coc[ra];
         const long long raw = cdil[std::min(rb + 1, ny)] - cdil[std::max(ra - 1, 0)];
-        if (ocean > 5 * ENS_NT || raw > ENS_KR * ENS_NT) return -1.0;
+        if (ocean > ENS_MAX_OCEAN || raw > ENS_MAX_RAW) return -1.0;
         return 11.0 * ocean + 4.5 * raw + 0.6 * rows * nx;   // cycles per day measured on B200 (phase timers)
     };
     const double INF = 1e300;
@@ -418,36 +421,79 @@ bool try_strip_tables(nesosim_ctx *ctx, int cl, StripTables &t, std::vector<unsi
         max_ocean = std::max(max_ocean, (int)ocl.size());
     }
     codes.push_back(0);
-    if (max_raw > ENS_KR * ENS_NT) return false;
     t.rows_alloc = max_rows;
     t.raw_alloc = max_raw;
     t.land_alloc = max_land;
     smem_bytes = ens_smem_bytes(max_rows, nx, (max_raw + 7) / 8 * 8 + max_land);
     if (smem_bytes > ENS_SMEM_CAP) return false;
-    ko_needed = std::max(1, (max_ocean + ENS_NT - 1) / ENS_NT);
-    return pick_variant(ko_needed) != nullptr;
+    max_ocean_out = max_ocean;
+    max_raw_out = max_raw;
+    day_cost = best[cl][ny];
+    return pick_variant(max_ocean, max_raw) != nullptr;
 }
 
+int max_active_clusters(const EnsVariant *v, int cl, size_t smem_bytes) {
+    if (cudaFuncSetAttribute((const void *)v->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.blockDim = dim3(v->nt);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.gridDim = dim3(cl * 64);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, (const void *)v->kernel, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// Choose the cluster size (CTAs per member): every size whose strips fit in shared memory is costed as
+// rounds(members / co-resident clusters) x (heaviest strip + fixed per-day overhead), the cheapest wins.
 int build_strip_tables(nesosim_ctx *ctx) {
     EnsembleState &e = ctx->ens;
     if (e.tables_ready) return NESOSIM_OK;
     int forced = 0;
     if (const char *env = getenv("NESOSIM_ENS_CLUSTER")) forced = atoi(env);
-    std::vector<unsigned short> codes;
-    bool ok = false;
-    for (int cl : {4, 8}) {
+    std::vector<unsigned short> best_codes;
+    double best_time = 1e300;
+    for (int cl = 2; cl <= ENS_MAX_CLUSTER; ++cl) {
         if (forced && cl != forced) continue;
-        if (try_strip_tables(ctx, cl, e.tables, codes, e.ko_needed, e.smem_bytes)) { ok = true; break; }
+        StripTables t;
+        std::vector<unsigned short> codes;
+        int mo = 0, mr = 0;
+        size_t smem = 0;
+        double day_cost = 0;
+        if (!try_strip_tables(ctx, cl, t, codes, mo, mr, smem, day_cost)) continue;
+        const EnsVariant *v = pick_variant(mo, mr);
+        const int ncl = max_active_clusters(v, cl, smem);
+        if (ncl < 1) continue;
+        const int rounds = (ctx->cfg.n_members + ncl - 1) / ncl;
+        const double time = rounds * (day_cost + 3000.0);
+        if (time < best_time) {
+            best_time = time;
+            e.tables = t;
+            e.max_ocean = mo;
+            e.max_raw = mr;
+            e.smem_bytes = smem;
+            e.max_clusters = ncl;
+            best_codes.swap(codes);
+        }
     }
-    if (!ok) return fail(NESOSIM_ERR_ARG, "grid does not fit the season-resident kernel's shared-memory strips");
-    CU(cudaMalloc(&e.codes_dev, codes.size() * sizeof(unsigned short)));
-    CU(cudaMemcpy(e.codes_dev, codes.data(), codes.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    if (best_time >= 1e300) return fail(NESOSIM_ERR_ARG, "grid does not fit the season-resident kernel's shared-memory strips");
+    CU(cudaMalloc(&e.codes_dev, best_codes.size() * sizeof(unsigned short)));
+    CU(cudaMemcpy(e.codes_dev, best_codes.data(), best_codes.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
     e.tables.codes = e.codes_dev;
     e.tables_ready = true;
     return NESOSIM_OK;
 }
 
-// The kernel keeps a whole member on one 4- or 8-CTA cluster: rows of at most 96 columns, strips that fit in
+// The kernel keeps a whole member on one cluster of 2..8 CTAs: rows of at most 96 columns, strips that fit in
 // shared memory, 16-byte aligned planes for the bulk stores.
 bool ensemble_eligible(nesosim_ctx *ctx, int first_step, int num_steps, const nesosim_outputs *out, const char **why) {
     const nesosim_config &c = ctx->cfg;
@@ -491,7 +537,7 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     ctx->launches += 2;
     CU(cudaGetLastError());
 
-    const EnsVariant *v = pick_variant(e.ko_needed);
+    const EnsVariant *v = pick_variant(e.max_ocean, e.max_raw);
     const int cl = e.tables.cluster;
     void (*kernel)(const EnsArgs) = v->kernel;
     CU(cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem_bytes));
@@ -500,15 +546,12 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cfg.blockDim = dim3(ENS_NT);
+    cfg.blockDim = dim3(v->nt);
     cfg.dynamicSmemBytes = e.smem_bytes;
     cfg.stream = st;
-    int max_clusters = 0;
-    cfg.gridDim = dim3(cl * 64);
-    CU(cudaOccupancyMaxActiveClusters(&max_clusters, (const void *)kernel, &cfg));
+    int max_clusters = e.max_clusters;
     if (max_clusters < 1) return fail(NESOSIM_ERR_CUDA, "no cluster of this size fits on the device");
     if (const char *envc = getenv("NESOSIM_ENS_CLUSTERS")) max_clusters = std::max(1, std::min(max_clusters, atoi(envc)));
-    e.max_clusters = max_clusters;
     const int ncl = std::min(max_clusters, mcount);
 
     EnsArgs a;

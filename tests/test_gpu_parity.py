@@ -102,12 +102,22 @@ def test_clim_density(cuda):
 
 
 @pytest.mark.parametrize("path", PATHS)
-@pytest.mark.parametrize("shape", [(45, 70), (9, 96), (95, 33)])
+@pytest.mark.parametrize("shape", [(45, 70), (9, 96), (94, 33)])
 def test_ragged_grid_not_multiple_of_tile(cuda, path, shape):
     mask = S.region_mask(shape=shape, kind="disc")
     got, refs = run_both(mask, 10, 50000, [MULTISEASON, ONESEASON], dict(atmlossInc=1), seed=15, ic_scale=3.0,
                          path=path)
     compare_all(got, refs)
+
+
+def test_odd_cell_count_falls_back_to_general_kernel(cuda):
+    """95x33 has an odd number of cells: planes are not 16-byte aligned, so the bulk-store kernel steps aside."""
+    from nesosim_b200 import _lib
+    mask = S.region_mask(shape=(95, 33), kind="disc")
+    got, refs = run_both(mask, 6, 50000, [MULTISEASON], dict(atmlossInc=1), seed=15, expect_path="general")
+    compare_all(got, refs)
+    with pytest.raises(_lib.NesosimError, match="not applicable"):
+        run_both(mask, 6, 50000, [MULTISEASON], dict(atmlossInc=1), seed=15, path="ensemble")
 
 
 def test_minimum_grid_2x2(cuda):
@@ -129,16 +139,16 @@ def test_25km_short_season(cuda):
     compare_all(got, refs)
 
 
-@pytest.mark.parametrize("cluster", ["4", "8"])
-@pytest.mark.parametrize("variant", ["ko1", "ko2", "ko3", "ko5"])
+@pytest.mark.parametrize("cluster", ["4", "5", "6", "8"])
+@pytest.mark.parametrize("variant", ["t512k1", "t384k2", "t256k2", "t256k3", "t256k4"])
 def test_ensemble_kernel_variants_many_members_per_cluster(cuda, variant, cluster, monkeypatch):
     """Every build variant of the season-resident kernel; 3 clusters share 11 members with per-member ICs."""
     from nesosim_b200.engine import SnowBudgetEngine
     monkeypatch.setenv("NESOSIM_ENS_VARIANT", variant)
     monkeypatch.setenv("NESOSIM_ENS_CLUSTERS", "3")
     monkeypatch.setenv("NESOSIM_ENS_CLUSTER", cluster)
-    # 100 km needs 8-CTA clusters (shared memory); a 48x90 cut of it also fits 4-CTA clusters
-    mask = S.region_mask(dx=100000) if cluster == "8" else np.ascontiguousarray(S.region_mask(dx=100000)[20:68])
+    # the full 100 km grid needs >= 5 CTAs per member (shared memory); a 48x90 cut of it also fits 4
+    mask = S.region_mask(dx=100000) if cluster != "4" else np.ascontiguousarray(S.region_mask(dx=100000)[20:68])
     T, M = 9, 11
     forcing = S.make_season(mask, T, seed=23)
     rng = np.random.default_rng(23)
