@@ -162,9 +162,10 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // generic-proxy writes to shared memory must be fenced before the async proxy (TMA) reads them
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// NT threads per CTA; KO owned ocean cells and KR raw-list entries per thread (capacities KO*NT, KR*NT per strip).
+// NT compute threads per CTA (+ one warp that only issues and drains the bulk stores, so nobody who computes
+// ever blocks on the TMA queue); KO owned ocean cells and KR raw-list entries per compute thread.
 template <int NT, int KO, int KR>
-__global__ void __launch_bounds__(NT, 1) ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
+__global__ void __launch_bounds__(NT + 32, 1) ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
     constexpr int SXR = ENS_SXR;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int ny = a.ny, nx = a.nx, CL = a.st.cluster;
@@ -184,6 +185,8 @@ __global__ void __launch_bounds__(NT, 1) ensemble_season_kernel(const __grid_con
     const int ra = a.st.row0[k], rb = a.st.row0[k + 1], nrow = rb - ra;
     const int ncell = nrow * nx;
     const int tid = threadIdx.x;
+    const bool comp = tid < NT;        // compute thread; the last warp is the store warp
+    const bool store_lane = (tid == NT);
     const int steps = a.T - 1;
 
     // neighbours' halo rows through distributed shared memory
@@ -193,9 +196,9 @@ __global__ void __launch_bounds__(NT, 1) ensemble_season_kernel(const __grid_con
 
     const int n_raw_int = a.st.raw_int_n[k], n_raw = a.st.raw_n[k];
     const int n_ocean = a.st.ocean_n[k], n_land = a.st.land_n[k];
-    for (int i = tid; i < n_raw; i += NT) s_raw_code[i] = a.st.codes[a.st.raw_off[k] + i];
-    for (int i = tid; i < n_land; i += NT) s_land_code[i] = a.st.codes[a.st.land_off[k] + i];
-    for (int i = tid; i < (RA + 2) * SXR; i += NT) {   // zero padding of convolve(boundary='fill')
+    for (int i = tid; i < n_raw; i += NT + 32) s_raw_code[i] = a.st.codes[a.st.raw_off[k] + i];
+    for (int i = tid; i < n_land; i += NT + 32) s_land_code[i] = a.st.codes[a.st.land_off[k] + i];
+    for (int i = tid; i < (RA + 2) * SXR; i += NT + 32) {   // zero padding of convolve(boundary='fill')
         s_adv[i] = make_double2(0.0, 0.0);
         s_div[i] = make_double2(0.0, 0.0);
     }
@@ -207,23 +210,36 @@ __global__ void __launch_bounds__(NT, 1) ensemble_season_kernel(const __grid_con
         const int idx = tid + j * NT;
         own_lr[j] = -1;
         own_c[j] = 0;
-        if (idx < n_ocean) {
+        if (comp && idx < n_ocean) {
             const int code = a.st.codes[a.st.ocean_off[k] + idx];
             own_lr[j] = code >> 7;
             own_c[j] = code & 127;
         }
     }
-    // raw-list entries this thread computes every day: tid + q*NT
-    int raw_r[KR], raw_c[KR];
+    // raw-list entries this thread computes every day: tid + q*NT.  For each, the shared-memory offsets (doubles,
+    // relative to s_plane, layer 0) of the cell in rows r-1, r, r+1; bit 30 marks a halo row, whose offset moves
+    // by one parity block every other day.  Layer 1 sits PE (own rows) or 2*nx (halo rows) further.
+    int raw_r[KR], raw_c[KR], raw_up[KR], raw_ce[KR], raw_dn[KR];
+    const int HALO0 = ENS_NPLANE * PE;                 // s_halo - s_plane
+    constexpr int HALO_FLAG = 1 << 30;
+    auto row_off = [&](int r, int c) -> int {          // parity-0 offset of (layer 0, global row r, column c)
+        if (r < ra) return (HALO0 + (((0 * 2 + 0) * 2 + 0) * 2 + (r - (ra - 2))) * nx + c) | HALO_FLAG;
+        if (r >= rb) return (HALO0 + (((0 * 2 + 1) * 2 + 0) * 2 + (r - rb)) * nx + c) | HALO_FLAG;
+        return (r - ra) * nx + c;
+    };
 #pragma unroll
     for (int q = 0; q < KR; ++q) {
         const int idx = tid + q * NT;
         raw_r[q] = -1;
-        raw_c[q] = 0;
-        if (idx < n_raw) {
+        raw_c[q] = raw_up[q] = raw_ce[q] = raw_dn[q] = 0;
+        if (comp && idx < n_raw) {
             const int code = a.st.codes[a.st.raw_off[k] + idx];
-            raw_r[q] = code >> 7;
-            raw_c[q] = code & 127;
+            const int r = code >> 7, c = code & 127;
+            raw_r[q] = r;
+            raw_c[q] = c;
+            raw_up[q] = row_off(r > 0 ? r - 1 : r, c);
+            raw_ce[q] = row_off(r, c);
+            raw_dn[q] = row_off(r < ny - 1 ? r + 1 : r, c);
         }
     }
 
@@ -245,13 +261,6 @@ __global__ void __launch_bounds__(NT, 1) ensemble_season_kernel(const __grid_con
             nb_dn[halo_off(par, 0, 1, lr - (nrow - 2)) + c] = h1;
         }
     };
-    // row pointer of layer l, global row r (own rows, or the halo rows of parity `par`)
-    auto hrow = [&](int par, int l, int r) -> const double * {
-        if (r < ra) return s_halo + halo_off(par, 0, l, r - (ra - 2));
-        if (r >= rb) return s_halo + halo_off(par, 1, l, r - rb);
-        return s_plane + l * PE + (r - ra) * nx;
-    };
-
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const bool timing = a.timing != nullptr && tid == 0;
     long long tlast = 0;
@@ -280,9 +289,9 @@ __global__ void __launch_bounds__(NT, 1) ensemble_season_kernel(const __grid_con
 
         // ---- slot 0: genEmptyArrays zeros + the IC split of main (NESOSIM.py:604-609), every cell of the strip.
         // The previous member's bulk stores may still be reading the planes.
-        if (tid == 0) bulk_wait_read<0>();
+        if (store_lane) bulk_wait_read<0>();
         __syncthreads();
-        for (int i = tid; i < ncell; i += NT) {
+        for (int i = tid; comp && i < ncell; i += NT) {
             const int lr = i / nx, c = i - lr * nx;
             const long long o = (long long)(ra + lr) * nx + c;
             double half = 0.0;
@@ -334,27 +343,30 @@ __global__ void __launch_bounds__(NT, 1) ensemble_season_kernel(const __grid_con
             // ---------------- phase A: raw advection / divergence (calcDynamics, NESOSIM.py:189-222) where an
             // ocean cell of this strip will read it
             if (a.sw.dynamics) {
+                const int hpar = par * 8 * nx;   // halo offset of today's parity block
 #pragma unroll
                 for (int q = 0; q < KR; ++q) {
                     if (raw_r[q] < 0) continue;
                     const int r = raw_r[q], c = raw_c[q];
-                    const double *c0 = hrow(par, 0, r) + c, *c1 = hrow(par, 1, r) + c;
+                    auto rowp = [&](int off) -> const double * {
+                        return s_plane + ((off & HALO_FLAG) ? (off & ~HALO_FLAG) + hpar : off);
+                    };
+                    auto layer1 = [&](int off) -> int { return (off & HALO_FLAG) ? 2 * nx : PE; };
+                    const double *c0 = rowp(raw_ce[q]), *u0 = rowp(raw_up[q]), *w0 = rowp(raw_dn[q]);
+                    const double *c1 = c0 + layer1(raw_ce[q]), *u1 = u0 + layer1(raw_up[q]), *w1 = w0 + layer1(raw_dn[q]);
                     const double h0 = c0[0], h1 = c1[0];
                     double gx0, gy0, gx1, gy1;
                     if (tid + q * NT < n_raw_int) {
-                        const double *u0 = hrow(par, 0, r - 1) + c, *u1 = hrow(par, 1, r - 1) + c;
-                        const double *w0 = hrow(par, 0, r + 1) + c, *w1 = hrow(par, 1, r + 1) + c;
                         gx0 = div_const(sub(c0[1], c0[-1]), a.g.two_dx);
                         gy0 = div_const(sub(w0[0], u0[0]), a.g.two_dx);
                         gx1 = div_const(sub(c1[1], c1[-1]), a.g.two_dx);
                         gy1 = div_const(sub(w1[0], u1[0]), a.g.two_dx);
                     } else {   // first/last row or column: one-sided differences (np.gradient edge_order=1)
                         const int cm = c > 0 ? -1 : 0, cp = c < nx - 1 ? 1 : 0;
-                        const int rm = r > 0 ? r - 1 : r, rp = r < ny - 1 ? r + 1 : r;
                         gx0 = gradient1d(c0[cm], h0, c0[cp], c, nx, a.g);
-                        gy0 = gradient1d(hrow(par, 0, rm)[c], h0, hrow(par, 0, rp)[c], r, ny, a.g);
+                        gy0 = gradient1d(u0[0], h0, w0[0], r, ny, a.g);
                         gx1 = gradient1d(c1[cm], h1, c1[cp], c, nx, a.g);
-                        gy1 = gradient1d(hrow(par, 1, rm)[c], h1, hrow(par, 1, rp)[c], r, ny, a.g);
+                        gy1 = gradient1d(u1[0], h1, w1[0], r, ny, a.g);
                     }
                     const int ro = (r - ra + 1) * SXR + c + 1;
                     s_adv[ro] = make_double2(zero_if_nonfinite(adv_term(d01[q].x, d01[q].y, gx0, gy0)),
@@ -366,8 +378,8 @@ __global__ void __launch_bounds__(NT, 1) ensemble_season_kernel(const __grid_con
             }
             ENS_TICK(0)   // phase A
             // the bulk stores of the previous day must have finished READING the planes before they change
-            if (tid == 0) bulk_wait_read<0>();
-            ENS_TICK(1)   // bulk stores drained
+            if (store_lane) bulk_wait_read<0>();
+            ENS_TICK(1)   // (store warp: bulk stores drained)
             __syncthreads();
             ENS_TICK(2)   // wait for the CTA
 
@@ -434,7 +446,7 @@ __global__ void __launch_bounds__(NT, 1) ensemble_season_kernel(const __grid_con
             // ---------------- land cells.  Step 0 sees the initial depths; afterwards h is NaN, so every switched-on
             // term is NaN and every switched-off term adds 0 (NESOSIM.py:287-322): closed form, written on the
             // first two days (both halo parities) and then left alone in the planes.
-            if (x <= 1) {
+            if (x <= 1 && comp) {
                 for (int i = tid; i < n_land; i += NT) {
                     const int code = s_land_code[i], lr = code >> 7, c = code & 127, ci = lr * nx + c;
                     double vLead = landLead, vAtm = landAtm, vWpl = landWp, vWpg = landWp, vWp = landWp;
@@ -469,7 +481,7 @@ __global__ void __launch_bounds__(NT, 1) ensemble_season_kernel(const __grid_con
             cluster_arrive_release();
             __syncthreads();
             ENS_TICK(4)   // arrive + CTA barrier
-            if (tid == 0) {
+            if (store_lane) {
                 const unsigned bytes = (unsigned)ncell * 8u;
 #pragma unroll
                 for (int p = 0; p < ENS_NPLANE; ++p) {
@@ -479,7 +491,7 @@ __global__ void __launch_bounds__(NT, 1) ensemble_season_kernel(const __grid_con
                 bulk_commit();
             }
             // snowAcc / snowOcean: member-independent running sums, copied row-contiguously
-            if (a.out[V_ACC] || a.out[V_OCEAN]) {
+            if (comp && (a.out[V_ACC] || a.out[V_OCEAN])) {
                 const double2 *DCx = a.DC + (long long)x * plane + (long long)ra * nx;
                 double *pa_ = a.out[V_ACC] ? outp(V_ACC, x + 1) : nullptr;
                 double *po_ = a.out[V_OCEAN] ? outp(V_OCEAN, x + 1) : nullptr;
@@ -506,7 +518,7 @@ __global__ void __launch_bounds__(NT, 1) ensemble_season_kernel(const __grid_con
             ENS_TICK(6)   // wait for the cluster
         }
     }
-    if (tid == 0) bulk_wait_all();
+    if (store_lane) bulk_wait_all();
 #undef ENS_TICK
     if (timing)
         for (int q = 0; q < 8; ++q) a.timing[(long long)blockIdx.x * 8 + q] = tacc[q];
@@ -520,7 +532,7 @@ struct EnsembleState {
     unsigned short *codes_dev = nullptr;
     StripTables tables;
     bool tables_ready = false;
-    int max_ocean = 0, max_raw = 0;    // longest ocean / raw list of any strip (selects the kernel variant)
+    int variant = 0;                   // index into the host's kernel-variant table
     size_t smem_bytes = 0;
     int max_clusters = 0;
 };

@@ -304,29 +304,17 @@ struct EnsVariant {
     void (*kernel)(const EnsArgs);
 };
 
-// every entry compiles without register spills (checked with -Xptxas -v); more threads first
+// nt = compute threads; one more warp issues the bulk stores.  Total warps 16 / 12 / 8 allow 128 / 168 / 255
+// registers per thread; every entry compiles without spills (checked with -Xptxas -v).  More threads first.
 const EnsVariant *ens_variants(int *n) {
     static const EnsVariant v[] = {
-        {"t512k1", 512, 1, 2, ensemble_season_kernel<512, 1, 2>},
-        {"t384k2", 384, 2, 3, ensemble_season_kernel<384, 2, 3>},
-        {"t256k2", 256, 2, 3, ensemble_season_kernel<256, 2, 3>},
-        {"t256k3", 256, 3, 4, ensemble_season_kernel<256, 3, 4>},
-        {"t256k4", 256, 4, 6, ensemble_season_kernel<256, 4, 6>},
+        {"t480k1", 480, 1, 2, ensemble_season_kernel<480, 1, 2>},
+        {"t352k2", 352, 2, 3, ensemble_season_kernel<352, 2, 3>},
+        {"t224k3", 224, 3, 5, ensemble_season_kernel<224, 3, 5>},
+        {"t224k4", 224, 4, 6, ensemble_season_kernel<224, 4, 6>},
     };
     *n = (int)(sizeof(v) / sizeof(v[0]));
     return v;
-}
-
-const EnsVariant *pick_variant(int max_ocean, int max_raw) {
-    int n;
-    const EnsVariant *v = ens_variants(&n);
-    auto fits = [&](const EnsVariant &e) { return e.ko * e.nt >= max_ocean && e.kr * e.nt >= max_raw; };
-    if (const char *env = getenv("NESOSIM_ENS_VARIANT"))
-        for (int i = 0; i < n; ++i)
-            if (!strcmp(env, v[i].name) && fits(v[i])) return &v[i];
-    for (int i = 0; i < n; ++i)
-        if (fits(v[i])) return &v[i];
-    return nullptr;
 }
 
 constexpr size_t ENS_SMEM_CAP = 227 * 1024;
@@ -335,8 +323,9 @@ constexpr size_t ENS_SMEM_CAP = 227 * 1024;
 // kernel walks.  A strip must satisfy the bulk-copy rules (16-byte aligned start, 16-byte multiple size), hold
 // at least the two rows its neighbours need as halo, and fit the per-thread list capacities.
 // Returns false if no such cut exists for this cluster size.
-bool try_strip_tables(nesosim_ctx *ctx, int cl, StripTables &t, std::vector<unsigned short> &codes, int &max_ocean_out,
-                      int &max_raw_out, size_t &smem_bytes, double &day_cost) {
+bool try_strip_tables(nesosim_ctx *ctx, int cl, int cap_ocean, int cap_raw, StripTables &t,
+                      std::vector<unsigned short> &codes, int &max_ocean_out, int &max_raw_out, size_t &smem_bytes,
+                      double &day_cost) {
     const int ny = ctx->cfg.ny, nx = ctx->cfg.nx;
     const std::vector<uint8_t> &mask = ctx->mask_host;
     auto land = [&](int r, int c) { const uint8_t m = mask[(size_t)r * nx + c]; return m > 10 || m < 1; };
@@ -366,7 +355,7 @@ bool try_strip_tables(nesosim_ctx *ctx, int cl, StripTables &t, std::vector<unsi
         if (((long long)rows * nx) % 2 || ((long long)ra * nx) % 2) return -1.0;
         const long long ocean = coc[rb] - coc[ra];
         const long long raw = cdil[std::min(rb + 1, ny)] - cdil[std::max(ra - 1, 0)];
-        if (ocean > ENS_MAX_OCEAN || raw > ENS_MAX_RAW) return -1.0;
+        if (ocean > cap_ocean || raw > cap_raw) return -1.0;
         return 11.0 * ocean + 4.5 * raw + 0.6 * rows * nx;   // cycles per day measured on B200 (phase timers)
     };
     const double INF = 1e300;
@@ -429,7 +418,7 @@ bool try_strip_tables(nesosim_ctx *ctx, int cl, StripTables &t, std::vector<unsi
     max_ocean_out = max_ocean;
     max_raw_out = max_raw;
     day_cost = best[cl][ny];
-    return pick_variant(max_ocean, max_raw) != nullptr;
+    return max_raw <= cap_raw;   // (the DP bounds the raw count from above only approximately)
 }
 
 int max_active_clusters(const EnsVariant *v, int cl, size_t smem_bytes) {
@@ -442,7 +431,7 @@ int max_active_clusters(const EnsVariant *v, int cl, size_t smem_bytes) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cfg.blockDim = dim3(v->nt);
+    cfg.blockDim = dim3(v->nt + 32);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.gridDim = dim3(cl * 64);
     int n = 0;
@@ -462,27 +451,33 @@ int build_strip_tables(nesosim_ctx *ctx) {
     if (const char *env = getenv("NESOSIM_ENS_CLUSTER")) forced = atoi(env);
     std::vector<unsigned short> best_codes;
     double best_time = 1e300;
+    int nv;
+    const EnsVariant *vars = ens_variants(&nv);
+    const char *forced_var = getenv("NESOSIM_ENS_VARIANT");
     for (int cl = 2; cl <= ENS_MAX_CLUSTER; ++cl) {
         if (forced && cl != forced) continue;
-        StripTables t;
-        std::vector<unsigned short> codes;
-        int mo = 0, mr = 0;
-        size_t smem = 0;
-        double day_cost = 0;
-        if (!try_strip_tables(ctx, cl, t, codes, mo, mr, smem, day_cost)) continue;
-        const EnsVariant *v = pick_variant(mo, mr);
-        const int ncl = max_active_clusters(v, cl, smem);
-        if (ncl < 1) continue;
-        const int rounds = (ctx->cfg.n_members + ncl - 1) / ncl;
-        const double time = rounds * (day_cost + 3000.0);
-        if (time < best_time) {
-            best_time = time;
-            e.tables = t;
-            e.max_ocean = mo;
-            e.max_raw = mr;
-            e.smem_bytes = smem;
-            e.max_clusters = ncl;
-            best_codes.swap(codes);
+        for (int vi = 0; vi < nv; ++vi) {
+            const EnsVariant *v = &vars[vi];
+            if (forced_var && strcmp(forced_var, v->name)) continue;
+            StripTables t;
+            std::vector<unsigned short> codes;
+            int mo = 0, mr = 0;
+            size_t smem = 0;
+            double day_cost = 0;
+            if (!try_strip_tables(ctx, cl, v->ko * v->nt, v->kr * v->nt, t, codes, mo, mr, smem, day_cost)) continue;
+            const int ncl = max_active_clusters(v, cl, smem);
+            if (ncl < 1) continue;
+            const int rounds = (ctx->cfg.n_members + ncl - 1) / ncl;
+            // per-day time: the strip's work spread over the compute threads + fixed barrier/drain overhead
+            const double time = rounds * (day_cost * (512.0 / v->nt) * 0.5 + day_cost * 0.5 + 3000.0);
+            if (time < best_time) {
+                best_time = time;
+                e.tables = t;
+                e.variant = vi;
+                e.smem_bytes = smem;
+                e.max_clusters = ncl;
+                best_codes.swap(codes);
+            }
         }
     }
     if (best_time >= 1e300) return fail(NESOSIM_ERR_ARG, "grid does not fit the season-resident kernel's shared-memory strips");
@@ -537,7 +532,8 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     ctx->launches += 2;
     CU(cudaGetLastError());
 
-    const EnsVariant *v = pick_variant(e.max_ocean, e.max_raw);
+    int nv_;
+    const EnsVariant *v = &ens_variants(&nv_)[e.variant];
     const int cl = e.tables.cluster;
     void (*kernel)(const EnsArgs) = v->kernel;
     CU(cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem_bytes));
@@ -546,7 +542,7 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cfg.blockDim = dim3(v->nt);
+    cfg.blockDim = dim3(v->nt + 32);
     cfg.dynamicSmemBytes = e.smem_bytes;
     cfg.stream = st;
     int max_clusters = e.max_clusters;

@@ -140,7 +140,7 @@ def test_25km_short_season(cuda):
 
 
 @pytest.mark.parametrize("cluster", ["4", "5", "6", "8"])
-@pytest.mark.parametrize("variant", ["t512k1", "t384k2", "t256k2", "t256k3", "t256k4"])
+@pytest.mark.parametrize("variant", ["t480k1", "t352k2", "t224k3", "t224k4"])
 def test_ensemble_kernel_variants_many_members_per_cluster(cuda, variant, cluster, monkeypatch):
     """Every build variant of the season-resident kernel; 3 clusters share 11 members with per-member ICs."""
     from nesosim_b200.engine import SnowBudgetEngine
