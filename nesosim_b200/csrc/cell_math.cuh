@@ -44,6 +44,21 @@ __device__ __forceinline__ double div_const(double x, const ConstDiv &d) {
     return div_generic(x, d.c);
 }
 
+// Branch-free form for the season-resident kernel's hot loops (requires d.fast): the same three operations for
+// operands inside the magnitude window, x*rc for zero / inf / NaN dividends, and a sticky flag for the only
+// remaining case (a finite dividend outside 2^-623..2^624, or a denormal), which the caller then recomputes
+// with div_const().  No divergence region, so independent cells interleave freely in the instruction stream.
+__device__ __forceinline__ double div_const_flagged(double x, const ConstDiv &d, unsigned &bad) {
+    const unsigned hi = (unsigned)__double2hiint(x);
+    const unsigned e = (hi >> 20) & 0x7ffu;
+    const double q0 = __dmul_rn(x, d.rc);
+    const double q = __fma_rn(__fma_rn(-d.c, q0, x), d.rc, q0);
+    const bool inwin = (e - 400u) <= 1246u;
+    const bool special = (e == 0x7ffu) || (((hi & 0x7fffffffu) | (unsigned)__double2loint(x)) == 0u);
+    bad |= (unsigned)(!inwin && !special);
+    return inwin ? q : q0;
+}
+
 // np.gradient(f, dx, axis) with edge_order=1 and uniform spacing (numpy; call sites NESOSIM.py:204-211):
 // interior (f[+1]-f[-1])/(2.*dx), first (f[1]-f[0])/dx, last (f[n-1]-f[n-2])/dx.
 struct GradConsts {
@@ -140,6 +155,20 @@ __device__ __forceinline__ double density_variable(double h0, double h1, bool la
     if (land) rho = qnan();
     if (den < k.minSnowD) rho = qnan();
     return rho;
+}
+// densityCalc for a cell that is known to be ocean, branch-free: the quotient only matters where the total depth
+// is a number >= minSnowD (everything else ends as NaN, NESOSIM.py:471); there both operands are normal numbers
+// unless minSnowD <= 0 or the depths overflow -- those lanes raise `bad` and are redone with density_variable().
+__device__ __forceinline__ double density_ocean_flagged(double h0, double h1, const ModelConsts &k, unsigned &bad) {
+    const double den = add(h0, h1);
+    const double num = add(mul(h0, k.rhoFresh), mul(h1, k.rhoOld));
+    const bool normal = (biased_exp(num) - 1u) <= 0x7fdu && (biased_exp(den) - 1u) <= 0x7fdu;
+    const bool need = !(den < k.minSnowD) && den == den;
+    double rho = __ddiv_rn(normal ? num : 1.0, normal ? den : 1.0);
+    bad |= (unsigned)(need && !normal);
+    if (rho > k.rhoOld) rho = k.rhoOld;
+    if (rho < k.rhoFresh) rho = k.rhoFresh;
+    return need ? rho : qnan();
 }
 // clim branch (NESOSIM.py:339-344)
 __device__ __forceinline__ double density_clim(double rho_new, double h0, double h1, double C, bool land,

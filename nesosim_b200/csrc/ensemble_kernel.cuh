@@ -1,16 +1,19 @@
 // ensemble_kernel.cuh -- season-resident path for small grids (the 100 km calibration ensemble).
 //
-// One thread-block CLUSTER (4 or 8 CTAs) owns one ensemble member for the whole season; each CTA holds a strip of
+// One thread-block CLUSTER (2..8 CTAs) owns one ensemble member for the whole season; each CTA holds a strip of
 // rows (strips are cut by the host so that their work balances).  Everything a member needs stays on chip for all
 // T-1 days, and HBM only ever sees the output planes, written once, as large contiguous TMA bulk stores:
 //   * ten output planes of the strip live in shared memory IN THE OUTPUT LAYOUT (rows x nx doubles, contiguous):
 //     h0, h1 (also the state the stencils read), density, snowAdv, snowDiv, snowLead, snowAtm, snowWindPackLoss/
-//     Gain/Net.  Each day the owning threads overwrite their cells and one thread issues one
-//     cp.async.bulk.global.shared::cta per plane (8-18 KB each).  Measured on B200 (tools/micro): fragmented
-//     per-thread stores of this pattern reach 1.6 TB/s, full-row st.global 4.4 TB/s, these bulk stores 5.8 TB/s.
-//   * the two boundary rows of each neighbour strip are pushed into double-buffered halo rows through
-//     distributed shared memory (st.shared::cluster), one split (arrive ... wait) cluster barrier per day;
-//   * the seven member-dependent accumulators are carried in REGISTERS of the thread that owns the cell.
+//     Gain/Net (also the running accumulators).  Measured on B200 (tools/micro): fragmented per-thread stores of
+//     this pattern reach 1.6 TB/s, full-row st.global 4.4 TB/s, bulk stores 5.8 TB/s;
+//   * every compute thread OWNS the same few cells for the whole season (KR raw-dynamics entries, KO ocean cells),
+//     so all shared-memory addresses are computed once, before the first day; a day is straight-line fp64 code;
+//   * the two boundary rows of each neighbour strip are pushed into halo rows through distributed shared memory
+//     (st.shared::cluster); two split (arrive ... wait) cluster barriers per day order "I have read my halo" and
+//     "my pushes have landed", so the halo is single-buffered and nobody ever waits at a barrier it just reached;
+//   * a dedicated DMA warp issues every HBM write: ten cp.async.bulk shared->global per day for the planes, and
+//     the member-independent snowAcc/snowOcean planes as bulk global->shared->global copies of the pre-pass sums.
 // The land mask is compiled into per-strip cell lists once per context: only ocean cells are owned and advanced;
 // only cells with an ocean cell in their 3x3 neighbourhood get raw advection/divergence; land cells (56 % of the
 // 100 km grid) have closed-form outputs after the first step -- h and density NaN, every accumulator NaN if its
@@ -20,8 +23,12 @@
 // snowfall -> accumulation/ocean flux and their running sums) and then shared by every member through L2.
 //
 // Arithmetic is the per-cell code of cell_math.cuh, shared with the general path: results are value-identical.
+// The hot loops use the branch-free flagged divisions; a thread whose flag rises (never, on physical data)
+// recomputes its own cells with the exact branching forms before anything is published.
 #pragma once
 #include <cooperative_groups.h>
+
+#include <type_traits>
 
 #include "cell_math.cuh"
 #include "day_kernels.cuh"
@@ -33,13 +40,14 @@ namespace cg = cooperative_groups;
 // ------------------------------------------------------------------ member-independent pre-pass (per season)
 // DA[x][cell][2] = (ut, vt), (gx(ut), gy(vt))   drift displacement and its gradients   (NESOSIM.py:204-205)
 // DB[x][cell]    = (acc, 1-C)                   accumulation delta (NESOSIM.py:260-263), open-water fraction
-// DC[x][cell]    = (snowAcc[x+1], snowOcean[x+1])   running sums (NESOSIM.py:264,268)
+// cumAcc[x][cell], cumOc[x][cell] = snowAcc[x+1], snowOcean[x+1]   running sums (NESOSIM.py:264,268)
 
 struct DeriveArgs {
     int ny, nx, steps;                 // steps = T-1
     const double *P, *C, *UV;          // [T][plane], [T][plane], [T][2][plane]
     double2 *DA;                       // [steps][plane][2]
-    double2 *DB, *DC;                  // [steps][plane]
+    double2 *DB;                       // [steps][plane]
+    double *cumAcc, *cumOc;            // [steps][plane] each
     ModelConsts k;
     GradConsts g;
     ConstDiv rho_new;
@@ -64,11 +72,11 @@ __global__ void derive_pointwise_kernel(const __grid_constant__ DeriveArgs a) {
     const double pd = div_const(a.P[(long long)x * plane + o], a.rho_new);
     const double omc = sub(1.0, C);
     a.DB[(long long)x * plane + o] = make_double2(mul(pd, C), omc);
-    a.DC[(long long)x * plane + o] = make_double2(0.0, -mul(pd, omc));   // .y parks oc until the scan
+    a.cumOc[(long long)x * plane + o] = -mul(pd, omc);   // parks oc until the scan
 }
 
 // One thread per cell, sequential in time, loads batched 8 days ahead (add-latency bound, not load-latency bound).
-__global__ void derive_scan_kernel(const double2 *DB, double2 *DC, long long plane, int steps) {
+__global__ void derive_scan_kernel(const double2 *DB, double *cumAcc, double *cumOc, long long plane, int steps) {
     const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= plane) return;
     double sa = 0.0, so = 0.0;
@@ -79,14 +87,15 @@ __global__ void derive_scan_kernel(const double2 *DB, double2 *DC, long long pla
         for (int j = 0; j < B; ++j) {
             const int x = min(x0 + j, steps - 1);
             da[j] = DB[(long long)x * plane + o].x;
-            dq[j] = DC[(long long)x * plane + o].y;
+            dq[j] = cumOc[(long long)x * plane + o];
         }
 #pragma unroll
         for (int j = 0; j < B; ++j) {
             if (x0 + j < steps) {
                 sa = add(sa, da[j]);
                 so = add(so, dq[j]);
-                DC[(long long)(x0 + j) * plane + o] = make_double2(sa, so);
+                cumAcc[(long long)(x0 + j) * plane + o] = sa;
+                cumOc[(long long)(x0 + j) * plane + o] = so;
             }
         }
     }
@@ -95,43 +104,63 @@ __global__ void derive_scan_kernel(const double2 *DB, double2 *DC, long long pla
 // ------------------------------------------------------------------------------------ the season kernel
 
 constexpr int ENS_MAX_CLUSTER = 8;
-constexpr int ENS_NT = 512;            // default CTA size (16 warps); the kernel is templated on it
-constexpr int ENS_SXR = 98;            // raw tile row stride; column c lives at c+1 (zero pad each side)
+constexpr int ENS_SXR = 98;            // raw tile row stride (double2); column c lives at c+1 (zero pad each side)
 constexpr int ENS_MAX_NX = 96;
-constexpr int ENS_MAX_OCEAN = 1024;    // per-strip capacities of the largest kernel variant
-constexpr int ENS_MAX_RAW = 1536;
 constexpr int ENS_NPLANE = 10;         // staged output planes: h0, h1, density, adv, div, lead, atm, wpl, wpg, wp
+constexpr int ENS_MIN_ROWS = 4;        // a strip's top two and bottom two rows must be distinct rows
+constexpr int ENS_NTIMER = 16;
 
 // plane index -> output variable
 __device__ __constant__ const int ENS_PLANE_VAR[ENS_NPLANE] = {V_H0, V_H1, V_DENS, V_ADV, V_DIV, V_LEAD, V_ATM, V_WPL, V_WPG, V_WP};
 enum { PL_H0 = 0, PL_H1, PL_DENS, PL_ADV, PL_DIV, PL_LEAD, PL_ATM, PL_WPL, PL_WPG, PL_WP };
+enum { BAR_A = 1, BAR_DRAIN = 2, BAR_STORE = 3 };   // named CTA barriers (0 is __syncthreads)
 
-// Shared memory, sized by the host for the tallest strip (`rows`):
-//   planes   [10][rows*nx] doubles   output layout; planes 0,1 are also the h the stencils read
-//   halos    [2 parity][2 side][2 layer][2 rows][nx] doubles
-//   raw adv  [rows+2][SXR] double2, raw div [rows+2][SXR] double2
-//   raw and land code lists (uint16)
-inline size_t ens_plane_elems(int rows, int nx) { return (size_t)((rows * nx + 1) / 2 * 2); }
-inline size_t ens_smem_bytes(int rows, int nx, int n_codes) {
-    return (ENS_NPLANE * ens_plane_elems(rows, nx) + 16 * (size_t)nx) * sizeof(double) +
-           (size_t)2 * (rows + 2) * ENS_SXR * sizeof(double2) + (size_t)((n_codes + 7) / 8 * 8) * sizeof(unsigned short);
+// Shared memory of one CTA, sized by the host for the tallest strip (`rows`).  Byte offsets from the base:
+//   h0 ext   [2 halo rows above][own rows][2 halo rows below]   (rows+4)*nx = PEX doubles; the rows below follow
+//            the strip's own last row directly, so the rows r-1 / r+1 of ANY h cell are exactly -+nx doubles away
+//   h1 ext   same, so layer 1 of ANY h cell sits exactly PEX doubles after layer 0
+//   planes 2..9 [PE] each (own cells only)
+//   staging  [2][PE]    snowAcc / snowOcean rows on their way global -> shared -> global (TMA only)
+//   raw adv  [(rows+2)*SXR + 1] double2,  raw div likewise (the +1 is the slot idle list entries write to)
+//   member coefficients [10], land codes (uint16), one mbarrier
+struct EnsLayout {
+    int PE, PEX;                       // doubles
+    unsigned off_stage, off_adv, tile_bytes, off_coef, off_codes, off_mbar, total;   // bytes
+    // planes 0,1: offset of the extended plane (own cell (lr,c) at +((lr+2)*nx+c)*8); planes 2..9: own cells
+    __host__ __device__ unsigned plane_off(int p) const {
+        return (unsigned)((p < 2 ? (long long)p * PEX : 2ll * PEX + (long long)(p - 2) * PE) * 8);
+    }
+};
+__host__ __device__ inline EnsLayout ens_layout(int rows, int nx, int land_alloc) {
+    EnsLayout L;
+    L.PE = (rows * nx + 1) / 2 * 2;
+    L.PEX = (rows + 4) * nx + ((rows * nx) & 1);
+    L.off_stage = (unsigned)((2ll * L.PEX + 8ll * L.PE) * 8);
+    L.off_adv = L.off_stage + (unsigned)(2 * L.PE * 8);
+    L.tile_bytes = (unsigned)(((rows + 2) * ENS_SXR + 1) * 16);
+    L.off_coef = L.off_adv + 2 * L.tile_bytes;
+    L.off_codes = L.off_coef + 10 * 8;
+    L.off_mbar = (L.off_codes + (unsigned)land_alloc * 2u + 15u) / 16u * 16u;
+    L.total = L.off_mbar + 16;
+    return L;
 }
 
 // Per-strip cell lists (uint16 code = row*128 + col; row is global for the raw list, strip-local for cells).
 struct StripTables {
     const unsigned short *codes;       // all lists concatenated (device)
-    int cluster;                       // CTAs per member (4 or 8)
+    int cluster;                       // CTAs per member
     int row0[ENS_MAX_CLUSTER + 1];     // strip k owns rows row0[k] .. row0[k+1]-1
     int raw_off[ENS_MAX_CLUSTER], raw_int_n[ENS_MAX_CLUSTER], raw_n[ENS_MAX_CLUSTER];   // interior entries first
     int ocean_off[ENS_MAX_CLUSTER], ocean_n[ENS_MAX_CLUSTER];
     int land_off[ENS_MAX_CLUSTER], land_n[ENS_MAX_CLUSTER];
     int rows_alloc;                    // tallest strip
-    int raw_alloc, land_alloc;         // longest raw / land list (shared-memory copies)
+    int raw_max, ocean_max, land_alloc;   // longest lists
 };
 
 struct EnsArgs {
     int ny, nx, T, M;
-    const double2 *DA, *DB, *DC;
+    const double2 *DA, *DB;
+    const double *cumAcc, *cumOc;
     const double *W;                   // wind [T][plane]
     const double *ic;                  // NULL -> zero depth
     long long ic_stride;               // 0 shared, plane per member
@@ -145,15 +174,21 @@ struct EnsArgs {
     double w[9];
     Switches sw;
     StripTables st;
-    long long *timing;                 // debug: [gridDim.x][8] phase cycle totals of thread 0 (NULL = off)
+    long long *timing;                 // debug: [gridDim.x][ENS_NTIMER] phase cycle totals (NULL = off)
 };
 
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 // shared -> global bulk copy (TMA), tracked by the issuing thread's bulk async-group
-__device__ __forceinline__ void bulk_store(double *gdst, const double *ssrc, unsigned bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-                 "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+__device__ __forceinline__ void bulk_store(double *gdst, unsigned ssrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy (TMA), completion counted in bytes on an mbarrier of this CTA
+__device__ __forceinline__ void bulk_load(unsigned sdst, const double *gsrc, unsigned bytes, unsigned mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst),
+                 "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -161,22 +196,59 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // generic-proxy writes to shared memory must be fenced before the async proxy (TMA) reads them
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(mbar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ unsigned map_to_rank(unsigned saddr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster(unsigned addr, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
 
-// NT compute threads per CTA (+ one warp that only issues and drains the bulk stores, so nobody who computes
-// ever blocks on the TMA queue); KO owned ocean cells and KR raw-list entries per compute thread.
-template <int NT, int KO, int KR>
-__global__ void __launch_bounds__(NT + 32, 1) ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
+// One day for a compute thread:
+//   A    raw advection/divergence of its KR list entries              (calcDynamics, NESOSIM.py:189-222)
+//   B    for its KO ocean cells: 3x3 Gaussian of the four raw planes   (smooth_snow,  NESOSIM.py:170-187),
+//        point-wise terms, accumulators, depth update, density         (calcBudget,   NESOSIM.py:260-347)
+//        -- everything into registers, then (once the previous day's bulk stores have read the planes) into the
+//        planes and the neighbours' halo rows
+// and for the DMA warp: drain, stage the running sums, issue the day's bulk stores.
+template <int NTC, int KR, int KO, bool TIMING>
+__global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
     constexpr int SXR = ENS_SXR;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int NTH = NTC + 32;
+    extern __shared__ __align__(128) unsigned char smem[];
     const int ny = a.ny, nx = a.nx, CL = a.st.cluster;
     const int RA = a.st.rows_alloc;
-    const int PE = (RA * nx + 1) / 2 * 2;              // plane stride (doubles)
-    double *s_plane = reinterpret_cast<double *>(smem_raw);   // [10][PE]
-    double *s_halo = s_plane + ENS_NPLANE * PE;        // [2 parity][2 side: 0 above, 1 below][2 layer][2 rows][nx]
-    double2 *s_adv = reinterpret_cast<double2 *>(s_halo + 16 * nx);   // [RA+2][SXR] (adv0,adv1) after NaN->0
-    double2 *s_div = s_adv + (RA + 2) * SXR;           // [RA+2][SXR] (div0,div1) after NaN->0
-    unsigned short *s_raw_code = reinterpret_cast<unsigned short *>(s_div + (RA + 2) * SXR);
-    unsigned short *s_land_code = s_raw_code + (a.st.raw_alloc + 7) / 8 * 8;
+    const EnsLayout L = ens_layout(RA, nx, a.st.land_alloc);
+    const unsigned PEXB = (unsigned)L.PEX * 8u;        // layer 0 -> layer 1 of any h cell (bytes)
+    const unsigned ROWB = (unsigned)nx * 8u;           // one row of h (bytes)
+    const unsigned HOWN = 2u * ROWB;                   // own cell (lr,c) of h0: HOWN + (lr*nx+c)*8
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
+    unsigned short *s_land_code = reinterpret_cast<unsigned short *>(smem + L.off_codes);
+    const unsigned mbar = sbase + L.off_mbar;
+
+    auto LD = [&](unsigned off) -> double { return *reinterpret_cast<const double *>(smem + off); };
+    auto LD2 = [&](unsigned off) -> double2 { return *reinterpret_cast<const double2 *>(smem + off); };
+    auto ST = [&](unsigned off, double v) { *reinterpret_cast<double *>(smem + off) = v; };
+    auto ST2 = [&](unsigned off, double2 v) { *reinterpret_cast<double2 *>(smem + off) = v; };
 
     cg::cluster_group cluster = cg::this_cluster();
     const int k = (int)cluster.block_rank();
@@ -185,100 +257,103 @@ __global__ void __launch_bounds__(NT + 32, 1) ensemble_season_kernel(const __gri
     const int ra = a.st.row0[k], rb = a.st.row0[k + 1], nrow = rb - ra;
     const int ncell = nrow * nx;
     const int tid = threadIdx.x;
-    const bool comp = tid < NT;        // compute thread; the last warp is the store warp
-    const bool store_lane = (tid == NT);
+    const bool comp = tid < NTC;       // compute thread; the last warp is the DMA warp
+    const bool dma_lane = (tid == NTC);
     const int steps = a.T - 1;
-
-    // neighbours' halo rows through distributed shared memory
-    double *nb_up = (k > 0) ? cluster.map_shared_rank(s_halo, k - 1) : nullptr;        // their side 1 (rows below them)
-    double *nb_dn = (k < CL - 1) ? cluster.map_shared_rank(s_halo, k + 1) : nullptr;   // their side 0 (rows above them)
-    auto halo_off = [&](int par, int side, int l, int row) { return (((par * 2 + side) * 2 + l) * 2 + row) * nx; };
 
     const int n_raw_int = a.st.raw_int_n[k], n_raw = a.st.raw_n[k];
     const int n_ocean = a.st.ocean_n[k], n_land = a.st.land_n[k];
-    for (int i = tid; i < n_raw; i += NT + 32) s_raw_code[i] = a.st.codes[a.st.raw_off[k] + i];
-    for (int i = tid; i < n_land; i += NT + 32) s_land_code[i] = a.st.codes[a.st.land_off[k] + i];
-    for (int i = tid; i < (RA + 2) * SXR; i += NT + 32) {   // zero padding of convolve(boundary='fill')
-        s_adv[i] = make_double2(0.0, 0.0);
-        s_div[i] = make_double2(0.0, 0.0);
-    }
+    for (int i = tid; i < n_land; i += NTH) s_land_code[i] = a.st.codes[a.st.land_off[k] + i];
+    for (unsigned i = tid; i < 2u * L.tile_bytes / 16u; i += NTH)   // zero padding of convolve(boundary='fill')
+        ST2(L.off_adv + i * 16u, make_double2(0.0, 0.0));
+    for (unsigned i = tid; i < 2u * (unsigned)L.PEX; i += NTH) ST(i * 8u, 0.0);   // halo rows nobody pushes to
+    if (dma_lane) mbar_init(mbar, 1);
 
-    // cells this thread owns for the whole season: ocean list entries tid + j*NT
-    int own_lr[KO], own_c[KO];
-#pragma unroll
-    for (int j = 0; j < KO; ++j) {
-        const int idx = tid + j * NT;
-        own_lr[j] = -1;
-        own_c[j] = 0;
-        if (comp && idx < n_ocean) {
-            const int code = a.st.codes[a.st.ocean_off[k] + idx];
-            own_lr[j] = code >> 7;
-            own_c[j] = code & 127;
+    // neighbour's halo cell (shared::cluster address, layer 0) that mirrors my local row lr, column c; 0 = none.
+    // My top two rows are the rows below the strip above; my bottom two rows are the rows above the strip below.
+    auto halo_target = [&](int lr, int c) -> unsigned {
+        if (lr < 2 && k > 0) {
+            const int nrow_up = ra - a.st.row0[k - 1];
+            return map_to_rank(sbase + (unsigned)((nrow_up + 2 + lr) * nx + c) * 8u, (unsigned)(k - 1));
         }
-    }
-    // raw-list entries this thread computes every day: tid + q*NT.  For each, the shared-memory offsets (doubles,
-    // relative to s_plane, layer 0) of the cell in rows r-1, r, r+1; bit 30 marks a halo row, whose offset moves
-    // by one parity block every other day.  Layer 1 sits PE (own rows) or 2*nx (halo rows) further.
-    int raw_r[KR], raw_c[KR], raw_up[KR], raw_ce[KR], raw_dn[KR];
-    const int HALO0 = ENS_NPLANE * PE;                 // s_halo - s_plane
-    constexpr int HALO_FLAG = 1 << 30;
-    auto row_off = [&](int r, int c) -> int {          // parity-0 offset of (layer 0, global row r, column c)
-        if (r < ra) return (HALO0 + (((0 * 2 + 0) * 2 + 0) * 2 + (r - (ra - 2))) * nx + c) | HALO_FLAG;
-        if (r >= rb) return (HALO0 + (((0 * 2 + 1) * 2 + 0) * 2 + (r - rb)) * nx + c) | HALO_FLAG;
-        return (r - ra) * nx + c;
+        if (lr >= nrow - 2 && k < CL - 1) return map_to_rank(sbase + (unsigned)((lr - (nrow - 2)) * nx + c) * 8u, (unsigned)(k + 1));
+        return 0u;
     };
+
+    // ---- the raw-list entries this thread computes every day (entries tid + q*NTC): offset of the centre cell in
+    // the extended h0 plane and of the entry's slot in the raw tiles.  flags: bit q = entry q valid, bit 8+j = owned
+    // cell j valid, bit 16 = some entry lies on the grid edge (one-sided differences)
+    unsigned a_c[KR], a_t[KR];
+    unsigned flags = 0;
 #pragma unroll
     for (int q = 0; q < KR; ++q) {
-        const int idx = tid + q * NT;
-        raw_r[q] = -1;
-        raw_c[q] = raw_up[q] = raw_ce[q] = raw_dn[q] = 0;
+        const int idx = tid + q * NTC;
+        a_c[q] = HOWN + 8u;                                      // idle entry: reads around cell (0,1), writes the spare slot
+        a_t[q] = L.off_adv + (unsigned)((RA + 2) * SXR) * 16u;
         if (comp && idx < n_raw) {
-            const int code = a.st.codes[a.st.raw_off[k] + idx];
-            const int r = code >> 7, c = code & 127;
-            raw_r[q] = r;
-            raw_c[q] = c;
-            raw_up[q] = row_off(r > 0 ? r - 1 : r, c);
-            raw_ce[q] = row_off(r, c);
-            raw_dn[q] = row_off(r < ny - 1 ? r + 1 : r, c);
+            const unsigned code = a.st.codes[a.st.raw_off[k] + idx];
+            const int r = (int)(code >> 7), c = (int)(code & 127u);
+            a_c[q] = (unsigned)((r - ra + 2) * nx + c) * 8u;
+            a_t[q] = L.off_adv + (unsigned)((r - ra + 1) * SXR + c + 1) * 16u;
+            flags |= 1u << q;
+            if (idx >= n_raw_int) flags |= 1u << 16;
+        }
+    }
+    // ---- the ocean cells this thread owns for the whole season (entries tid + j*NTC): offset of the cell in an
+    // own-cells plane, of its top-left 3x3 tap in the raw tiles, and its mirror in a neighbour's halo
+    unsigned b_ci[KO], b_t[KO], b_rem[KO];
+#pragma unroll
+    for (int j = 0; j < KO; ++j) {
+        const int idx = tid + j * NTC;
+        b_t[j] = L.off_adv;
+        b_ci[j] = 0;
+        b_rem[j] = 0;
+        if (comp && idx < n_ocean) {
+            const unsigned code = a.st.codes[a.st.ocean_off[k] + idx];
+            const int lr = (int)(code >> 7), c = (int)(code & 127u);
+            b_t[j] = L.off_adv + (unsigned)(lr * SXR + c) * 16u;
+            b_ci[j] = (unsigned)(lr * nx + c) * 8u;
+            b_rem[j] = halo_target(lr, c);
+            flags |= 1u << (8 + j);
         }
     }
 
     const double nan = qnan();
-    // closed-form land values from slot 2 on (slot 1 is computed from the initial depths)
-    const double landAdv = a.sw.dynamics ? nan : 0.0, landLead = a.sw.leadloss ? nan : 0.0;
-    const double landAtm = a.sw.atmloss ? nan : 0.0, landWp = a.sw.windpack ? nan : 0.0;
+    const bool all_fast = a.g.dx.fast && a.g.two_dx.fast && a.conv_div.fast;
+    // global byte offsets of this strip's forcing relative to a day's plane: cell (ra-2, 0) for the raw entries
+    // (a_c counts from the first halo row), cell (ra, 0) for the owned cells
+    const long long go_raw = (long long)(ra - 2) * nx, go_own = (long long)ra * nx;
 
-    // write (h0,h1) of local row lr, column c: own planes (in place) + the neighbours' halo rows of parity `par`
-    auto put_h = [&](int par, int lr, int c, double h0, double h1) {
-        s_plane[PL_H0 * PE + lr * nx + c] = h0;
-        s_plane[PL_H1 * PE + lr * nx + c] = h1;
-        if (lr < 2 && nb_up) {
-            nb_up[halo_off(par, 1, 0, lr) + c] = h0;
-            nb_up[halo_off(par, 1, 1, lr) + c] = h1;
-        }
-        if (lr >= nrow - 2 && nb_dn) {
-            nb_dn[halo_off(par, 0, 0, lr - (nrow - 2)) + c] = h0;
-            nb_dn[halo_off(par, 0, 1, lr - (nrow - 2)) + c] = h1;
+    // write (h0,h1) of local row lr, column c: own planes + the neighbour's halo row (slow form: init, land)
+    auto put_h = [&](int lr, int c, double h0, double h1) {
+        const unsigned off = HOWN + (unsigned)(lr * nx + c) * 8u;
+        ST(off, h0);
+        ST(off + PEXB, h1);
+        const unsigned rem = halo_target(lr, c);
+        if (rem) {
+            st_cluster(rem, h0);
+            st_cluster(rem + PEXB, h1);
         }
     };
-    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const bool timing = a.timing != nullptr && tid == 0;
+
+    long long tacc[TIMING ? 8 : 1] = {0};
+    const bool timing = TIMING && a.timing != nullptr && (tid == 0 || dma_lane);
     long long tlast = 0;
 #define ENS_TICK(slot)                                   \
-    if (timing) {                                        \
+    if (TIMING && timing) {                              \
         const long long now_ = clock64();                \
         tacc[slot] += now_ - tlast;                      \
         tlast = now_;                                    \
     }
 
-    cluster.sync();   // every CTA of the cluster is running before anyone writes into a neighbour's shared memory
+    // every CTA of the cluster is running (and has zeroed its tiles) before anyone writes into a neighbour
+    cluster_arrive_release();
+    cluster_wait_acquire();
+
+    unsigned stage_parity = 0;
+    const bool want_cum = a.out[V_ACC] != nullptr || a.out[V_OCEAN] != nullptr;
 
     for (int m = cid; m < a.M; m += ncl) {
-        const MemberCoef mc = a.coef[m];
-        double accAdv[KO], accDiv[KO], accLead[KO], accAtm[KO], accWpl[KO], accWpg[KO], accWp[KO];
-#pragma unroll
-        for (int j = 0; j < KO; ++j) accAdv[j] = accDiv[j] = accLead[j] = accAtm[j] = accWpl[j] = accWpg[j] = accWp[j] = 0.0;
-
         // output address of variable v, time slot `slot` of member m, first cell of this strip
         const long long mo_plane = (long long)m * a.mstride[V_DENS] + (long long)ra * nx;
         const long long mo_depth = (long long)m * a.mstride[V_H0] + (long long)ra * nx;
@@ -287,172 +362,281 @@ __global__ void __launch_bounds__(NT + 32, 1) ensemble_season_kernel(const __gri
                                             : a.out[v] + (mo_plane + (long long)slot * plane);
         };
 
+        if (!comp) {
+            // =============================================================== DMA warp
+            if (dma_lane) bulk_wait_read<0>();   // the previous member's stores have read the planes
+            __syncwarp();
+            bar_arrive(BAR_DRAIN, NTH);
+            cluster_arrive_release();
+            cluster_wait_acquire();
+            if (TIMING && timing) tlast = clock64();
+            for (int x = 0; x < steps; ++x) {
+                cluster_arrive_release();        // #1 (this warp never reads the halo)
+                if (dma_lane) {
+                    bulk_wait_read<0>();         // day x-1: planes and staging rows have been read
+                    ENS_TICK(0)                  // drain
+                    if (want_cum) {
+                        const unsigned bytes = (unsigned)ncell * 8u;
+                        const long long go = (long long)x * plane + go_own;
+                        mbar_expect_tx(mbar, (a.out[V_ACC] ? bytes : 0u) + (a.out[V_OCEAN] ? bytes : 0u));
+                        if (a.out[V_ACC]) bulk_load(sbase + L.off_stage, a.cumAcc + go, bytes, mbar);
+                        if (a.out[V_OCEAN]) bulk_load(sbase + L.off_stage + (unsigned)L.PE * 8u, a.cumOc + go, bytes, mbar);
+                    }
+                }
+                __syncwarp();
+                cluster_wait_acquire();          // #1
+                bar_arrive(BAR_DRAIN, NTH);      // compute warps may overwrite the planes
+                cluster_arrive_release();        // #2
+                ENS_TICK(1)
+                bar_sync(BAR_STORE, NTH);        // planes of day x+1 are complete (and fenced for the async proxy)
+                ENS_TICK(2)                      // waiting for the compute warps
+                if (dma_lane) {
+                    const unsigned bytes = (unsigned)ncell * 8u;
+#pragma unroll
+                    for (int p = 0; p < ENS_NPLANE; ++p) {
+                        const int v = ENS_PLANE_VAR[p];
+                        if (a.out[v]) bulk_store(outp(v, x + 1), sbase + L.plane_off(p) + (p < 2 ? HOWN : 0u), bytes);
+                    }
+                    if (want_cum) {
+                        mbar_wait(mbar, stage_parity);
+                        if (a.out[V_ACC]) bulk_store(outp(V_ACC, x + 1), sbase + L.off_stage, bytes);
+                        if (a.out[V_OCEAN]) bulk_store(outp(V_OCEAN, x + 1), sbase + L.off_stage + (unsigned)L.PE * 8u, bytes);
+                    }
+                    bulk_commit();
+                    ENS_TICK(3)                  // issue
+                }
+                stage_parity ^= (unsigned)want_cum;
+                __syncwarp();
+                cluster_wait_acquire();          // #2
+            }
+            continue;
+        }
+
+        // =================================================================== compute warps
+        bar_sync(BAR_DRAIN, NTH);   // the previous member's bulk stores have read the planes
+        // coefficient products the reference forms before touching the arrays, for windT = 0 and 1, as pairs
+        if (tid == 0) {
+            const MemberCoef mc = a.coef[m];
+            double *cf = reinterpret_cast<double *>(smem + L.off_coef);
+            cf[0] = mul(mul(0.0, mc.llf), a.k.deltaT); cf[1] = mul(mul(1.0, mc.llf), a.k.deltaT);   // NESOSIM.py:71
+            cf[2] = mul(0.0, a.k.deltaT);              cf[3] = mul(1.0, a.k.deltaT);                // NESOSIM.py:94
+            cf[4] = mul(mc.neg_wpf_dt, 0.0);           cf[5] = mul(mc.neg_wpf_dt, 1.0);             // NESOSIM.py:119
+            cf[6] = mul(mc.wpf_dt, 0.0);               cf[7] = mul(mc.wpf_dt, 1.0);                 // NESOSIM.py:122
+            cf[8] = mc.wpt;                            cf[9] = mc.alf;
+        }
         // ---- slot 0: genEmptyArrays zeros + the IC split of main (NESOSIM.py:604-609), every cell of the strip.
-        // The previous member's bulk stores may still be reading the planes.
-        if (store_lane) bulk_wait_read<0>();
-        __syncthreads();
-        for (int i = tid; comp && i < ncell; i += NT) {
+        for (int i = tid; i < ncell; i += NTC) {
             const int lr = i / nx, c = i - lr * nx;
-            const long long o = (long long)(ra + lr) * nx + c;
+            const long long o = go_own + i;
             double half = 0.0;
             if (a.ic) {
                 double v = a.ic[(long long)m * a.ic_stride + o];
                 if (a.conc0[o] < a.k.minConc) v = 0.0;
                 half = mul(v, 0.5);
             }
-            put_h(0, lr, c, half, half);
+            put_h(lr, c, half, half);
+#pragma unroll
+            for (int p = PL_DENS; p < ENS_NPLANE; ++p) ST(L.plane_off(p) + (unsigned)i * 8u, 0.0);   // accumulators start at zero
 #pragma unroll
             for (int v = 0; v < NVAR; ++v)
                 if (a.out[v]) outp(v, 0)[i] = (v == V_H0 || v == V_H1) ? half : 0.0;
         }
-        cluster.sync();
+        cluster_arrive_release();
+        cluster_wait_acquire();
 
-        // member-independent inputs are always requested one phase ahead, so their L2 latency is never exposed
-        double2 d01[KR], d23[KR];   // (ut,vt), (gxu,gyv) of this thread's raw entries
-        double2 f_b[KO];            // (acc, 1-C) of the owned cells
-        double f_W[KO];
-        auto load_raw_inputs = [&](int x) {
-            const double2 *DAx = a.DA + (long long)x * plane * 2;
+        // member-independent inputs are requested ahead of their phase: L2 latency never shows
+        double2 p01[KR], p23[KR], pfb[KO];
+        double pW[KO];
+        auto fetch_raw_inputs = [&](int x) {
+            const char *base = reinterpret_cast<const char *>(a.DA) + ((long long)x * plane + go_raw) * 32;
 #pragma unroll
-            for (int q = 0; q < KR; ++q)
-                if (raw_r[q] >= 0) {
-                    d01[q] = __ldg(DAx + (raw_r[q] * nx + raw_c[q]) * 2);
-                    d23[q] = __ldg(DAx + (raw_r[q] * nx + raw_c[q]) * 2 + 1);
-                }
-        };
-        auto load_cell_inputs = [&](int x) {
-#pragma unroll
-            for (int j = 0; j < KO; ++j)
-                if (own_lr[j] >= 0) {
-                    const long long o = (long long)x * plane + (ra + own_lr[j]) * nx + own_c[j];
-                    f_b[j] = __ldg(a.DB + o);
-                    f_W[j] = __ldg(a.W + o);
-                }
-        };
-#pragma unroll
-        for (int q = 0; q < KR; ++q) d01[q] = d23[q] = make_double2(0.0, 0.0);
-#pragma unroll
-        for (int j = 0; j < KO; ++j) { f_b[j] = make_double2(0.0, 0.0); f_W[j] = 0.0; }
-        if (a.sw.dynamics) load_raw_inputs(0);
-        load_cell_inputs(0);
-
-        if (timing) tlast = clock64();
-        for (int x = 0; x < steps; ++x) {
-            const int par = x & 1;
-
-            // ---------------- phase A: raw advection / divergence (calcDynamics, NESOSIM.py:189-222) where an
-            // ocean cell of this strip will read it
-            if (a.sw.dynamics) {
-                const int hpar = par * 8 * nx;   // halo offset of today's parity block
-#pragma unroll
-                for (int q = 0; q < KR; ++q) {
-                    if (raw_r[q] < 0) continue;
-                    const int r = raw_r[q], c = raw_c[q];
-                    auto rowp = [&](int off) -> const double * {
-                        return s_plane + ((off & HALO_FLAG) ? (off & ~HALO_FLAG) + hpar : off);
-                    };
-                    auto layer1 = [&](int off) -> int { return (off & HALO_FLAG) ? 2 * nx : PE; };
-                    const double *c0 = rowp(raw_ce[q]), *u0 = rowp(raw_up[q]), *w0 = rowp(raw_dn[q]);
-                    const double *c1 = c0 + layer1(raw_ce[q]), *u1 = u0 + layer1(raw_up[q]), *w1 = w0 + layer1(raw_dn[q]);
-                    const double h0 = c0[0], h1 = c1[0];
-                    double gx0, gy0, gx1, gy1;
-                    if (tid + q * NT < n_raw_int) {
-                        gx0 = div_const(sub(c0[1], c0[-1]), a.g.two_dx);
-                        gy0 = div_const(sub(w0[0], u0[0]), a.g.two_dx);
-                        gx1 = div_const(sub(c1[1], c1[-1]), a.g.two_dx);
-                        gy1 = div_const(sub(w1[0], u1[0]), a.g.two_dx);
-                    } else {   // first/last row or column: one-sided differences (np.gradient edge_order=1)
-                        const int cm = c > 0 ? -1 : 0, cp = c < nx - 1 ? 1 : 0;
-                        gx0 = gradient1d(c0[cm], h0, c0[cp], c, nx, a.g);
-                        gy0 = gradient1d(u0[0], h0, w0[0], r, ny, a.g);
-                        gx1 = gradient1d(c1[cm], h1, c1[cp], c, nx, a.g);
-                        gy1 = gradient1d(u1[0], h1, w1[0], r, ny, a.g);
-                    }
-                    const int ro = (r - ra + 1) * SXR + c + 1;
-                    s_adv[ro] = make_double2(zero_if_nonfinite(adv_term(d01[q].x, d01[q].y, gx0, gy0)),
-                                             zero_if_nonfinite(adv_term(d01[q].x, d01[q].y, gx1, gy1)));
-                    s_div[ro] = make_double2(zero_if_nonfinite(div_term(h0, d23[q].x, d23[q].y)),
-                                             zero_if_nonfinite(div_term(h1, d23[q].x, d23[q].y)));
-                }
-                if (x + 1 < steps) load_raw_inputs(x + 1);
+            for (int q = 0; q < KR; ++q) {
+                const double2 *p = reinterpret_cast<const double2 *>(base + (size_t)a_c[q] * 4u);
+                p01[q] = __ldg(p);
+                p23[q] = __ldg(p + 1);
             }
-            ENS_TICK(0)   // phase A
-            // the bulk stores of the previous day must have finished READING the planes before they change
-            if (store_lane) bulk_wait_read<0>();
-            ENS_TICK(1)   // (store warp: bulk stores drained)
-            __syncthreads();
-            ENS_TICK(2)   // wait for the CTA
-
-            // ---------------- phase B: owned ocean cells -- point-wise terms, 3x3 smoothing, update, plane entries
+        };
+        auto fetch_cell_inputs = [&](int x) {
+            const char *bb = reinterpret_cast<const char *>(a.DB) + ((long long)x * plane + go_own) * 16;
+            const char *bw = reinterpret_cast<const char *>(a.W) + ((long long)x * plane + go_own) * 8;
 #pragma unroll
             for (int j = 0; j < KO; ++j) {
-                if (own_lr[j] < 0) continue;
-                const int lr = own_lr[j], c = own_c[j], ci = lr * nx + c;
-                const double h0 = s_plane[PL_H0 * PE + ci], h1 = s_plane[PL_H1 * PE + ci];
-                const double W = f_W[j];
-                const double wt = wind_flag(W, mc.wpt);
-                const double lead = a.sw.leadloss ? -mul(mul(mul(mul(mul(wt, mc.llf), a.k.deltaT), h0), W), f_b[j].y) : 0.0;
-                const double atm = a.sw.atmloss ? atm_loss(wt, h0, W, mc, a.k) : 0.0;
-                double wpl = 0.0, wpg = 0.0, wpn = 0.0;
-                if (a.sw.windpack) wind_packing(wt, h0, mc, a.k, wpl, wpg, wpn);
-                accLead[j] = add(accLead[j], lead);
-                accAtm[j] = add(accAtm[j], atm);
-                accWpl[j] = add(accWpl[j], wpl);
-                accWpg[j] = add(accWpg[j], wpg);
-                accWp[j] = add(accWp[j], wpn);
-                double t0 = add(add(add(add(h0, f_b[j].x), wpl), lead), atm);   // NESOSIM.py:327 before the dynamics terms
-                double t1 = add(h1, wpg);                                      // NESOSIM.py:329
-                if (a.sw.dynamics) {
-                    // astropy tap order: rows outer, columns inner, flipped kernel, accumulators start at 0.0
-                    const double2 *pa = s_adv + lr * SXR + c, *pd = s_div + lr * SXR + c;
-                    double a0 = 0.0, a1 = 0.0, d0 = 0.0, d1 = 0.0;
-#pragma unroll
-                    for (int ii = 0; ii < 3; ++ii)
-#pragma unroll
-                        for (int jj = 0; jj < 3; ++jj) {
-                            const double wgt = a.w[(2 - ii) * 3 + (2 - jj)];
-                            const double2 va = pa[ii * SXR + jj], vd = pd[ii * SXR + jj];
-                            a0 = add(a0, mul(va.x, wgt));
-                            a1 = add(a1, mul(va.y, wgt));
-                            d0 = add(d0, mul(vd.x, wgt));
-                            d1 = add(d1, mul(vd.y, wgt));
-                        }
-                    // smooth_snow's division, then fill_nan_no_negative on an ocean cell (NESOSIM.py:276-284)
-                    a0 = mask_nan(div_const(a0, a.conv_div), false, false);
-                    a1 = mask_nan(div_const(a1, a.conv_div), false, false);
-                    d0 = mask_nan(div_const(d0, a.conv_div), false, false);
-                    d1 = mask_nan(div_const(d1, a.conv_div), false, false);
-                    accAdv[j] = add(add(accAdv[j], a0), a1);     // NESOSIM.py:290
-                    accDiv[j] = add(add(accDiv[j], d0), d1);     // NESOSIM.py:291
-                    t0 = add(add(t0, a0), d0);
-                    t1 = add(add(t1, a1), d1);
-                } else {
-                    accAdv[j] = add(add(accAdv[j], 0.0), 0.0);
-                    accDiv[j] = add(add(accDiv[j], 0.0), 0.0);
-                    t0 = add(add(t0, 0.0), 0.0);
-                    t1 = add(add(t1, 0.0), 0.0);
-                }
-                const double h0n = mask_nan(t0, false, true), h1n = mask_nan(t1, false, true);   // NESOSIM.py:332-333
-                put_h(par ^ 1, lr, c, h0n, h1n);
-                s_plane[PL_DENS * PE + ci] = density_variable(h0n, h1n, false, a.k);
-                s_plane[PL_ADV * PE + ci] = accAdv[j];
-                s_plane[PL_DIV * PE + ci] = accDiv[j];
-                s_plane[PL_LEAD * PE + ci] = accLead[j];
-                s_plane[PL_ATM * PE + ci] = accAtm[j];
-                s_plane[PL_WPL * PE + ci] = accWpl[j];
-                s_plane[PL_WPG * PE + ci] = accWpg[j];
-                s_plane[PL_WP * PE + ci] = accWp[j];
+                pfb[j] = __ldg(reinterpret_cast<const double2 *>(bb + (size_t)b_ci[j] * 2u));
+                pW[j] = __ldg(reinterpret_cast<const double *>(bw + b_ci[j]));
             }
-            // ---------------- land cells.  Step 0 sees the initial depths; afterwards h is NaN, so every switched-on
-            // term is NaN and every switched-off term adds 0 (NESOSIM.py:287-322): closed form, written on the
-            // first two days (both halo parities) and then left alone in the planes.
-            if (x <= 1 && comp) {
-                for (int i = tid; i < n_land; i += NT) {
-                    const int code = s_land_code[i], lr = code >> 7, c = code & 127, ci = lr * nx + c;
+        };
+#pragma unroll
+        for (int q = 0; q < KR; ++q) p01[q] = p23[q] = make_double2(0.0, 0.0);
+        if (a.sw.dynamics) fetch_raw_inputs(0);
+
+        if (TIMING && timing) tlast = clock64();
+        for (int x = 0; x < steps; ++x) {
+            fetch_cell_inputs(x);   // consumed in B, in flight during A
+
+            // ---------------- A: raw advection / divergence
+            if (a.sw.dynamics) {
+                unsigned bad = 1u;
+                if (!(flags & (1u << 16)) && all_fast) {
+                    bad = 0u;
+#pragma unroll
+                    for (int q = 0; q < KR; ++q) {
+                        const unsigned ac = a_c[q];
+                        unsigned bq = 0u;
+                        const double h0 = LD(ac), h1 = LD(ac + PEXB);
+                        const double gx0 = div_const_flagged(sub(LD(ac + 8u), LD(ac - 8u)), a.g.two_dx, bq);
+                        const double gy0 = div_const_flagged(sub(LD(ac + ROWB), LD(ac - ROWB)), a.g.two_dx, bq);
+                        const double gx1 = div_const_flagged(sub(LD(ac + PEXB + 8u), LD(ac + PEXB - 8u)), a.g.two_dx, bq);
+                        const double gy1 = div_const_flagged(sub(LD(ac + PEXB + ROWB), LD(ac + PEXB - ROWB)), a.g.two_dx, bq);
+                        ST2(a_t[q], make_double2(zero_if_nonfinite(adv_term(p01[q].x, p01[q].y, gx0, gy0)),
+                                                 zero_if_nonfinite(adv_term(p01[q].x, p01[q].y, gx1, gy1))));
+                        ST2(a_t[q] + L.tile_bytes, make_double2(zero_if_nonfinite(div_term(h0, p23[q].x, p23[q].y)),
+                                                                zero_if_nonfinite(div_term(h1, p23[q].x, p23[q].y))));
+                        bad |= bq & (flags >> q);
+                    }
+                    bad &= 1u;
+                }
+                if (bad) {   // grid-edge entries (one-sided differences, np.gradient edge_order=1) and exact redo
+#pragma unroll
+                    for (int q = 0; q < KR; ++q) {
+                        if (!((flags >> q) & 1u)) continue;
+                        const unsigned ac = a_c[q];
+                        const int cell = (int)(ac >> 3), lr2 = cell / nx, c = cell - lr2 * nx, r = ra - 2 + lr2;
+                        const unsigned au = r > 0 ? ac - ROWB : ac, aw = r < ny - 1 ? ac + ROWB : ac;
+                        const unsigned am = c > 0 ? ac - 8u : ac, ap = c < nx - 1 ? ac + 8u : ac;
+                        const double h0 = LD(ac), h1 = LD(ac + PEXB);
+                        const double gx0 = gradient1d(LD(am), h0, LD(ap), c, nx, a.g);
+                        const double gy0 = gradient1d(LD(au), h0, LD(aw), r, ny, a.g);
+                        const double gx1 = gradient1d(LD(am + PEXB), h1, LD(ap + PEXB), c, nx, a.g);
+                        const double gy1 = gradient1d(LD(au + PEXB), h1, LD(aw + PEXB), r, ny, a.g);
+                        ST2(a_t[q], make_double2(zero_if_nonfinite(adv_term(p01[q].x, p01[q].y, gx0, gy0)),
+                                                 zero_if_nonfinite(adv_term(p01[q].x, p01[q].y, gx1, gy1))));
+                        ST2(a_t[q] + L.tile_bytes, make_double2(zero_if_nonfinite(div_term(h0, p23[q].x, p23[q].y)),
+                                                                zero_if_nonfinite(div_term(h1, p23[q].x, p23[q].y))));
+                    }
+                }
+            }
+            ENS_TICK(0)   // A
+            cluster_arrive_release();   // #1: this CTA no longer reads its halo rows of day x
+            bar_sync(BAR_A, NTC);       // raw tiles complete
+            ENS_TICK(1)
+
+            // ---------------- B: owned ocean cells, everything into registers
+            double r_h0[KO], r_h1[KO], r_dn[KO], r_adv[KO], r_div[KO], r_lead[KO], r_atm[KO], r_wpl[KO], r_wpg[KO], r_wp[KO];
+            auto b_compute = [&](auto exact_tag, unsigned &bad) {
+                constexpr bool EXACT = decltype(exact_tag)::value;
+#pragma unroll
+                for (int j = 0; j < KO; ++j) {
+                    const unsigned ci = b_ci[j];
+                    unsigned bq = 0u;
+                    double2 sa = make_double2(0.0, 0.0), sd = sa;              // zeros when dynamicsInc == 0 (NESOSIM.py:287-288)
+                    if (a.sw.dynamics) {
+                        // astropy tap order: rows outer, columns inner, flipped kernel, accumulators start at 0.0;
+                        // then smooth_snow's division and fill_nan_no_negative on an ocean cell (NESOSIM.py:276-284)
+                        const unsigned ta = b_t[j], td = ta + L.tile_bytes;
+                        double a0 = 0.0, a1 = 0.0, d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                        for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+                            for (int jj = 0; jj < 3; ++jj) {
+                                const double wgt = a.w[(2 - ii) * 3 + (2 - jj)];
+                                const double2 va = LD2(ta + (unsigned)(ii * SXR + jj) * 16u);
+                                const double2 vd = LD2(td + (unsigned)(ii * SXR + jj) * 16u);
+                                a0 = add(a0, mul(va.x, wgt));
+                                a1 = add(a1, mul(va.y, wgt));
+                                d0 = add(d0, mul(vd.x, wgt));
+                                d1 = add(d1, mul(vd.y, wgt));
+                            }
+                        if constexpr (EXACT) {
+                            sa = make_double2(mask_nan(div_const(a0, a.conv_div), false, false), mask_nan(div_const(a1, a.conv_div), false, false));
+                            sd = make_double2(mask_nan(div_const(d0, a.conv_div), false, false), mask_nan(div_const(d1, a.conv_div), false, false));
+                        } else {
+                            sa = make_double2(mask_nan(div_const_flagged(a0, a.conv_div, bq), false, false),
+                                              mask_nan(div_const_flagged(a1, a.conv_div, bq), false, false));
+                            sd = make_double2(mask_nan(div_const_flagged(d0, a.conv_div, bq), false, false),
+                                              mask_nan(div_const_flagged(d1, a.conv_div, bq), false, false));
+                        }
+                    }
+                    const double h0 = LD(HOWN + ci), h1 = LD(HOWN + PEXB + ci);
+                    const double W = pW[j];
+                    const double2 fb = pfb[j];
+                    const unsigned wsel = (W > LD(L.off_coef + 64u)) ? 8u : 0u;   // windT (NaN > thr is False) picks the pair entry
+                    double lead = -mul(mul(mul(LD(L.off_coef + wsel), h0), W), fb.y);
+                    double atm = -mul(mul(mul(LD(L.off_coef + 16u + wsel), h0), W), LD(L.off_coef + 72u));
+                    double wpl = mul(LD(L.off_coef + 32u + wsel), h0);
+                    double wpg = mul(mul(LD(L.off_coef + 48u + wsel), h0), a.k.rho_ratio);
+                    double wpn = add(wpl, wpg);
+                    if (!a.sw.leadloss) lead = 0.0;
+                    if (!a.sw.atmloss) atm = 0.0;
+                    if (!a.sw.windpack) wpl = wpg = wpn = 0.0;
+                    r_lead[j] = add(LD(L.plane_off(PL_LEAD) + ci), lead);
+                    r_atm[j] = add(LD(L.plane_off(PL_ATM) + ci), atm);
+                    r_wpl[j] = add(LD(L.plane_off(PL_WPL) + ci), wpl);
+                    r_wpg[j] = add(LD(L.plane_off(PL_WPG) + ci), wpg);
+                    r_wp[j] = add(LD(L.plane_off(PL_WP) + ci), wpn);
+                    double t0 = add(add(add(add(h0, fb.x), wpl), lead), atm);   // NESOSIM.py:327 before the dynamics terms
+                    double t1 = add(h1, wpg);                                  // NESOSIM.py:329
+                    r_adv[j] = add(add(LD(L.plane_off(PL_ADV) + ci), sa.x), sa.y);   // NESOSIM.py:290
+                    r_div[j] = add(add(LD(L.plane_off(PL_DIV) + ci), sd.x), sd.y);   // NESOSIM.py:291
+                    t0 = add(add(t0, sa.x), sd.x);
+                    t1 = add(add(t1, sa.y), sd.y);
+                    r_h0[j] = mask_nan(t0, false, true);   // NESOSIM.py:332-333
+                    r_h1[j] = mask_nan(t1, false, true);
+                    if constexpr (EXACT) r_dn[j] = density_variable(r_h0[j], r_h1[j], false, a.k);
+                    else r_dn[j] = density_ocean_flagged(r_h0[j], r_h1[j], a.k, bq);
+                    bad |= bq & (flags >> (8 + j));
+                }
+            };
+            {
+                unsigned bad = 1u;
+                if (all_fast) {
+                    bad = 0u;
+                    b_compute(std::false_type{}, bad);
+                    bad &= 1u;
+                }
+                if (bad) b_compute(std::true_type{}, bad);
+            }
+            if (a.sw.dynamics && x + 1 < steps) fetch_raw_inputs(x + 1);   // consumed in the next A
+            ENS_TICK(2)   // B compute
+            cluster_wait_acquire();         // #1: every CTA of the cluster has finished reading its halo rows
+            ENS_TICK(3)
+            bar_sync(BAR_DRAIN, NTH);       // the bulk stores of day x have finished READING the planes
+            ENS_TICK(4)   // drain
+
+            // ---------------- publish: planes of day x+1 and the neighbours' halo rows
+#pragma unroll
+            for (int j = 0; j < KO; ++j) {
+                if (!((flags >> (8 + j)) & 1u)) continue;
+                const unsigned ci = b_ci[j];
+                ST(HOWN + ci, r_h0[j]);
+                ST(HOWN + PEXB + ci, r_h1[j]);
+                ST(L.plane_off(PL_DENS) + ci, r_dn[j]);
+                ST(L.plane_off(PL_ADV) + ci, r_adv[j]);
+                ST(L.plane_off(PL_DIV) + ci, r_div[j]);
+                ST(L.plane_off(PL_LEAD) + ci, r_lead[j]);
+                ST(L.plane_off(PL_ATM) + ci, r_atm[j]);
+                ST(L.plane_off(PL_WPL) + ci, r_wpl[j]);
+                ST(L.plane_off(PL_WPG) + ci, r_wpg[j]);
+                ST(L.plane_off(PL_WP) + ci, r_wp[j]);
+                if (b_rem[j]) {
+                    st_cluster(b_rem[j], r_h0[j]);
+                    st_cluster(b_rem[j] + PEXB, r_h1[j]);
+                }
+            }
+            // land cells.  Step 0 sees the initial depths; afterwards h is NaN, so every switched-on term is NaN
+            // and every switched-off term adds 0 (NESOSIM.py:287-322): closed form, written on the first two days
+            // and then left alone in the planes.
+            if (x <= 1) {
+                const MemberCoef mc = a.coef[m];
+                // closed-form land values from slot 2 on (slot 1 is computed from the initial depths)
+                const double landAdv = a.sw.dynamics ? nan : 0.0, landLead = a.sw.leadloss ? nan : 0.0;
+                const double landAtm = a.sw.atmloss ? nan : 0.0, landWp = a.sw.windpack ? nan : 0.0;
+                for (int i = tid; i < n_land; i += NTC) {
+                    const int code = s_land_code[i], lr = code >> 7, c = code & 127;
+                    const unsigned ci = (unsigned)(lr * nx + c) * 8u;
                     double vLead = landLead, vAtm = landAtm, vWpl = landWp, vWpg = landWp, vWp = landWp;
                     if (x == 0) {
-                        const long long o = (long long)(ra + lr) * nx + c;
-                        const double h0 = s_plane[PL_H0 * PE + ci];
+                        const long long o = go_own + (long long)lr * nx + c;
+                        const double h0 = LD(HOWN + ci);
                         const double W = __ldg(a.W + o);
                         const double omc = __ldg(a.DB + o).y;
                         const double wt = wind_flag(W, mc.wpt);
@@ -464,77 +648,43 @@ __global__ void __launch_bounds__(NT + 32, 1) ensemble_season_kernel(const __gri
                         vWpg = add(0.0, wpg);
                         vWp = add(0.0, wpn);
                     }
-                    put_h(par ^ 1, lr, c, nan, nan);
-                    s_plane[PL_DENS * PE + ci] = nan;
-                    s_plane[PL_ADV * PE + ci] = landAdv;
-                    s_plane[PL_DIV * PE + ci] = landAdv;
-                    s_plane[PL_LEAD * PE + ci] = vLead;
-                    s_plane[PL_ATM * PE + ci] = vAtm;
-                    s_plane[PL_WPL * PE + ci] = vWpl;
-                    s_plane[PL_WPG * PE + ci] = vWpg;
-                    s_plane[PL_WP * PE + ci] = vWp;
+                    put_h(lr, c, nan, nan);
+                    ST(L.plane_off(PL_DENS) + ci, nan);
+                    ST(L.plane_off(PL_ADV) + ci, landAdv);
+                    ST(L.plane_off(PL_DIV) + ci, landAdv);
+                    ST(L.plane_off(PL_LEAD) + ci, vLead);
+                    ST(L.plane_off(PL_ATM) + ci, vAtm);
+                    ST(L.plane_off(PL_WPL) + ci, vWpl);
+                    ST(L.plane_off(PL_WPG) + ci, vWpg);
+                    ST(L.plane_off(PL_WP) + ci, vWp);
                 }
             }
             fence_async_smem();
-            ENS_TICK(3)   // phase B
-            // Planes and pushed halos of day x+1 are written: arrive now, wait at the end of the day.
-            cluster_arrive_release();
-            __syncthreads();
-            ENS_TICK(4)   // arrive + CTA barrier
-            if (store_lane) {
-                const unsigned bytes = (unsigned)ncell * 8u;
-#pragma unroll
-                for (int p = 0; p < ENS_NPLANE; ++p) {
-                    const int v = ENS_PLANE_VAR[p];
-                    if (a.out[v]) bulk_store(outp(v, x + 1), s_plane + p * PE, bytes);
-                }
-                bulk_commit();
-            }
-            // snowAcc / snowOcean: member-independent running sums, copied row-contiguously
-            if (comp && (a.out[V_ACC] || a.out[V_OCEAN])) {
-                const double2 *DCx = a.DC + (long long)x * plane + (long long)ra * nx;
-                double *pa_ = a.out[V_ACC] ? outp(V_ACC, x + 1) : nullptr;
-                double *po_ = a.out[V_OCEAN] ? outp(V_OCEAN, x + 1) : nullptr;
-                for (int base = 0; base < ncell; base += 4 * NT) {   // all loads of a batch in flight before the stores
-                    double2 cum[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int i = base + q * NT + tid;
-                        cum[q] = (i < ncell) ? __ldg(DCx + i) : make_double2(0.0, 0.0);
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int i = base + q * NT + tid;
-                        if (i < ncell) {
-                            if (pa_) __stcs(pa_ + i, cum[q].x);
-                            if (po_) __stcs(po_ + i, cum[q].y);
-                        }
-                    }
-                }
-            }
-            if (x + 1 < steps) load_cell_inputs(x + 1);
-            ENS_TICK(5)   // bulk issue + running-sum copies
-            cluster_wait_acquire();   // pushed halos of day x+1 are visible; raw tiles are free again
-            ENS_TICK(6)   // wait for the cluster
+            cluster_arrive_release();       // #2: my halo pushes of day x+1 are done
+            ENS_TICK(5)   // publish
+            bar_sync(BAR_STORE, NTH);       // planes complete: the DMA warp issues the bulk stores
+            ENS_TICK(6)
+            cluster_wait_acquire();         // #2: the neighbours' pushes have landed in my halo rows
+            ENS_TICK(7)
         }
     }
-    if (store_lane) bulk_wait_all();
+    if (dma_lane) bulk_wait_all();
 #undef ENS_TICK
-    if (timing)
-        for (int q = 0; q < 8; ++q) a.timing[(long long)blockIdx.x * 8 + q] = tacc[q];
+    if (TIMING && timing)
+        for (int q = 0; q < (TIMING ? 8 : 1); ++q) a.timing[(long long)blockIdx.x * ENS_NTIMER + (dma_lane ? 8 : 0) + q] = tacc[q];
 }
 
 // host-side state of this path
 struct EnsembleState {
     bool derived_valid = false;
-    void *derived = nullptr;           // DA | DB | DC
+    void *derived = nullptr;           // DA | DB | cumAcc | cumOc
     size_t derived_bytes = 0;
     unsigned short *codes_dev = nullptr;
     StripTables tables;
     bool tables_ready = false;
-    int variant = 0;                   // index into the host's kernel-variant table
     size_t smem_bytes = 0;
     int max_clusters = 0;
+    int variant = -1;
 };
 
 inline void ensemble_release(EnsembleState &e) {

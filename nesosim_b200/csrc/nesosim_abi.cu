@@ -298,20 +298,20 @@ int launch_init(nesosim_ctx *ctx, const double *ic, int ic_per_member, const dou
 
 // ------------------------------------------------------------------ season-resident ensemble path (host side)
 
+// Build variants of the season kernel: NTC compute threads (+ one DMA warp), KR raw-list entries and KO owned
+// ocean cells per compute thread.  A variant fits a strip decomposition when every strip's lists fit KR*NTC and
+// KO*NTC; fewer threads mean more registers per thread (65536 / (NTC+32)).  Order = preference.
 struct EnsVariant {
     const char *name;
-    int nt, ko, kr;                       // threads per CTA, owned ocean cells and raw-list entries per thread
+    int ntc, kr, ko;
     void (*kernel)(const EnsArgs);
+    void (*kernel_timing)(const EnsArgs);
 };
-
-// nt = compute threads; one more warp issues the bulk stores.  Total warps 16 / 12 / 8 allow 128 / 168 / 255
-// registers per thread; every entry compiles without spills (checked with -Xptxas -v).  More threads first.
+#define ENS_V(ntc, kr, ko) \
+    {"t" #ntc "r" #kr "o" #ko, ntc, kr, ko, ensemble_season_kernel<ntc, kr, ko, false>, ensemble_season_kernel<ntc, kr, ko, true>}
 const EnsVariant *ens_variants(int *n) {
     static const EnsVariant v[] = {
-        {"t480k1", 480, 1, 2, ensemble_season_kernel<480, 1, 2>},
-        {"t352k2", 352, 2, 3, ensemble_season_kernel<352, 2, 3>},
-        {"t224k3", 224, 3, 5, ensemble_season_kernel<224, 3, 5>},
-        {"t224k4", 224, 4, 6, ensemble_season_kernel<224, 4, 6>},
+        ENS_V(608, 2, 1), ENS_V(480, 2, 2), ENS_V(352, 3, 2), ENS_V(736, 2, 1), ENS_V(224, 4, 3), ENS_V(352, 6, 5),
     };
     *n = (int)(sizeof(v) / sizeof(v[0]));
     return v;
@@ -321,15 +321,14 @@ constexpr size_t ENS_SMEM_CAP = 227 * 1024;
 
 // Cut the grid into `cl` row strips with balanced work and compile the mask into the per-strip cell lists the
 // kernel walks.  A strip must satisfy the bulk-copy rules (16-byte aligned start, 16-byte multiple size), hold
-// at least the two rows its neighbours need as halo, and fit the per-thread list capacities.
+// at least ENS_MIN_ROWS rows (its top two and bottom two rows are its neighbours' halos) and fit shared memory.
 // Returns false if no such cut exists for this cluster size.
-bool try_strip_tables(nesosim_ctx *ctx, int cl, int cap_ocean, int cap_raw, StripTables &t,
-                      std::vector<unsigned short> &codes, int &max_ocean_out, int &max_raw_out, size_t &smem_bytes,
+bool try_strip_tables(nesosim_ctx *ctx, int cl, StripTables &t, std::vector<unsigned short> &codes, size_t &smem_bytes,
                       double &day_cost) {
     const int ny = ctx->cfg.ny, nx = ctx->cfg.nx;
     const std::vector<uint8_t> &mask = ctx->mask_host;
     auto land = [&](int r, int c) { const uint8_t m = mask[(size_t)r * nx + c]; return m > 10 || m < 1; };
-    if (ny < 2 * cl) return false;
+    if (ny < ENS_MIN_ROWS * cl) return false;
     // per-row ocean count and count of cells with an ocean cell in their 3x3 neighbourhood
     std::vector<int> oc(ny, 0), dil(ny, 0);
     for (int r = 0; r < ny; ++r)
@@ -343,28 +342,28 @@ bool try_strip_tables(nesosim_ctx *ctx, int cl, int cap_ocean, int cap_raw, Stri
         }
     std::vector<long long> coc(ny + 1, 0), cdil(ny + 1, 0);
     for (int r = 0; r < ny; ++r) { coc[r + 1] = coc[r] + oc[r]; cdil[r + 1] = cdil[r] + dil[r]; }
-    const int max_rows_smem = [&] {   // tallest strip whose tiles fit in shared memory (lists sized generously)
+    const int max_rows_smem = [&] {   // tallest strip whose tiles fit in shared memory (land list sized generously)
         int best = 0;
-        for (int rows = 2; rows <= ny; ++rows)
-            if (ens_smem_bytes(rows, nx, (rows + 2) * nx + rows * nx + 16) <= ENS_SMEM_CAP) best = rows;
+        for (int rows = ENS_MIN_ROWS; rows <= ny; ++rows)
+            if (ens_layout(rows, nx, rows * nx).total <= ENS_SMEM_CAP) best = rows;
         return best;
     }();
     auto strip_cost = [&](int ra, int rb) -> double {   // < 0: not allowed
         const int rows = rb - ra;
-        if (rows < 2 || rows > max_rows_smem) return -1.0;
+        if (rows < ENS_MIN_ROWS || rows > max_rows_smem) return -1.0;
         if (((long long)rows * nx) % 2 || ((long long)ra * nx) % 2) return -1.0;
         const long long ocean = coc[rb] - coc[ra];
         const long long raw = cdil[std::min(rb + 1, ny)] - cdil[std::max(ra - 1, 0)];
-        if (ocean > cap_ocean || raw > cap_raw) return -1.0;
-        return 11.0 * ocean + 4.5 * raw + 0.6 * rows * nx;   // cycles per day measured on B200 (phase timers)
+        // relative cost per day: an owned ocean cell ~3 raw entries of arithmetic; every cell is stored
+        return 3.0 * ocean + 1.0 * raw + 0.5 * rows * nx;
     };
     const double INF = 1e300;
     std::vector<std::vector<double>> best(cl + 1, std::vector<double>(ny + 1, INF));
     std::vector<std::vector<int>> from(cl + 1, std::vector<int>(ny + 1, -1));
     best[0][0] = 0.0;
     for (int k = 1; k <= cl; ++k)
-        for (int r = 2 * k; r <= ny; ++r)
-            for (int q = 2 * (k - 1); q <= r - 2; ++q) {
+        for (int r = ENS_MIN_ROWS * k; r <= ny; ++r)
+            for (int q = ENS_MIN_ROWS * (k - 1); q <= r - ENS_MIN_ROWS; ++q) {
                 if (best[k - 1][q] >= INF) continue;
                 const double c = strip_cost(q, r);
                 if (c < 0) continue;
@@ -411,14 +410,13 @@ bool try_strip_tables(nesosim_ctx *ctx, int cl, int cap_ocean, int cap_raw, Stri
     }
     codes.push_back(0);
     t.rows_alloc = max_rows;
-    t.raw_alloc = max_raw;
+    t.raw_max = max_raw;
+    t.ocean_max = max_ocean;
     t.land_alloc = max_land;
-    smem_bytes = ens_smem_bytes(max_rows, nx, (max_raw + 7) / 8 * 8 + max_land);
+    smem_bytes = ens_layout(max_rows, nx, max_land).total;
     if (smem_bytes > ENS_SMEM_CAP) return false;
-    max_ocean_out = max_ocean;
-    max_raw_out = max_raw;
     day_cost = best[cl][ny];
-    return max_raw <= cap_raw;   // (the DP bounds the raw count from above only approximately)
+    return true;
 }
 
 int max_active_clusters(const EnsVariant *v, int cl, size_t smem_bytes) {
@@ -426,12 +424,13 @@ int max_active_clusters(const EnsVariant *v, int cl, size_t smem_bytes) {
         cudaGetLastError();
         return 0;
     }
+    if (cl > 8) cudaFuncSetAttribute((const void *)v->kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cfg.blockDim = dim3(v->nt + 32);
+    cfg.blockDim = dim3(v->ntc + 32);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.gridDim = dim3(cl * 64);
     int n = 0;
@@ -442,42 +441,43 @@ int max_active_clusters(const EnsVariant *v, int cl, size_t smem_bytes) {
     return n;
 }
 
-// Choose the cluster size (CTAs per member): every size whose strips fit in shared memory is costed as
-// rounds(members / co-resident clusters) x (heaviest strip + fixed per-day overhead), the cheapest wins.
+// Choose the cluster size (CTAs per member) and the build variant: every size whose strips fit in shared memory is
+// costed as rounds(members / co-resident clusters) x (heaviest strip + fixed per-day overhead), the cheapest wins;
+// the variant is the first in preference order whose per-thread capacities hold the strips' lists.
 int build_strip_tables(nesosim_ctx *ctx) {
     EnsembleState &e = ctx->ens;
     if (e.tables_ready) return NESOSIM_OK;
     int forced = 0;
     if (const char *env = getenv("NESOSIM_ENS_CLUSTER")) forced = atoi(env);
-    std::vector<unsigned short> best_codes;
-    double best_time = 1e300;
+    const char *forced_var = getenv("NESOSIM_ENS_VARIANT");
     int nv;
     const EnsVariant *vars = ens_variants(&nv);
-    const char *forced_var = getenv("NESOSIM_ENS_VARIANT");
+    std::vector<unsigned short> best_codes;
+    double best_time = 1e300;
     for (int cl = 2; cl <= ENS_MAX_CLUSTER; ++cl) {
         if (forced && cl != forced) continue;
-        for (int vi = 0; vi < nv; ++vi) {
-            const EnsVariant *v = &vars[vi];
-            if (forced_var && strcmp(forced_var, v->name)) continue;
-            StripTables t;
-            std::vector<unsigned short> codes;
-            int mo = 0, mr = 0;
-            size_t smem = 0;
-            double day_cost = 0;
-            if (!try_strip_tables(ctx, cl, v->ko * v->nt, v->kr * v->nt, t, codes, mo, mr, smem, day_cost)) continue;
-            const int ncl = max_active_clusters(v, cl, smem);
-            if (ncl < 1) continue;
-            const int rounds = (ctx->cfg.n_members + ncl - 1) / ncl;
-            // per-day time: the strip's work spread over the compute threads + fixed barrier/drain overhead
-            const double time = rounds * (day_cost * (512.0 / v->nt) * 0.5 + day_cost * 0.5 + 3000.0);
-            if (time < best_time) {
-                best_time = time;
-                e.tables = t;
-                e.variant = vi;
-                e.smem_bytes = smem;
-                e.max_clusters = ncl;
-                best_codes.swap(codes);
-            }
+        StripTables t;
+        std::vector<unsigned short> codes;
+        size_t smem = 0;
+        double day_cost = 0;
+        if (!try_strip_tables(ctx, cl, t, codes, smem, day_cost)) continue;
+        int vi = -1;
+        for (int i = 0; i < nv && vi < 0; ++i) {
+            if (forced_var && *forced_var && strcmp(forced_var, vars[i].name)) continue;
+            if (t.raw_max <= vars[i].kr * vars[i].ntc && t.ocean_max <= vars[i].ko * vars[i].ntc) vi = i;
+        }
+        if (vi < 0) continue;
+        const int ncl = max_active_clusters(&vars[vi], cl, smem);
+        if (ncl < 1) continue;
+        const int rounds = (ctx->cfg.n_members + ncl - 1) / ncl;
+        const double time = rounds * (day_cost + 1500.0);   // heaviest strip + fixed barrier overhead per day
+        if (time < best_time) {
+            best_time = time;
+            e.tables = t;
+            e.smem_bytes = smem;
+            e.max_clusters = ncl;
+            e.variant = vi;
+            best_codes.swap(codes);
         }
     }
     if (best_time >= 1e300) return fail(NESOSIM_ERR_ARG, "grid does not fit the season-resident kernel's shared-memory strips");
@@ -493,7 +493,8 @@ int build_strip_tables(nesosim_ctx *ctx) {
 bool ensemble_eligible(nesosim_ctx *ctx, int first_step, int num_steps, const nesosim_outputs *out, const char **why) {
     const nesosim_config &c = ctx->cfg;
     if (c.nx > ENS_MAX_NX) { *why = "nx > 96"; return false; }
-    if (c.ny < 8) { *why = "ny < 8"; return false; }
+    if (c.nx < 3) { *why = "nx < 3"; return false; }
+    if (c.ny < 2 * ENS_MIN_ROWS) { *why = "ny < 8"; return false; }
     if (((long long)c.ny * c.nx) % 2) { *why = "odd number of cells (bulk stores need 16-byte aligned planes)"; return false; }
     if (c.density_clim) { *why = "densityType='clim'"; return false; }
     if (first_step != 0 || num_steps != c.num_days - 1) { *why = "partial season"; return false; }
@@ -519,30 +520,32 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
         CU(cudaMalloc(&e.derived, need));
         e.derived_bytes = need;
     }
-    double2 *DA = (double2 *)e.derived, *DB = DA + 2 * cells, *DC = DB + cells;
+    double2 *DA = (double2 *)e.derived, *DB = DA + 2 * cells;
+    double *cumAcc = (double *)(DB + cells), *cumOc = cumAcc + cells;
     // member-independent pre-pass: part of the season, recomputed on every call
     DeriveArgs d;
     d.ny = c.ny; d.nx = c.nx; d.steps = steps;
     d.P = ctx->P; d.C = ctx->C; d.UV = ctx->UV;
-    d.DA = DA; d.DB = DB; d.DC = DC;
+    d.DA = DA; d.DB = DB; d.cumAcc = cumAcc; d.cumOc = cumOc;
     d.k = ctx->k; d.g = ctx->g; d.rho_new = ctx->rho_fresh_div;
     dim3 blk(32, 8), grid((c.nx + 31) / 32, (c.ny + 7) / 8, steps);
     derive_pointwise_kernel<<<grid, blk, 0, st>>>(d);
-    derive_scan_kernel<<<(unsigned)((plane + 63) / 64), 64, 0, st>>>(DB, DC, plane, steps);
+    derive_scan_kernel<<<(unsigned)((plane + 63) / 64), 64, 0, st>>>(DB, cumAcc, cumOc, plane, steps);
     ctx->launches += 2;
     CU(cudaGetLastError());
 
     int nv_;
     const EnsVariant *v = &ens_variants(&nv_)[e.variant];
     const int cl = e.tables.cluster;
-    void (*kernel)(const EnsArgs) = v->kernel;
+    const bool dbg_timing = getenv("NESOSIM_ENS_TIMING") != nullptr;   // debug aid: per-phase cycle totals to stderr
+    void (*kernel)(const EnsArgs) = dbg_timing ? v->kernel_timing : v->kernel;
     CU(cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem_bytes));
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cfg.blockDim = dim3(v->nt + 32);
+    cfg.blockDim = dim3(v->ntc + 32);
     cfg.dynamicSmemBytes = e.smem_bytes;
     cfg.stream = st;
     int max_clusters = e.max_clusters;
@@ -552,7 +555,7 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
 
     EnsArgs a;
     a.ny = c.ny; a.nx = c.nx; a.T = c.num_days; a.M = mcount;
-    a.DA = DA; a.DB = DB; a.DC = DC;
+    a.DA = DA; a.DB = DB; a.cumAcc = cumAcc; a.cumOc = cumOc;
     a.W = ctx->W;
     a.ic = (ic_dev && ic_per_member) ? ic_dev + (long long)m0 * plane : ic_dev;
     a.ic_stride = ic_per_member ? plane : 0;
@@ -568,26 +571,26 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     a.sw = Switches{c.dynamicsInc == 1, c.leadlossInc == 1, c.windpackInc == 1, c.atmlossInc == 1, 0};
     a.st = e.tables;
     a.timing = nullptr;
-    const bool dbg_timing = getenv("NESOSIM_ENS_TIMING") != nullptr;   // debug aid: per-phase cycle totals to stderr
     if (dbg_timing) {
-        CU(cudaMalloc(&a.timing, sizeof(long long) * 8 * ncl * cl));
-        CU(cudaMemset(a.timing, 0, sizeof(long long) * 8 * ncl * cl));
+        CU(cudaMalloc(&a.timing, sizeof(long long) * ENS_NTIMER * ncl * cl));
+        CU(cudaMemset(a.timing, 0, sizeof(long long) * ENS_NTIMER * ncl * cl));
     }
     cfg.gridDim = dim3(ncl * cl);
     CU(cudaLaunchKernelEx(&cfg, kernel, a));
     ctx->launches++;
     CU(cudaGetLastError());
     if (dbg_timing) {
-        std::vector<long long> h(8 * ncl * cl);
+        std::vector<long long> h(ENS_NTIMER * ncl * cl);
         CU(cudaMemcpy(h.data(), a.timing, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(a.timing);
-        static const char *names[8] = {"phaseA", "bulk_drain", "cta_sync", "phaseB", "arrive_sync", "issue_copy", "cluster_wait", "-"};
+        static const char *names[12] = {"A", "barA", "Bcompute", "clwait1", "drain", "publish", "barStore", "clwait2",
+                                        "dma:drain", "dma:arrive", "dma:wait_compute", "dma:issue"};
         const double days = (double)(c.num_days - 1) * ((mcount + ncl - 1) / ncl);
         for (int kk = 0; kk < cl; ++kk) {
             fprintf(stderr, "[ens timing] %s cluster=%d x %d smem=%zu strip %d rows %d ocean %d land %d raw %d | cycles/day:", v->name, cl,
                     ncl, e.smem_bytes, kk, e.tables.row0[kk + 1] - e.tables.row0[kk], e.tables.ocean_n[kk], e.tables.land_n[kk],
                     e.tables.raw_n[kk]);
-            for (int q = 0; q < 7; ++q) fprintf(stderr, " %s=%.0f", names[q], h[kk * 8 + q] / days);
+            for (int q = 0; q < 12; ++q) fprintf(stderr, " %s=%.0f", names[q], h[kk * ENS_NTIMER + q] / days);
             fprintf(stderr, "\n");
         }
     }

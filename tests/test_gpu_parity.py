@@ -139,12 +139,11 @@ def test_25km_short_season(cuda):
     compare_all(got, refs)
 
 
-@pytest.mark.parametrize("cluster", ["4", "5", "6", "8"])
-@pytest.mark.parametrize("variant", ["t480k1", "t352k2", "t224k3", "t224k4"])
-def test_ensemble_kernel_variants_many_members_per_cluster(cuda, variant, cluster, monkeypatch):
-    """Every build variant of the season-resident kernel; 3 clusters share 11 members with per-member ICs."""
+@pytest.mark.parametrize("cluster", ["4", "5", "6", "7", "8"])
+def test_ensemble_kernel_cluster_sizes_many_members_per_cluster(cuda, cluster, monkeypatch):
+    """Every cluster size of the season-resident kernel; 3 clusters share 11 members with per-member ICs."""
     from nesosim_b200.engine import SnowBudgetEngine
-    monkeypatch.setenv("NESOSIM_ENS_VARIANT", variant)
+    variant = "cluster" + cluster
     monkeypatch.setenv("NESOSIM_ENS_CLUSTERS", "3")
     monkeypatch.setenv("NESOSIM_ENS_CLUSTER", cluster)
     # the full 100 km grid needs >= 5 CTAs per member (shared memory); a 48x90 cut of it also fits 4
@@ -160,6 +159,27 @@ def test_ensemble_kernel_variants_many_members_per_cluster(cuda, variant, cluste
     out = {k: v.cpu().numpy() for k, v in eng.run_season(params, ic).items()}
     for m in range(M):
         ref = O.run_season(forcing, ic[m], mask, 100000, oracle_params(params[m]), O.Flags(atmlossInc=1))
+        for name in out:
+            assert_parity(out[name][m], ref[name], "%s[%d] %s" % (name, m, variant))
+
+
+@pytest.mark.parametrize("variant", ["t608r2o1", "t480r2o2", "t352r3o2", "t736r2o1", "t224r4o3", "t352r6o5"])
+def test_ensemble_kernel_build_variants(cuda, variant, monkeypatch):
+    """Every build variant (threads x owned cells per thread) of the season-resident kernel on the 100 km grid."""
+    from nesosim_b200.engine import SnowBudgetEngine
+    monkeypatch.setenv("NESOSIM_ENS_VARIANT", variant)
+    monkeypatch.setenv("NESOSIM_ENS_CLUSTERS", "2")
+    mask = S.region_mask(dx=100000)
+    T, M = 8, 5
+    forcing = S.make_season(mask, T, seed=29)
+    ic = S.make_ic(mask, seed=29)
+    params = S.ensemble_params(M, seed=29)
+    eng = SnowBudgetEngine(mask, T, 100000, n_members=M, atmlossInc=1)
+    eng.set_path("ensemble")
+    eng.set_forcing(forcing["precip"], forcing["conc"], forcing["wind"], forcing["drift"])
+    out = {k: v.cpu().numpy() for k, v in eng.run_season(params, ic).items()}
+    for m in range(M):
+        ref = O.run_season(forcing, ic, mask, 100000, oracle_params(params[m]), O.Flags(atmlossInc=1))
         for name in out:
             assert_parity(out[name][m], ref[name], "%s[%d] %s" % (name, m, variant))
 
