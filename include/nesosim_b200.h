@@ -94,7 +94,10 @@ int nesosim_set_forcing(nesosim_ctx *ctx, const double *precip_dev, const double
  * x = first_step .. first_step+num_steps-1 of `for x in range(numDays-1): calcBudget(...)`
  * (NESOSIM.py:614-639) for every member.  Slot 0 of every non-NULL output is (re)written when
  * first_step == 0 (zeros; IC halves for snowDepths) so callers need not zero-fill.  num_steps < 0 means
- * "to the end" (T-1-first_step).  Asynchronous on `stream`. */
+ * "to the end" (T-1-first_step).  Asynchronous on `stream`, except that the season-resident path (see
+ * nesosim_set_path) synchronises the stream once at the end to read its operand-range flag: that kernel only
+ * carries the proven-exact fast divisions, and a season in which some operand left their range (denormal or
+ * > 2^624 magnitudes; never on physical data) is transparently redone by the general per-day kernels. */
 int nesosim_run_season(nesosim_ctx *ctx, const nesosim_member_params *params_host, const double *ic_dev,
                        int ic_per_member, const nesosim_outputs *out, int first_step, int num_steps,
                        void *stream);
@@ -149,6 +152,9 @@ int nesosim_last_path(const nesosim_ctx *ctx);
  * replica of the device routine (same branches, std::fma) so CPU tests can compare it with x / c. */
 int    nesosim_const_div_is_fast(double c);
 double nesosim_const_div_eval_host(double x, double c);
+
+/* Seasons the season-resident path had to hand back to the general kernels (see nesosim_run_season). */
+int64_t nesosim_rerun_count(const nesosim_ctx *ctx);
 
 /* Number of kernel launches this context has issued since creation (bench.py reports it). */
 int64_t nesosim_launch_count(const nesosim_ctx *ctx);

@@ -69,6 +69,7 @@ _SIGNATURES = {
     "nesosim_op_density": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double,
                                      C.c_void_p, C.c_void_p]),
     "nesosim_launch_count": (C.c_int64, [C.c_void_p]),
+    "nesosim_rerun_count": (C.c_int64, [C.c_void_p]),
     "nesosim_set_path": (C.c_int, [C.c_void_p, C.c_int]),
     "nesosim_last_path": (C.c_int, [C.c_void_p]),
     "nesosim_const_div_is_fast": (C.c_int, [C.c_double]),

@@ -23,8 +23,9 @@
 // snowfall -> accumulation/ocean flux and their running sums) and then shared by every member through L2.
 //
 // Arithmetic is the per-cell code of cell_math.cuh, shared with the general path: results are value-identical.
-// The hot loops use the branch-free flagged divisions; a thread whose flag rises (never, on physical data)
-// recomputes its own cells with the exact branching forms before anything is published.
+// The loops use only the branch-free flagged divisions (cell_math.cuh); if any lane ever leaves their proven
+// operand range (never, on physical data) the kernel raises EnsArgs::status and the host discards the season and
+// reruns it with the general per-day kernels, which carry the full IEEE division paths.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -109,6 +110,7 @@ constexpr int ENS_MAX_NX = 96;
 constexpr int ENS_NPLANE = 10;         // staged output planes: h0, h1, density, adv, div, lead, atm, wpl, wpg, wp
 constexpr int ENS_MIN_ROWS = 4;        // a strip's top two and bottom two rows must be distinct rows
 constexpr int ENS_NTIMER = 16;
+constexpr int PF_DAYS = 3;               // forcing is pulled into L2 this many days ahead of its use
 
 // plane index -> output variable
 __device__ __constant__ const int ENS_PLANE_VAR[ENS_NPLANE] = {V_H0, V_H1, V_DENS, V_ADV, V_DIV, V_LEAD, V_ATM, V_WPL, V_WPG, V_WP};
@@ -122,7 +124,7 @@ enum { BAR_A = 1, BAR_DRAIN = 2, BAR_STORE = 3 };   // named CTA barriers (0 is 
 //   planes 2..9 [PE] each (own cells only)
 //   staging  [2][PE]    snowAcc / snowOcean rows on their way global -> shared -> global (TMA only)
 //   raw adv  [(rows+2)*SXR + 1] double2,  raw div likewise (the +1 is the slot idle list entries write to)
-//   member coefficients [10], land codes (uint16), one mbarrier
+//   member coefficients [10], land codes (uint16), three mbarriers (staging loads, halo pushes, neighbours done reading)
 struct EnsLayout {
     int PE, PEX;                       // doubles
     unsigned off_stage, off_adv, tile_bytes, off_coef, off_codes, off_mbar, total;   // bytes
@@ -141,7 +143,7 @@ __host__ __device__ inline EnsLayout ens_layout(int rows, int nx, int land_alloc
     L.off_coef = L.off_adv + 2 * L.tile_bytes;
     L.off_codes = L.off_coef + 10 * 8;
     L.off_mbar = (L.off_codes + (unsigned)land_alloc * 2u + 15u) / 16u * 16u;
-    L.total = L.off_mbar + 16;
+    L.total = L.off_mbar + 32;   // [0] staging loads, [8] halo pushes, [16] neighbours done reading
     return L;
 }
 
@@ -153,6 +155,8 @@ struct StripTables {
     int raw_off[ENS_MAX_CLUSTER], raw_int_n[ENS_MAX_CLUSTER], raw_n[ENS_MAX_CLUSTER];   // interior entries first
     int ocean_off[ENS_MAX_CLUSTER], ocean_n[ENS_MAX_CLUSTER];
     int land_off[ENS_MAX_CLUSTER], land_n[ENS_MAX_CLUSTER];
+    int hland_off[ENS_MAX_CLUSTER], hland_n[ENS_MAX_CLUSTER];   // land cells of the strip's four halo rows (ext row*128+col)
+    int halo_tx[ENS_MAX_CLUSTER];      // bytes the neighbours push into the strip's halo rows per day (16 per ocean cell)
     int rows_alloc;                    // tallest strip
     int raw_max, ocean_max, land_alloc;   // longest lists
 };
@@ -174,11 +178,14 @@ struct EnsArgs {
     double w[9];
     Switches sw;
     StripTables st;
+    int *status;                       // set to 1 if any operand left the fast divisions' proven range (host reruns)
     long long *timing;                 // debug: [gridDim.x][ENS_NTIMER] phase cycle totals (NULL = off)
 };
 
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// execution barrier only (no memory fence on the arriving side): orders "I have stopped READING" against later writers
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 // shared -> global bulk copy (TMA), tracked by the issuing thread's bulk async-group
@@ -214,6 +221,33 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
         "DONE_%=:\n"
         "}\n" ::"r"(mbar), "r"(parity) : "memory");
 }
+// arrive (count 1) on an mbarrier of ANOTHER CTA of the cluster, without any memory ordering: used only to say
+// "this CTA has stopped reading", after the reads' values have been consumed
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(unsigned rmbar) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(rmbar) : "memory");
+}
+// pull a range of global memory into L2 ahead of its use (no registers, no shared memory)
+__device__ __forceinline__ void l2_prefetch(const void *gsrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+// 8-byte store into another CTA's shared memory that also counts 8 bytes on that CTA's mbarrier: the consumer
+// sees the data once its barrier phase completes -- no fence, no cluster barrier on the producer side
+__device__ __forceinline__ void st_async(unsigned raddr, double v, unsigned rmbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(raddr),
+                 "l"(__double_as_longlong(v)), "r"(rmbar) : "memory");
+}
+// Forcing loads that must be ISSUED where they are written (a phase ahead of their use): volatile, so the
+// compiler cannot sink them below the barriers in between to shorten the registers' live ranges.
+__device__ __forceinline__ double2 ldg_early2(const void *p) {
+    double2 v;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ldg_early(const void *p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ unsigned map_to_rank(unsigned saddr, unsigned rank) {
     unsigned r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
@@ -227,9 +261,14 @@ __device__ __forceinline__ void st_cluster(unsigned addr, double v) {
 //   A    raw advection/divergence of its KR list entries              (calcDynamics, NESOSIM.py:189-222)
 //   B    for its KO ocean cells: 3x3 Gaussian of the four raw planes   (smooth_snow,  NESOSIM.py:170-187),
 //        point-wise terms, accumulators, depth update, density         (calcBudget,   NESOSIM.py:260-347)
-//        -- everything into registers, then (once the previous day's bulk stores have read the planes) into the
-//        planes and the neighbours' halo rows
+//        -- the cell's two depths and seven accumulators never leave its registers; once the previous day's bulk
+//        stores have read the planes, the new values are copied into the planes and the neighbours' halo rows
 // and for the DMA warp: drain, stage the running sums, issue the day's bulk stores.
+// Cross-CTA ordering per day, both through mbarriers in each CTA's shared memory and neither with a memory fence
+// (a fence or an acquiring wait would serialise with the forcing loads in flight): (1) "my neighbours have finished
+// reading their halo rows" -- each CTA, after its phase A, arrives (relaxed) on its neighbours' barrier; only the
+// threads that push wait on it; (2) "my neighbours' halo cells of day x+1 have landed" -- the barrier counts the
+// bytes they deliver with st.async.  Cluster-wide barriers are used once per member only.
 template <int NTC, int KR, int KO, bool TIMING>
 __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
     constexpr int SXR = ENS_SXR;
@@ -243,7 +282,7 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
     const unsigned HOWN = 2u * ROWB;                   // own cell (lr,c) of h0: HOWN + (lr*nx+c)*8
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
     unsigned short *s_land_code = reinterpret_cast<unsigned short *>(smem + L.off_codes);
-    const unsigned mbar = sbase + L.off_mbar;
+    const unsigned mbar_stage = sbase + L.off_mbar, mbar_halo = mbar_stage + 8u, mbar_done = mbar_stage + 16u;
 
     auto LD = [&](unsigned off) -> double { return *reinterpret_cast<const double *>(smem + off); };
     auto LD2 = [&](unsigned off) -> double2 { return *reinterpret_cast<const double2 *>(smem + off); };
@@ -267,7 +306,11 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
     for (unsigned i = tid; i < 2u * L.tile_bytes / 16u; i += NTH)   // zero padding of convolve(boundary='fill')
         ST2(L.off_adv + i * 16u, make_double2(0.0, 0.0));
     for (unsigned i = tid; i < 2u * (unsigned)L.PEX; i += NTH) ST(i * 8u, 0.0);   // halo rows nobody pushes to
-    if (dma_lane) mbar_init(mbar, 1);
+    if (dma_lane) {
+        mbar_init(mbar_stage, 1);
+        mbar_init(mbar_halo, 1);
+        mbar_init(mbar_done, (k > 0 ? 1u : 0u) + (k < CL - 1 ? 1u : 0u) + (CL == 1 ? 1u : 0u));
+    }
 
     // neighbour's halo cell (shared::cluster address, layer 0) that mirrors my local row lr, column c; 0 = none.
     // My top two rows are the rows below the strip above; my bottom two rows are the rows above the strip below.
@@ -279,62 +322,62 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
         if (lr >= nrow - 2 && k < CL - 1) return map_to_rank(sbase + (unsigned)((lr - (nrow - 2)) * nx + c) * 8u, (unsigned)(k + 1));
         return 0u;
     };
+    const unsigned rmbar_up = k > 0 ? map_to_rank(mbar_halo, (unsigned)(k - 1)) : 0u;
+    const unsigned rmbar_dn = k < CL - 1 ? map_to_rank(mbar_halo, (unsigned)(k + 1)) : 0u;
+    const unsigned rdone_up = k > 0 ? map_to_rank(mbar_done, (unsigned)(k - 1)) : 0u;
+    const unsigned rdone_dn = k < CL - 1 ? map_to_rank(mbar_done, (unsigned)(k + 1)) : 0u;
 
-    // ---- the raw-list entries this thread computes every day (entries tid + q*NTC): offset of the centre cell in
+    // Work split: the first sA (sB) threads take KR (KO) list entries each, sA (sB) apart, so that whole warps
+    // beyond the lists skip a phase and the warps inside it carry full entries.
+    const int sA = ((n_raw + KR - 1) / KR + 31) & ~31, sB = ((n_ocean + KO - 1) / KO + 31) & ~31;
+    const bool actA = tid < sA && a.sw.dynamics, actB = tid < sB;
+
+    // ---- the raw-list entries this thread computes every day (entries tid + q*sA): offset of the centre cell in
     // the extended h0 plane and of the entry's slot in the raw tiles.  flags: bit q = entry q valid, bit 8+j = owned
-    // cell j valid, bit 16 = some entry lies on the grid edge (one-sided differences)
+    // cell j valid, bit 16 = some entry lies on the grid edge (one-sided differences), bit 20+j = cell j's halo
+    // mirror is in the strip below (else above)
     unsigned a_c[KR], a_t[KR];
-    unsigned flags = 0;
+    unsigned flags = 0, eflags = 0;    // eflags: 4 bits per entry -- first column, last column, first row, last row
 #pragma unroll
     for (int q = 0; q < KR; ++q) {
-        const int idx = tid + q * NTC;
+        const int idx = tid + q * sA;
         a_c[q] = HOWN + 8u;                                      // idle entry: reads around cell (0,1), writes the spare slot
         a_t[q] = L.off_adv + (unsigned)((RA + 2) * SXR) * 16u;
-        if (comp && idx < n_raw) {
+        if (tid < sA && idx < n_raw) {
             const unsigned code = a.st.codes[a.st.raw_off[k] + idx];
             const int r = (int)(code >> 7), c = (int)(code & 127u);
             a_c[q] = (unsigned)((r - ra + 2) * nx + c) * 8u;
             a_t[q] = L.off_adv + (unsigned)((r - ra + 1) * SXR + c + 1) * 16u;
             flags |= 1u << q;
             if (idx >= n_raw_int) flags |= 1u << 16;
+            eflags |= ((c == 0 ? 1u : 0u) | (c == nx - 1 ? 2u : 0u) | (r == 0 ? 4u : 0u) | (r == ny - 1 ? 8u : 0u)) << (4 * q);
         }
     }
-    // ---- the ocean cells this thread owns for the whole season (entries tid + j*NTC): offset of the cell in an
+    // ---- the ocean cells this thread owns for the whole season (entries tid + j*sB): offset of the cell in an
     // own-cells plane, of its top-left 3x3 tap in the raw tiles, and its mirror in a neighbour's halo
     unsigned b_ci[KO], b_t[KO], b_rem[KO];
 #pragma unroll
     for (int j = 0; j < KO; ++j) {
-        const int idx = tid + j * NTC;
+        const int idx = tid + j * sB;
         b_t[j] = L.off_adv;
         b_ci[j] = 0;
         b_rem[j] = 0;
-        if (comp && idx < n_ocean) {
+        if (tid < sB && idx < n_ocean) {
             const unsigned code = a.st.codes[a.st.ocean_off[k] + idx];
             const int lr = (int)(code >> 7), c = (int)(code & 127u);
             b_t[j] = L.off_adv + (unsigned)(lr * SXR + c) * 16u;
             b_ci[j] = (unsigned)(lr * nx + c) * 8u;
             b_rem[j] = halo_target(lr, c);
             flags |= 1u << (8 + j);
+            if (lr >= 2) flags |= 1u << (20 + j);
         }
     }
 
     const double nan = qnan();
-    const bool all_fast = a.g.dx.fast && a.g.two_dx.fast && a.conv_div.fast;
-    // global byte offsets of this strip's forcing relative to a day's plane: cell (ra-2, 0) for the raw entries
+    unsigned badacc = 0;               // sticky: some division operand left the proven range
+    // global offsets of this strip's forcing relative to a day's plane: cell (ra-2, 0) for the raw entries
     // (a_c counts from the first halo row), cell (ra, 0) for the owned cells
     const long long go_raw = (long long)(ra - 2) * nx, go_own = (long long)ra * nx;
-
-    // write (h0,h1) of local row lr, column c: own planes + the neighbour's halo row (slow form: init, land)
-    auto put_h = [&](int lr, int c, double h0, double h1) {
-        const unsigned off = HOWN + (unsigned)(lr * nx + c) * 8u;
-        ST(off, h0);
-        ST(off + PEXB, h1);
-        const unsigned rem = halo_target(lr, c);
-        if (rem) {
-            st_cluster(rem, h0);
-            st_cluster(rem + PEXB, h1);
-        }
-    };
 
     long long tacc[TIMING ? 8 : 1] = {0};
     const bool timing = TIMING && a.timing != nullptr && (tid == 0 || dma_lane);
@@ -350,7 +393,7 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
     cluster_arrive_release();
     cluster_wait_acquire();
 
-    unsigned stage_parity = 0;
+    unsigned stage_parity = 0, halo_parity = 0, done_parity = 0;
     const bool want_cum = a.out[V_ACC] != nullptr || a.out[V_OCEAN] != nullptr;
 
     for (int m = cid; m < a.M; m += ncl) {
@@ -371,22 +414,28 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
             cluster_wait_acquire();
             if (TIMING && timing) tlast = clock64();
             for (int x = 0; x < steps; ++x) {
-                cluster_arrive_release();        // #1 (this warp never reads the halo)
                 if (dma_lane) {
+                    if (x + PF_DAYS < steps) {   // pull the forcing of day x+PF_DAYS into L2
+                        const long long gp = (long long)(x + PF_DAYS) * plane;
+                        const int r0 = ra > 0 ? ra - 1 : ra, r1 = rb < ny ? rb + 1 : rb;
+                        if (a.sw.dynamics) l2_prefetch(a.DA + (gp + (long long)r0 * nx) * 2, (unsigned)((r1 - r0) * nx) * 32u);
+                        l2_prefetch(a.DB + gp + go_own, (unsigned)ncell * 16u);
+                        l2_prefetch(a.W + gp + go_own, (unsigned)ncell * 8u);
+                        if (a.out[V_ACC]) l2_prefetch(a.cumAcc + gp + go_own, (unsigned)ncell * 8u);
+                        if (a.out[V_OCEAN]) l2_prefetch(a.cumOc + gp + go_own, (unsigned)ncell * 8u);
+                    }
                     bulk_wait_read<0>();         // day x-1: planes and staging rows have been read
                     ENS_TICK(0)                  // drain
                     if (want_cum) {
                         const unsigned bytes = (unsigned)ncell * 8u;
                         const long long go = (long long)x * plane + go_own;
-                        mbar_expect_tx(mbar, (a.out[V_ACC] ? bytes : 0u) + (a.out[V_OCEAN] ? bytes : 0u));
-                        if (a.out[V_ACC]) bulk_load(sbase + L.off_stage, a.cumAcc + go, bytes, mbar);
-                        if (a.out[V_OCEAN]) bulk_load(sbase + L.off_stage + (unsigned)L.PE * 8u, a.cumOc + go, bytes, mbar);
+                        mbar_expect_tx(mbar_stage, (a.out[V_ACC] ? bytes : 0u) + (a.out[V_OCEAN] ? bytes : 0u));
+                        if (a.out[V_ACC]) bulk_load(sbase + L.off_stage, a.cumAcc + go, bytes, mbar_stage);
+                        if (a.out[V_OCEAN]) bulk_load(sbase + L.off_stage + (unsigned)L.PE * 8u, a.cumOc + go, bytes, mbar_stage);
                     }
                 }
                 __syncwarp();
-                cluster_wait_acquire();          // #1
                 bar_arrive(BAR_DRAIN, NTH);      // compute warps may overwrite the planes
-                cluster_arrive_release();        // #2
                 ENS_TICK(1)
                 bar_sync(BAR_STORE, NTH);        // planes of day x+1 are complete (and fenced for the async proxy)
                 ENS_TICK(2)                      // waiting for the compute warps
@@ -398,7 +447,7 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
                         if (a.out[v]) bulk_store(outp(v, x + 1), sbase + L.plane_off(p) + (p < 2 ? HOWN : 0u), bytes);
                     }
                     if (want_cum) {
-                        mbar_wait(mbar, stage_parity);
+                        mbar_wait(mbar_stage, stage_parity);
                         if (a.out[V_ACC]) bulk_store(outp(V_ACC, x + 1), sbase + L.off_stage, bytes);
                         if (a.out[V_OCEAN]) bulk_store(outp(V_OCEAN, x + 1), sbase + L.off_stage + (unsigned)L.PE * 8u, bytes);
                     }
@@ -407,7 +456,6 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
                 }
                 stage_parity ^= (unsigned)want_cum;
                 __syncwarp();
-                cluster_wait_acquire();          // #2
             }
             continue;
         }
@@ -434,7 +482,14 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
                 if (a.conc0[o] < a.k.minConc) v = 0.0;
                 half = mul(v, 0.5);
             }
-            put_h(lr, c, half, half);
+            const unsigned off = HOWN + (unsigned)i * 8u;
+            ST(off, half);
+            ST(off + PEXB, half);
+            const unsigned rem = halo_target(lr, c);
+            if (rem) {
+                st_cluster(rem, half);
+                st_cluster(rem + PEXB, half);
+            }
 #pragma unroll
             for (int p = PL_DENS; p < ENS_NPLANE; ++p) ST(L.plane_off(p) + (unsigned)i * 8u, 0.0);   // accumulators start at zero
 #pragma unroll
@@ -444,6 +499,15 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
         cluster_arrive_release();
         cluster_wait_acquire();
 
+        // state of the owned cells, in registers for the whole season
+        double r_h0[KO], r_h1[KO], r_dn[KO], r_adv[KO], r_div[KO], r_lead[KO], r_atm[KO], r_wpl[KO], r_wpg[KO], r_wp[KO];
+#pragma unroll
+        for (int j = 0; j < KO; ++j) {
+            r_h0[j] = LD(HOWN + b_ci[j]);
+            r_h1[j] = LD(HOWN + PEXB + b_ci[j]);
+            r_dn[j] = r_adv[j] = r_div[j] = r_lead[j] = r_atm[j] = r_wpl[j] = r_wpg[j] = r_wp[j] = 0.0;
+        }
+
         // member-independent inputs are requested ahead of their phase: L2 latency never shows
         double2 p01[KR], p23[KR], pfb[KO];
         double pW[KO];
@@ -451,9 +515,9 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
             const char *base = reinterpret_cast<const char *>(a.DA) + ((long long)x * plane + go_raw) * 32;
 #pragma unroll
             for (int q = 0; q < KR; ++q) {
-                const double2 *p = reinterpret_cast<const double2 *>(base + (size_t)a_c[q] * 4u);
-                p01[q] = __ldg(p);
-                p23[q] = __ldg(p + 1);
+                const char *p = base + (size_t)a_c[q] * 4u;
+                p01[q] = ldg_early2(p);
+                p23[q] = ldg_early2(p + 16);
             }
         };
         auto fetch_cell_inputs = [&](int x) {
@@ -461,23 +525,24 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
             const char *bw = reinterpret_cast<const char *>(a.W) + ((long long)x * plane + go_own) * 8;
 #pragma unroll
             for (int j = 0; j < KO; ++j) {
-                pfb[j] = __ldg(reinterpret_cast<const double2 *>(bb + (size_t)b_ci[j] * 2u));
-                pW[j] = __ldg(reinterpret_cast<const double *>(bw + b_ci[j]));
+                pfb[j] = ldg_early2(bb + (size_t)b_ci[j] * 2u);
+                pW[j] = ldg_early(bw + b_ci[j]);
             }
         };
 #pragma unroll
         for (int q = 0; q < KR; ++q) p01[q] = p23[q] = make_double2(0.0, 0.0);
-        if (a.sw.dynamics) fetch_raw_inputs(0);
+#pragma unroll
+        for (int j = 0; j < KO; ++j) { pfb[j] = make_double2(0.0, 0.0); pW[j] = 0.0; }
+        if (actA) fetch_raw_inputs(0);
 
         if (TIMING && timing) tlast = clock64();
         for (int x = 0; x < steps; ++x) {
-            fetch_cell_inputs(x);   // consumed in B, in flight during A
+            if (tid == 0) mbar_expect_tx(mbar_halo, (unsigned)a.st.halo_tx[k]);   // today's pushes from the neighbours
+            if (actB) fetch_cell_inputs(x);   // consumed in B, in flight during A
 
             // ---------------- A: raw advection / divergence
-            if (a.sw.dynamics) {
-                unsigned bad = 1u;
-                if (!(flags & (1u << 16)) && all_fast) {
-                    bad = 0u;
+            if (actA) {
+                if (!(flags & (1u << 16))) {
 #pragma unroll
                     for (int q = 0; q < KR; ++q) {
                         const unsigned ac = a_c[q];
@@ -491,42 +556,44 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
                                                  zero_if_nonfinite(adv_term(p01[q].x, p01[q].y, gx1, gy1))));
                         ST2(a_t[q] + L.tile_bytes, make_double2(zero_if_nonfinite(div_term(h0, p23[q].x, p23[q].y)),
                                                                 zero_if_nonfinite(div_term(h1, p23[q].x, p23[q].y))));
-                        bad |= bq & (flags >> q);
+                        badacc |= bq & (flags >> q);
                     }
-                    bad &= 1u;
-                }
-                if (bad) {   // grid-edge entries (one-sided differences, np.gradient edge_order=1) and exact redo
+                } else {   // some entry on the grid edge: one-sided differences there (np.gradient edge_order=1)
 #pragma unroll
                     for (int q = 0; q < KR; ++q) {
-                        if (!((flags >> q) & 1u)) continue;
-                        const unsigned ac = a_c[q];
-                        const int cell = (int)(ac >> 3), lr2 = cell / nx, c = cell - lr2 * nx, r = ra - 2 + lr2;
-                        const unsigned au = r > 0 ? ac - ROWB : ac, aw = r < ny - 1 ? ac + ROWB : ac;
-                        const unsigned am = c > 0 ? ac - 8u : ac, ap = c < nx - 1 ? ac + 8u : ac;
+                        const unsigned ac = a_c[q], ef = eflags >> (4 * q);
+                        unsigned bq = 0u;
+                        const unsigned am = (ef & 1u) ? ac : ac - 8u, ap = (ef & 2u) ? ac : ac + 8u;
+                        const unsigned au = (ef & 4u) ? ac : ac - ROWB, aw = (ef & 8u) ? ac : ac + ROWB;
+                        const bool ex = (ef & 3u) != 0u, ey = (ef & 12u) != 0u;
+                        ConstDiv dxx, dyy;
+                        dxx.c = ex ? a.g.dx.c : a.g.two_dx.c; dxx.rc = ex ? a.g.dx.rc : a.g.two_dx.rc; dxx.fast = 1;
+                        dyy.c = ey ? a.g.dx.c : a.g.two_dx.c; dyy.rc = ey ? a.g.dx.rc : a.g.two_dx.rc; dyy.fast = 1;
                         const double h0 = LD(ac), h1 = LD(ac + PEXB);
-                        const double gx0 = gradient1d(LD(am), h0, LD(ap), c, nx, a.g);
-                        const double gy0 = gradient1d(LD(au), h0, LD(aw), r, ny, a.g);
-                        const double gx1 = gradient1d(LD(am + PEXB), h1, LD(ap + PEXB), c, nx, a.g);
-                        const double gy1 = gradient1d(LD(au + PEXB), h1, LD(aw + PEXB), r, ny, a.g);
+                        const double gx0 = div_const_flagged(sub(LD(ap), LD(am)), dxx, bq);
+                        const double gy0 = div_const_flagged(sub(LD(aw), LD(au)), dyy, bq);
+                        const double gx1 = div_const_flagged(sub(LD(ap + PEXB), LD(am + PEXB)), dxx, bq);
+                        const double gy1 = div_const_flagged(sub(LD(aw + PEXB), LD(au + PEXB)), dyy, bq);
                         ST2(a_t[q], make_double2(zero_if_nonfinite(adv_term(p01[q].x, p01[q].y, gx0, gy0)),
                                                  zero_if_nonfinite(adv_term(p01[q].x, p01[q].y, gx1, gy1))));
                         ST2(a_t[q] + L.tile_bytes, make_double2(zero_if_nonfinite(div_term(h0, p23[q].x, p23[q].y)),
                                                                 zero_if_nonfinite(div_term(h1, p23[q].x, p23[q].y))));
+                        badacc |= bq & (flags >> q);
                     }
                 }
             }
             ENS_TICK(0)   // A
-            cluster_arrive_release();   // #1: this CTA no longer reads its halo rows of day x
-            bar_sync(BAR_A, NTC);       // raw tiles complete
+            bar_sync(BAR_A, NTC);       // raw tiles complete; nobody in this CTA reads the halo rows of day x any more
+            if (tid == 0) {             // (1)
+                if (rdone_up) mbar_arrive_remote_relaxed(rdone_up);
+                if (rdone_dn) mbar_arrive_remote_relaxed(rdone_dn);
+            }
             ENS_TICK(1)
 
-            // ---------------- B: owned ocean cells, everything into registers
-            double r_h0[KO], r_h1[KO], r_dn[KO], r_adv[KO], r_div[KO], r_lead[KO], r_atm[KO], r_wpl[KO], r_wpg[KO], r_wp[KO];
-            auto b_compute = [&](auto exact_tag, unsigned &bad) {
-                constexpr bool EXACT = decltype(exact_tag)::value;
+            // ---------------- B: owned ocean cells, registers only
+            if (actB) {
 #pragma unroll
                 for (int j = 0; j < KO; ++j) {
-                    const unsigned ci = b_ci[j];
                     unsigned bq = 0u;
                     double2 sa = make_double2(0.0, 0.0), sd = sa;              // zeros when dynamicsInc == 0 (NESOSIM.py:287-288)
                     if (a.sw.dynamics) {
@@ -546,17 +613,12 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
                                 d0 = add(d0, mul(vd.x, wgt));
                                 d1 = add(d1, mul(vd.y, wgt));
                             }
-                        if constexpr (EXACT) {
-                            sa = make_double2(mask_nan(div_const(a0, a.conv_div), false, false), mask_nan(div_const(a1, a.conv_div), false, false));
-                            sd = make_double2(mask_nan(div_const(d0, a.conv_div), false, false), mask_nan(div_const(d1, a.conv_div), false, false));
-                        } else {
-                            sa = make_double2(mask_nan(div_const_flagged(a0, a.conv_div, bq), false, false),
-                                              mask_nan(div_const_flagged(a1, a.conv_div, bq), false, false));
-                            sd = make_double2(mask_nan(div_const_flagged(d0, a.conv_div, bq), false, false),
-                                              mask_nan(div_const_flagged(d1, a.conv_div, bq), false, false));
-                        }
+                        sa = make_double2(mask_nan(div_const_flagged(a0, a.conv_div, bq), false, false),
+                                          mask_nan(div_const_flagged(a1, a.conv_div, bq), false, false));
+                        sd = make_double2(mask_nan(div_const_flagged(d0, a.conv_div, bq), false, false),
+                                          mask_nan(div_const_flagged(d1, a.conv_div, bq), false, false));
                     }
-                    const double h0 = LD(HOWN + ci), h1 = LD(HOWN + PEXB + ci);
+                    const double h0 = r_h0[j], h1 = r_h1[j];
                     const double W = pW[j];
                     const double2 fb = pfb[j];
                     const unsigned wsel = (W > LD(L.off_coef + 64u)) ? 8u : 0u;   // windT (NaN > thr is False) picks the pair entry
@@ -568,63 +630,61 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
                     if (!a.sw.leadloss) lead = 0.0;
                     if (!a.sw.atmloss) atm = 0.0;
                     if (!a.sw.windpack) wpl = wpg = wpn = 0.0;
-                    r_lead[j] = add(LD(L.plane_off(PL_LEAD) + ci), lead);
-                    r_atm[j] = add(LD(L.plane_off(PL_ATM) + ci), atm);
-                    r_wpl[j] = add(LD(L.plane_off(PL_WPL) + ci), wpl);
-                    r_wpg[j] = add(LD(L.plane_off(PL_WPG) + ci), wpg);
-                    r_wp[j] = add(LD(L.plane_off(PL_WP) + ci), wpn);
+                    r_lead[j] = add(r_lead[j], lead);
+                    r_atm[j] = add(r_atm[j], atm);
+                    r_wpl[j] = add(r_wpl[j], wpl);
+                    r_wpg[j] = add(r_wpg[j], wpg);
+                    r_wp[j] = add(r_wp[j], wpn);
                     double t0 = add(add(add(add(h0, fb.x), wpl), lead), atm);   // NESOSIM.py:327 before the dynamics terms
                     double t1 = add(h1, wpg);                                  // NESOSIM.py:329
-                    r_adv[j] = add(add(LD(L.plane_off(PL_ADV) + ci), sa.x), sa.y);   // NESOSIM.py:290
-                    r_div[j] = add(add(LD(L.plane_off(PL_DIV) + ci), sd.x), sd.y);   // NESOSIM.py:291
+                    r_adv[j] = add(add(r_adv[j], sa.x), sa.y);   // NESOSIM.py:290
+                    r_div[j] = add(add(r_div[j], sd.x), sd.y);   // NESOSIM.py:291
                     t0 = add(add(t0, sa.x), sd.x);
                     t1 = add(add(t1, sa.y), sd.y);
                     r_h0[j] = mask_nan(t0, false, true);   // NESOSIM.py:332-333
                     r_h1[j] = mask_nan(t1, false, true);
-                    if constexpr (EXACT) r_dn[j] = density_variable(r_h0[j], r_h1[j], false, a.k);
-                    else r_dn[j] = density_ocean_flagged(r_h0[j], r_h1[j], a.k, bq);
-                    bad |= bq & (flags >> (8 + j));
+                    r_dn[j] = density_ocean_flagged(r_h0[j], r_h1[j], a.k, bq);
+                    badacc |= bq & (flags >> (8 + j));
                 }
-            };
-            {
-                unsigned bad = 1u;
-                if (all_fast) {
-                    bad = 0u;
-                    b_compute(std::false_type{}, bad);
-                    bad &= 1u;
-                }
-                if (bad) b_compute(std::true_type{}, bad);
             }
-            if (a.sw.dynamics && x + 1 < steps) fetch_raw_inputs(x + 1);   // consumed in the next A
+            if (actA && x + 1 < steps) fetch_raw_inputs(x + 1);   // consumed in the next A
             ENS_TICK(2)   // B compute
-            cluster_wait_acquire();         // #1: every CTA of the cluster has finished reading its halo rows
             ENS_TICK(3)
             bar_sync(BAR_DRAIN, NTH);       // the bulk stores of day x have finished READING the planes
             ENS_TICK(4)   // drain
 
             // ---------------- publish: planes of day x+1 and the neighbours' halo rows
+            bool waited_done = false;
+            if (actB) {
 #pragma unroll
-            for (int j = 0; j < KO; ++j) {
-                if (!((flags >> (8 + j)) & 1u)) continue;
-                const unsigned ci = b_ci[j];
-                ST(HOWN + ci, r_h0[j]);
-                ST(HOWN + PEXB + ci, r_h1[j]);
-                ST(L.plane_off(PL_DENS) + ci, r_dn[j]);
-                ST(L.plane_off(PL_ADV) + ci, r_adv[j]);
-                ST(L.plane_off(PL_DIV) + ci, r_div[j]);
-                ST(L.plane_off(PL_LEAD) + ci, r_lead[j]);
-                ST(L.plane_off(PL_ATM) + ci, r_atm[j]);
-                ST(L.plane_off(PL_WPL) + ci, r_wpl[j]);
-                ST(L.plane_off(PL_WPG) + ci, r_wpg[j]);
-                ST(L.plane_off(PL_WP) + ci, r_wp[j]);
-                if (b_rem[j]) {
-                    st_cluster(b_rem[j], r_h0[j]);
-                    st_cluster(b_rem[j] + PEXB, r_h1[j]);
+                for (int j = 0; j < KO; ++j) {
+                    if (!((flags >> (8 + j)) & 1u)) continue;
+                    const unsigned ci = b_ci[j];
+                    ST(HOWN + ci, r_h0[j]);
+                    ST(HOWN + PEXB + ci, r_h1[j]);
+                    ST(L.plane_off(PL_DENS) + ci, r_dn[j]);
+                    ST(L.plane_off(PL_ADV) + ci, r_adv[j]);
+                    ST(L.plane_off(PL_DIV) + ci, r_div[j]);
+                    ST(L.plane_off(PL_LEAD) + ci, r_lead[j]);
+                    ST(L.plane_off(PL_ATM) + ci, r_atm[j]);
+                    ST(L.plane_off(PL_WPL) + ci, r_wpl[j]);
+                    ST(L.plane_off(PL_WPG) + ci, r_wpg[j]);
+                    ST(L.plane_off(PL_WP) + ci, r_wp[j]);
+                    if (b_rem[j]) {
+                        if (!waited_done) {   // (1): my neighbours have finished reading their halo rows of day x
+                            mbar_wait(mbar_done, done_parity);
+                            waited_done = true;
+                        }
+                        const unsigned rmb = ((flags >> (20 + j)) & 1u) ? rmbar_dn : rmbar_up;
+                        st_async(b_rem[j], r_h0[j], rmb);
+                        st_async(b_rem[j] + PEXB, r_h1[j], rmb);
+                    }
                 }
             }
             // land cells.  Step 0 sees the initial depths; afterwards h is NaN, so every switched-on term is NaN
             // and every switched-off term adds 0 (NESOSIM.py:287-322): closed form, written on the first two days
-            // and then left alone in the planes.
+            // and then left alone in the planes.  The land cells of my halo rows turn NaN the same way; nobody
+            // pushes them, so I write them myself.
             if (x <= 1) {
                 const MemberCoef mc = a.coef[m];
                 // closed-form land values from slot 2 on (slot 1 is computed from the initial depths)
@@ -648,7 +708,8 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
                         vWpg = add(0.0, wpg);
                         vWp = add(0.0, wpn);
                     }
-                    put_h(lr, c, nan, nan);
+                    ST(HOWN + ci, nan);
+                    ST(HOWN + PEXB + ci, nan);
                     ST(L.plane_off(PL_DENS) + ci, nan);
                     ST(L.plane_off(PL_ADV) + ci, landAdv);
                     ST(L.plane_off(PL_DIV) + ci, landAdv);
@@ -658,17 +719,28 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
                     ST(L.plane_off(PL_WPG) + ci, vWpg);
                     ST(L.plane_off(PL_WP) + ci, vWp);
                 }
+                for (int i = tid; i < a.st.hland_n[k]; i += NTC) {
+                    const int code = a.st.codes[a.st.hland_off[k] + i];
+                    const unsigned off = (unsigned)((code >> 7) * nx + (code & 127)) * 8u;
+                    ST(off, nan);
+                    ST(off + PEXB, nan);
+                }
             }
             fence_async_smem();
-            cluster_arrive_release();       // #2: my halo pushes of day x+1 are done
             ENS_TICK(5)   // publish
             bar_sync(BAR_STORE, NTH);       // planes complete: the DMA warp issues the bulk stores
             ENS_TICK(6)
-            cluster_wait_acquire();         // #2: the neighbours' pushes have landed in my halo rows
+            mbar_wait(mbar_halo, halo_parity);   // (2): the neighbours' pushes have landed in my halo rows
+            halo_parity ^= 1u;
+            done_parity ^= 1u;
             ENS_TICK(7)
         }
     }
     if (dma_lane) bulk_wait_all();
+    if (badacc & 1u) atomicOr(a.status, 1);
+    // nobody leaves while a neighbour may still be pushing into its shared memory or waiting for its arrival
+    cluster_arrive_release();
+    cluster_wait_acquire();
 #undef ENS_TICK
     if (TIMING && timing)
         for (int q = 0; q < (TIMING ? 8 : 1); ++q) a.timing[(long long)blockIdx.x * ENS_NTIMER + (dma_lane ? 8 : 0) + q] = tacc[q];

@@ -156,6 +156,8 @@ struct nesosim_ctx {
     GradConsts g;
     ConstDiv conv_div, rho_fresh_div;
     EnsembleState ens;              // season-resident ensemble path (ensemble_kernel.cuh)
+    int ens_status = 0;             // flag read back from the last season-resident launch (1 = rerun needed)
+    long long ens_reruns = 0;
     int path = 0;                   // 0 auto, 1 general per-day launches, 2 season-resident ensemble kernel
     int last_path = 0;              // which path the last run_season used (1 or 2)
 };
@@ -311,7 +313,7 @@ struct EnsVariant {
     {"t" #ntc "r" #kr "o" #ko, ntc, kr, ko, ensemble_season_kernel<ntc, kr, ko, false>, ensemble_season_kernel<ntc, kr, ko, true>}
 const EnsVariant *ens_variants(int *n) {
     static const EnsVariant v[] = {
-        ENS_V(608, 2, 1), ENS_V(480, 2, 2), ENS_V(352, 3, 2), ENS_V(736, 2, 1), ENS_V(224, 4, 3), ENS_V(352, 6, 5),
+        ENS_V(352, 3, 2), ENS_V(224, 4, 3), ENS_V(480, 2, 2), ENS_V(608, 2, 1), ENS_V(480, 2, 1), ENS_V(736, 2, 1), ENS_V(352, 6, 5),
     };
     *n = (int)(sizeof(v) / sizeof(v[0]));
     return v;
@@ -323,8 +325,8 @@ constexpr size_t ENS_SMEM_CAP = 227 * 1024;
 // kernel walks.  A strip must satisfy the bulk-copy rules (16-byte aligned start, 16-byte multiple size), hold
 // at least ENS_MIN_ROWS rows (its top two and bottom two rows are its neighbours' halos) and fit shared memory.
 // Returns false if no such cut exists for this cluster size.
-bool try_strip_tables(nesosim_ctx *ctx, int cl, StripTables &t, std::vector<unsigned short> &codes, size_t &smem_bytes,
-                      double &day_cost) {
+bool try_strip_tables(nesosim_ctx *ctx, int cl, int cap_raw, int cap_ocean, StripTables &t,
+                      std::vector<unsigned short> &codes, size_t &smem_bytes, double &day_cost) {
     const int ny = ctx->cfg.ny, nx = ctx->cfg.nx;
     const std::vector<uint8_t> &mask = ctx->mask_host;
     auto land = [&](int r, int c) { const uint8_t m = mask[(size_t)r * nx + c]; return m > 10 || m < 1; };
@@ -353,7 +355,8 @@ bool try_strip_tables(nesosim_ctx *ctx, int cl, StripTables &t, std::vector<unsi
         if (rows < ENS_MIN_ROWS || rows > max_rows_smem) return -1.0;
         if (((long long)rows * nx) % 2 || ((long long)ra * nx) % 2) return -1.0;
         const long long ocean = coc[rb] - coc[ra];
-        const long long raw = cdil[std::min(rb + 1, ny)] - cdil[std::max(ra - 1, 0)];
+        const long long raw = cdil[std::min(rb + 1, ny)] - cdil[std::max(ra - 1, 0)];   // (upper bound of the list length)
+        if (ocean > cap_ocean || raw > cap_raw) return -1.0;
         // relative cost per day: an owned ocean cell ~3 raw entries of arithmetic; every cell is stored
         return 3.0 * ocean + 1.0 * raw + 0.5 * rows * nx;
     };
@@ -403,6 +406,21 @@ bool try_strip_tables(nesosim_ctx *ctx, int cl, StripTables &t, std::vector<unsi
         append(ri, t.raw_off[k], t.raw_n[k]);
         append(ocl, t.ocean_off[k], t.ocean_n[k]);
         append(la, t.land_off[k], t.land_n[k]);
+        // the four halo rows (two above, two below; inside the grid and owned by a neighbour strip): their land
+        // cells, as (row of the extended plane)*128 + col, and the bytes their ocean cells receive per day
+        std::vector<unsigned short> hl;
+        int halo_ocean = 0;
+        for (int hr = 0; hr < 4; ++hr) {
+            const int r = hr < 2 ? ra - 2 + hr : rb + (hr - 2);
+            if ((hr < 2 && k == 0) || (hr >= 2 && k == cl - 1)) continue;
+            const int ext_row = r - (ra - 2);
+            for (int c = 0; c < nx; ++c) {
+                if (land(r, c)) hl.push_back((unsigned short)(ext_row * 128 + c));
+                else ++halo_ocean;
+            }
+        }
+        append(hl, t.hland_off[k], t.hland_n[k]);
+        t.halo_tx[k] = halo_ocean * 16;
         max_raw = std::max(max_raw, t.raw_n[k]);
         max_rows = std::max(max_rows, rb - ra);
         max_land = std::max(max_land, (int)la.size());
@@ -454,31 +472,31 @@ int build_strip_tables(nesosim_ctx *ctx) {
     const EnsVariant *vars = ens_variants(&nv);
     std::vector<unsigned short> best_codes;
     double best_time = 1e300;
-    for (int cl = 2; cl <= ENS_MAX_CLUSTER; ++cl) {
-        if (forced && cl != forced) continue;
-        StripTables t;
-        std::vector<unsigned short> codes;
-        size_t smem = 0;
-        double day_cost = 0;
-        if (!try_strip_tables(ctx, cl, t, codes, smem, day_cost)) continue;
-        int vi = -1;
-        for (int i = 0; i < nv && vi < 0; ++i) {
-            if (forced_var && *forced_var && strcmp(forced_var, vars[i].name)) continue;
-            if (t.raw_max <= vars[i].kr * vars[i].ntc && t.ocean_max <= vars[i].ko * vars[i].ntc) vi = i;
+    for (int vi = 0; vi < nv; ++vi) {
+        if (forced_var && *forced_var && strcmp(forced_var, vars[vi].name)) continue;
+        bool found = false;
+        for (int cl = 2; cl <= ENS_MAX_CLUSTER; ++cl) {
+            if (forced && cl != forced) continue;
+            StripTables t;
+            std::vector<unsigned short> codes;
+            size_t smem = 0;
+            double day_cost = 0;
+            if (!try_strip_tables(ctx, cl, vars[vi].kr * vars[vi].ntc, vars[vi].ko * vars[vi].ntc, t, codes, smem, day_cost)) continue;
+            const int ncl = max_active_clusters(&vars[vi], cl, smem);
+            if (ncl < 1) continue;
+            const int rounds = (ctx->cfg.n_members + ncl - 1) / ncl;
+            const double time = rounds * (day_cost + 1500.0);   // heaviest strip + fixed barrier overhead per day
+            if (time < best_time) {
+                best_time = time;
+                e.tables = t;
+                e.smem_bytes = smem;
+                e.max_clusters = ncl;
+                e.variant = vi;
+                best_codes.swap(codes);
+                found = true;
+            }
         }
-        if (vi < 0) continue;
-        const int ncl = max_active_clusters(&vars[vi], cl, smem);
-        if (ncl < 1) continue;
-        const int rounds = (ctx->cfg.n_members + ncl - 1) / ncl;
-        const double time = rounds * (day_cost + 1500.0);   // heaviest strip + fixed barrier overhead per day
-        if (time < best_time) {
-            best_time = time;
-            e.tables = t;
-            e.smem_bytes = smem;
-            e.max_clusters = ncl;
-            e.variant = vi;
-            best_codes.swap(codes);
-        }
+        if (found) break;   // variants are listed in order of preference: the first one that fits wins
     }
     if (best_time >= 1e300) return fail(NESOSIM_ERR_ARG, "grid does not fit the season-resident kernel's shared-memory strips");
     CU(cudaMalloc(&e.codes_dev, best_codes.size() * sizeof(unsigned short)));
@@ -501,6 +519,7 @@ bool ensemble_eligible(nesosim_ctx *ctx, int first_step, int num_steps, const ne
     for (int v = 0; v < NVAR; ++v)
         if (out_base(out, v) && ((uintptr_t)out_base(out, v) % 16)) { *why = "output array not 16-byte aligned"; return false; }
     if ((out->depth_member_stride % 2) || (out->plane_member_stride % 2)) { *why = "odd member stride"; return false; }
+    if (!(ctx->g.dx.fast && ctx->g.two_dx.fast && ctx->conv_div.fast)) { *why = "a divisor without the exact fast-division proof"; return false; }
     if (build_strip_tables(ctx) != NESOSIM_OK) { *why = "no strip decomposition fits"; return false; }
     return true;
 }
@@ -570,6 +589,8 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     std::memcpy(a.w, c.conv_weights, sizeof(a.w));
     a.sw = Switches{c.dynamicsInc == 1, c.leadlossInc == 1, c.windpackInc == 1, c.atmlossInc == 1, 0};
     a.st = e.tables;
+    a.status = ctx->flags_dev;
+    CU(cudaMemsetAsync(ctx->flags_dev, 0, sizeof(int), st));
     a.timing = nullptr;
     if (dbg_timing) {
         CU(cudaMalloc(&a.timing, sizeof(long long) * ENS_NTIMER * ncl * cl));
@@ -579,11 +600,15 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     CU(cudaLaunchKernelEx(&cfg, kernel, a));
     ctx->launches++;
     CU(cudaGetLastError());
+    // The kernel only carries the fast divisions; if an operand left their proven range the season is redone by
+    // the general kernels (run_members looks at ens_status).  Reading the flag needs the stream to finish.
+    CU(cudaMemcpyAsync(&ctx->ens_status, ctx->flags_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     if (dbg_timing) {
         std::vector<long long> h(ENS_NTIMER * ncl * cl);
         CU(cudaMemcpy(h.data(), a.timing, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(a.timing);
-        static const char *names[12] = {"A", "barA", "Bcompute", "clwait1", "drain", "publish", "barStore", "clwait2",
+        static const char *names[12] = {"A", "barA", "Bcompute", "clwait1", "drain", "publish", "barStore", "halowait",
                                         "dma:drain", "dma:arrive", "dma:wait_compute", "dma:issue"};
         const double days = (double)(c.num_days - 1) * ((mcount + ncl - 1) / ncl);
         for (int kk = 0; kk < cl; ++kk) {
@@ -610,7 +635,9 @@ int run_members(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, const
         return fail(NESOSIM_ERR_ARG, std::string("season-resident ensemble path not applicable: ") + why);
     if (ctx->path != 1 && can_ens) {
         ctx->last_path = 2;
-        return run_ensemble(ctx, ic_dev, ic_per_member, out, m0, mcount, st);
+        rc = run_ensemble(ctx, ic_dev, ic_per_member, out, m0, mcount, st);
+        if (rc || !ctx->ens_status) return rc;
+        ctx->ens_reruns++;          // fall through: redo these members with the general kernels
     }
     ctx->last_path = 1;
     if (any_missing(out) && (rc = ensure_scratch(ctx))) return rc;
@@ -817,6 +844,7 @@ int nesosim_op_density(const double *depths_dev, const uint8_t *mask_dev, int64_
 }
 
 int64_t nesosim_launch_count(const nesosim_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int64_t nesosim_rerun_count(const nesosim_ctx *ctx) { return ctx ? ctx->ens_reruns : 0; }
 
 int nesosim_set_path(nesosim_ctx *ctx, int path) {
     if (!ctx || path < 0 || path > 2) return fail(NESOSIM_ERR_ARG, "path must be 0 (auto), 1 (per-day kernel) or 2 (season-resident)");

@@ -177,6 +177,10 @@ class SnowBudgetEngine:
     def launch_count(self):
         return int(self.lib.nesosim_launch_count(self.handle))
 
+    def rerun_count(self):
+        """Seasons the season-resident kernel handed back to the general kernels (operand-range flag)."""
+        return int(self.lib.nesosim_rerun_count(self.handle))
+
     PATHS = {"auto": 0, "general": 1, "ensemble": 2}
 
     def set_path(self, path):
