@@ -23,9 +23,11 @@
 // snowfall -> accumulation/ocean flux and their running sums) and then shared by every member through L2.
 //
 // Arithmetic is the per-cell code of cell_math.cuh, shared with the general path: results are value-identical.
-// The loops use only the branch-free flagged divisions (cell_math.cuh); if any lane ever leaves their proven
-// operand range (never, on physical data) the kernel raises EnsArgs::status and the host discards the season and
-// reruns it with the general per-day kernels, which carry the full IEEE division paths.
+// The loops use only the bare three-operation constant divisions (cell_math.cuh div_const_bare): their operand
+// range is guaranteed by guarding the INPUTS -- every depth the kernel publishes and every drift term of the
+// pre-pass must be zero, NaN or within [2^-150, 2^150] (out_of_guard).  If anything ever leaves that guard (never,
+// on physical data) EnsArgs::status is raised and the host discards the season and reruns it with the general
+// per-day kernels, which carry the full IEEE division paths.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -52,6 +54,7 @@ struct DeriveArgs {
     ModelConsts k;
     GradConsts g;
     ConstDiv rho_new;
+    int *status;                       // raised when a drift term leaves the season kernel's operand guard
 };
 
 __global__ void derive_pointwise_kernel(const __grid_constant__ DeriveArgs a) {
@@ -66,9 +69,11 @@ __global__ void derive_pointwise_kernel(const __grid_constant__ DeriveArgs a) {
     auto vt = [&](int r, int c) { return mul(V[(long long)r * a.nx + c], a.k.deltaT); };
     const double utc = ut(gy, gx), vtc = vt(gy, gx);
     double2 *da = a.DA + ((long long)x * plane + o) * 2;
+    const double gxu = gradient1d(ut(gy, xm), utc, ut(gy, xp), gx, a.nx, a.g);
+    const double gyv = gradient1d(vt(ym, gx), vtc, vt(yp, gx), gy, a.ny, a.g);
     da[0] = make_double2(utc, vtc);
-    da[1] = make_double2(gradient1d(ut(gy, xm), utc, ut(gy, xp), gx, a.nx, a.g),
-                         gradient1d(vt(ym, gx), vtc, vt(yp, gx), gy, a.ny, a.g));
+    da[1] = make_double2(gxu, gyv);
+    if (out_of_guard(utc) | out_of_guard(vtc) | out_of_guard(gxu) | out_of_guard(gyv)) atomicOr(a.status, 1);
     const double C = a.C[(long long)x * plane + o];
     const double pd = div_const(a.P[(long long)x * plane + o], a.rho_new);
     const double omc = sub(1.0, C);
@@ -109,7 +114,7 @@ constexpr int ENS_SXR = 98;            // raw tile row stride (double2); column 
 constexpr int ENS_MAX_NX = 96;
 constexpr int ENS_NPLANE = 10;         // staged output planes: h0, h1, density, adv, div, lead, atm, wpl, wpg, wp
 constexpr int ENS_MIN_ROWS = 4;        // a strip's top two and bottom two rows must be distinct rows
-constexpr int ENS_NTIMER = 16;
+constexpr int ENS_NTIMER = 64;           // [0..7] thread 0 phases, [8..15] DMA lane, [16..39] per-warp A, [40..63] per-warp B
 constexpr int PF_DAYS = 3;               // forcing is pulled into L2 this many days ahead of its use
 
 // plane index -> output variable
@@ -178,6 +183,7 @@ struct EnsArgs {
     double w[9];
     Switches sw;
     StripTables st;
+    int dbg;                           // timing experiments only (NESOSIM_ENS_DBG): 1 forcing always from day 0, 2 no L2 prefetch, 4 no bulk stores
     int *status;                       // set to 1 if any operand left the fast divisions' proven range (host reruns)
     long long *timing;                 // debug: [gridDim.x][ENS_NTIMER] phase cycle totals (NULL = off)
 };
@@ -327,42 +333,48 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
     const unsigned rdone_up = k > 0 ? map_to_rank(mbar_done, (unsigned)(k - 1)) : 0u;
     const unsigned rdone_dn = k < CL - 1 ? map_to_rank(mbar_done, (unsigned)(k + 1)) : 0u;
 
-    // Work split: the first sA (sB) threads take KR (KO) list entries each, sA (sB) apart, so that whole warps
-    // beyond the lists skip a phase and the warps inside it carry full entries.
-    const int sA = ((n_raw + KR - 1) / KR + 31) & ~31, sB = ((n_ocean + KO - 1) / KO + 31) & ~31;
-    const bool actA = tid < sA && a.sw.dynamics, actB = tid < sB;
+    // Work split: list entry i belongs to thread i % NTC, so every warp carries floor or ceil of the average and
+    // the four schedulers of the SM see the same load.  nqA / nqB = entries of this WARP (warp-uniform: the phase
+    // bodies are instantiated per count, so a warp never executes an entry none of its lanes owns).
+    const int wbase = tid & ~31;
+    // Raw-list entries on the grid edge (the last n_raw - n_raw_int of the list; one-sided differences, and often a
+    // whole column, i.e. bank-conflicting) are dealt one per thread from the LAST thread downwards, in a slot of
+    // their own, so they fall on the warps with the fewest interior entries and only that slot runs the edge code.
+    const int n_edge = n_raw - n_raw_int;
+    const int nqA = a.sw.dynamics ? min(KR, max(0, (n_raw_int - wbase + NTC - 1) / NTC)) : 0;
+    const bool hasE = a.sw.dynamics && (NTC - 1 - (wbase + 31)) < n_edge;   // some lane of this warp holds an edge entry
+    const int nqB = min(KO, max(0, (n_ocean - wbase + NTC - 1) / NTC));
 
-    // ---- the raw-list entries this thread computes every day (entries tid + q*sA): offset of the centre cell in
-    // the extended h0 plane and of the entry's slot in the raw tiles.  flags: bit q = entry q valid, bit 8+j = owned
-    // cell j valid, bit 16 = some entry lies on the grid edge (one-sided differences), bit 20+j = cell j's halo
-    // mirror is in the strip below (else above)
-    unsigned a_c[KR], a_t[KR];
-    unsigned flags = 0, eflags = 0;    // eflags: 4 bits per entry -- first column, last column, first row, last row
+    // ---- the raw-list entries this thread computes every day (interior entries tid + q*NTC in slots 0..KR-1, at most
+    // one edge entry in slot KR): offset of the centre cell in the extended h0 plane and of the entry's slot in the raw
+    // tiles.  flags: bit 8+j = owned cell j valid, bit 20+j = cell j's halo mirror is in the strip below (else above).
+    // eflags (edge slot): first column, last column, first row, last row.
+    unsigned a_c[KR + 1], a_t[KR + 1];
+    unsigned flags = 0, eflags = 0;
 #pragma unroll
-    for (int q = 0; q < KR; ++q) {
-        const int idx = tid + q * sA;
+    for (int q = 0; q <= KR; ++q) {
+        const int idx = (q < KR) ? tid + q * NTC : n_raw_int + (NTC - 1 - tid);
+        const bool valid = comp && ((q < KR) ? idx < n_raw_int : idx < n_raw);
         a_c[q] = HOWN + 8u;                                      // idle entry: reads around cell (0,1), writes the spare slot
         a_t[q] = L.off_adv + (unsigned)((RA + 2) * SXR) * 16u;
-        if (tid < sA && idx < n_raw) {
+        if (valid) {
             const unsigned code = a.st.codes[a.st.raw_off[k] + idx];
             const int r = (int)(code >> 7), c = (int)(code & 127u);
             a_c[q] = (unsigned)((r - ra + 2) * nx + c) * 8u;
             a_t[q] = L.off_adv + (unsigned)((r - ra + 1) * SXR + c + 1) * 16u;
-            flags |= 1u << q;
-            if (idx >= n_raw_int) flags |= 1u << 16;
-            eflags |= ((c == 0 ? 1u : 0u) | (c == nx - 1 ? 2u : 0u) | (r == 0 ? 4u : 0u) | (r == ny - 1 ? 8u : 0u)) << (4 * q);
+            if (q == KR) eflags = (c == 0 ? 1u : 0u) | (c == nx - 1 ? 2u : 0u) | (r == 0 ? 4u : 0u) | (r == ny - 1 ? 8u : 0u);
         }
     }
-    // ---- the ocean cells this thread owns for the whole season (entries tid + j*sB): offset of the cell in an
+    // ---- the ocean cells this thread owns for the whole season (entries tid + j*NTC): offset of the cell in an
     // own-cells plane, of its top-left 3x3 tap in the raw tiles, and its mirror in a neighbour's halo
     unsigned b_ci[KO], b_t[KO], b_rem[KO];
 #pragma unroll
     for (int j = 0; j < KO; ++j) {
-        const int idx = tid + j * sB;
+        const int idx = tid + j * NTC;
         b_t[j] = L.off_adv;
         b_ci[j] = 0;
         b_rem[j] = 0;
-        if (tid < sB && idx < n_ocean) {
+        if (comp && idx < n_ocean) {
             const unsigned code = a.st.codes[a.st.ocean_off[k] + idx];
             const int lr = (int)(code >> 7), c = (int)(code & 127u);
             b_t[j] = L.off_adv + (unsigned)(lr * SXR + c) * 16u;
@@ -380,6 +392,8 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
     const long long go_raw = (long long)(ra - 2) * nx, go_own = (long long)ra * nx;
 
     long long tacc[TIMING ? 8 : 1] = {0};
+    long long twA = 0, twB = 0, tw0 = 0;   // per-warp durations of the two compute phases (lane 0 of each warp)
+    const bool wtiming = TIMING && a.timing != nullptr && comp && (tid & 31) == 0 && (tid >> 5) < 24;
     const bool timing = TIMING && a.timing != nullptr && (tid == 0 || dma_lane);
     long long tlast = 0;
 #define ENS_TICK(slot)                                   \
@@ -415,7 +429,7 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
             if (TIMING && timing) tlast = clock64();
             for (int x = 0; x < steps; ++x) {
                 if (dma_lane) {
-                    if (x + PF_DAYS < steps) {   // pull the forcing of day x+PF_DAYS into L2
+                    if (x + PF_DAYS < steps && !(a.dbg & 2)) {   // pull the forcing of day x+PF_DAYS into L2
                         const long long gp = (long long)(x + PF_DAYS) * plane;
                         const int r0 = ra > 0 ? ra - 1 : ra, r1 = rb < ny ? rb + 1 : rb;
                         if (a.sw.dynamics) l2_prefetch(a.DA + (gp + (long long)r0 * nx) * 2, (unsigned)((r1 - r0) * nx) * 32u);
@@ -444,7 +458,7 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
 #pragma unroll
                     for (int p = 0; p < ENS_NPLANE; ++p) {
                         const int v = ENS_PLANE_VAR[p];
-                        if (a.out[v]) bulk_store(outp(v, x + 1), sbase + L.plane_off(p) + (p < 2 ? HOWN : 0u), bytes);
+                        if (a.out[v] && !(a.dbg & 4)) bulk_store(outp(v, x + 1), sbase + L.plane_off(p) + (p < 2 ? HOWN : 0u), bytes);
                     }
                     if (want_cum) {
                         mbar_wait(mbar_stage, stage_parity);
@@ -482,6 +496,7 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
                 if (a.conc0[o] < a.k.minConc) v = 0.0;
                 half = mul(v, 0.5);
             }
+            badacc |= out_of_guard(half);
             const unsigned off = HOWN + (unsigned)i * 8u;
             ST(off, half);
             ST(off + PEXB, half);
@@ -509,79 +524,97 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
         }
 
         // member-independent inputs are requested ahead of their phase: L2 latency never shows
-        double2 p01[KR], p23[KR], pfb[KO];
+        double2 p01[KR + 1], p23[KR + 1], pfb[KO];
         double pW[KO];
         auto fetch_raw_inputs = [&](int x) {
+            if (a.dbg & 1) x = 0;
             const char *base = reinterpret_cast<const char *>(a.DA) + ((long long)x * plane + go_raw) * 32;
 #pragma unroll
-            for (int q = 0; q < KR; ++q) {
-                const char *p = base + (size_t)a_c[q] * 4u;
-                p01[q] = ldg_early2(p);
-                p23[q] = ldg_early2(p + 16);
+            for (int q = 0; q <= KR; ++q) {
+                if ((q < KR) ? (q < nqA) : hasE) {
+                    const char *p = base + (size_t)a_c[q] * 4u;
+                    p01[q] = ldg_early2(p);
+                    p23[q] = ldg_early2(p + 16);
+                }
             }
         };
         auto fetch_cell_inputs = [&](int x) {
+            if (a.dbg & 1) x = 0;
             const char *bb = reinterpret_cast<const char *>(a.DB) + ((long long)x * plane + go_own) * 16;
             const char *bw = reinterpret_cast<const char *>(a.W) + ((long long)x * plane + go_own) * 8;
 #pragma unroll
             for (int j = 0; j < KO; ++j) {
-                pfb[j] = ldg_early2(bb + (size_t)b_ci[j] * 2u);
-                pW[j] = ldg_early(bw + b_ci[j]);
+                if (j < nqB) {
+                    pfb[j] = ldg_early2(bb + (size_t)b_ci[j] * 2u);
+                    pW[j] = ldg_early(bw + b_ci[j]);
+                }
             }
         };
 #pragma unroll
-        for (int q = 0; q < KR; ++q) p01[q] = p23[q] = make_double2(0.0, 0.0);
+        for (int q = 0; q <= KR; ++q) p01[q] = p23[q] = make_double2(0.0, 0.0);
 #pragma unroll
         for (int j = 0; j < KO; ++j) { pfb[j] = make_double2(0.0, 0.0); pW[j] = 0.0; }
-        if (actA) fetch_raw_inputs(0);
+        if (nqA || hasE) fetch_raw_inputs(0);
 
         if (TIMING && timing) tlast = clock64();
         for (int x = 0; x < steps; ++x) {
             if (tid == 0) mbar_expect_tx(mbar_halo, (unsigned)a.st.halo_tx[k]);   // today's pushes from the neighbours
-            if (actB) fetch_cell_inputs(x);   // consumed in B, in flight during A
+            fetch_cell_inputs(x);   // consumed in B, in flight during A
+            if (TIMING && wtiming) tw0 = clock64();
 
-            // ---------------- A: raw advection / divergence
-            if (actA) {
-                if (!(flags & (1u << 16))) {
+            // ---------------- A: raw advection / divergence.  All loads and arithmetic of the warp's entries first,
+            // the tile stores last: nothing in between can alias, so the entries' dependency chains interleave.
+            auto phaseA = [&](auto nq_tag, auto edge_tag) {
+                constexpr int NQ = decltype(nq_tag)::value;
+                constexpr bool EDGE = decltype(edge_tag)::value;      // the warp also has entries in the edge slot
+                constexpr int NE = NQ + (EDGE ? 1 : 0);
+                double2 o_adv[NE], o_div[NE];
 #pragma unroll
-                    for (int q = 0; q < KR; ++q) {
-                        const unsigned ac = a_c[q];
-                        unsigned bq = 0u;
-                        const double h0 = LD(ac), h1 = LD(ac + PEXB);
-                        const double gx0 = div_const_flagged(sub(LD(ac + 8u), LD(ac - 8u)), a.g.two_dx, bq);
-                        const double gy0 = div_const_flagged(sub(LD(ac + ROWB), LD(ac - ROWB)), a.g.two_dx, bq);
-                        const double gx1 = div_const_flagged(sub(LD(ac + PEXB + 8u), LD(ac + PEXB - 8u)), a.g.two_dx, bq);
-                        const double gy1 = div_const_flagged(sub(LD(ac + PEXB + ROWB), LD(ac + PEXB - ROWB)), a.g.two_dx, bq);
-                        ST2(a_t[q], make_double2(zero_if_nonfinite(adv_term(p01[q].x, p01[q].y, gx0, gy0)),
-                                                 zero_if_nonfinite(adv_term(p01[q].x, p01[q].y, gx1, gy1))));
-                        ST2(a_t[q] + L.tile_bytes, make_double2(zero_if_nonfinite(div_term(h0, p23[q].x, p23[q].y)),
-                                                                zero_if_nonfinite(div_term(h1, p23[q].x, p23[q].y))));
-                        badacc |= bq & (flags >> q);
-                    }
-                } else {   // some entry on the grid edge: one-sided differences there (np.gradient edge_order=1)
-#pragma unroll
-                    for (int q = 0; q < KR; ++q) {
-                        const unsigned ac = a_c[q], ef = eflags >> (4 * q);
-                        unsigned bq = 0u;
+                for (int e = 0; e < NE; ++e) {
+                    const int q = (e < NQ) ? e : KR;
+                    const unsigned ac = a_c[q];
+                    const double h0 = LD(ac), h1 = LD(ac + PEXB);
+                    double gx0, gy0, gx1, gy1;
+                    if (e < NQ) {
+                        gx0 = div_const_bare(sub(LD(ac + 8u), LD(ac - 8u)), a.g.two_dx);
+                        gy0 = div_const_bare(sub(LD(ac + ROWB), LD(ac - ROWB)), a.g.two_dx);
+                        gx1 = div_const_bare(sub(LD(ac + PEXB + 8u), LD(ac + PEXB - 8u)), a.g.two_dx);
+                        gy1 = div_const_bare(sub(LD(ac + PEXB + ROWB), LD(ac + PEXB - ROWB)), a.g.two_dx);
+                    } else {   // grid edge: one-sided differences there (np.gradient edge_order=1)
+                        const unsigned ef = eflags;
                         const unsigned am = (ef & 1u) ? ac : ac - 8u, ap = (ef & 2u) ? ac : ac + 8u;
                         const unsigned au = (ef & 4u) ? ac : ac - ROWB, aw = (ef & 8u) ? ac : ac + ROWB;
                         const bool ex = (ef & 3u) != 0u, ey = (ef & 12u) != 0u;
                         ConstDiv dxx, dyy;
                         dxx.c = ex ? a.g.dx.c : a.g.two_dx.c; dxx.rc = ex ? a.g.dx.rc : a.g.two_dx.rc; dxx.fast = 1;
                         dyy.c = ey ? a.g.dx.c : a.g.two_dx.c; dyy.rc = ey ? a.g.dx.rc : a.g.two_dx.rc; dyy.fast = 1;
-                        const double h0 = LD(ac), h1 = LD(ac + PEXB);
-                        const double gx0 = div_const_flagged(sub(LD(ap), LD(am)), dxx, bq);
-                        const double gy0 = div_const_flagged(sub(LD(aw), LD(au)), dyy, bq);
-                        const double gx1 = div_const_flagged(sub(LD(ap + PEXB), LD(am + PEXB)), dxx, bq);
-                        const double gy1 = div_const_flagged(sub(LD(aw + PEXB), LD(au + PEXB)), dyy, bq);
-                        ST2(a_t[q], make_double2(zero_if_nonfinite(adv_term(p01[q].x, p01[q].y, gx0, gy0)),
-                                                 zero_if_nonfinite(adv_term(p01[q].x, p01[q].y, gx1, gy1))));
-                        ST2(a_t[q] + L.tile_bytes, make_double2(zero_if_nonfinite(div_term(h0, p23[q].x, p23[q].y)),
-                                                                zero_if_nonfinite(div_term(h1, p23[q].x, p23[q].y))));
-                        badacc |= bq & (flags >> q);
+                        gx0 = div_const_bare(sub(LD(ap), LD(am)), dxx);
+                        gy0 = div_const_bare(sub(LD(aw), LD(au)), dyy);
+                        gx1 = div_const_bare(sub(LD(ap + PEXB), LD(am + PEXB)), dxx);
+                        gy1 = div_const_bare(sub(LD(aw + PEXB), LD(au + PEXB)), dyy);
                     }
+                    o_adv[e] = make_double2(zero_if_nonfinite(adv_term(p01[q].x, p01[q].y, gx0, gy0)),
+                                            zero_if_nonfinite(adv_term(p01[q].x, p01[q].y, gx1, gy1)));
+                    o_div[e] = make_double2(zero_if_nonfinite(div_term(h0, p23[q].x, p23[q].y)),
+                                            zero_if_nonfinite(div_term(h1, p23[q].x, p23[q].y)));
                 }
-            }
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    const int q = (e < NQ) ? e : KR;
+                    ST2(a_t[q], o_adv[e]);
+                    ST2(a_t[q] + L.tile_bytes, o_div[e]);
+                }
+            };
+            auto dispatchA = [&](auto edge_tag) {
+#define ENS_A_CASE(n) \
+    if constexpr (KR >= n) { if (nqA == n) phaseA(std::integral_constant<int, n>{}, edge_tag); }
+                ENS_A_CASE(1) ENS_A_CASE(2) ENS_A_CASE(3) ENS_A_CASE(4) ENS_A_CASE(5) ENS_A_CASE(6)
+                if constexpr (decltype(edge_tag)::value) { if (nqA == 0) phaseA(std::integral_constant<int, 0>{}, edge_tag); }
+#undef ENS_A_CASE
+            };
+            if (!hasE) dispatchA(std::false_type{});
+            else dispatchA(std::true_type{});
+            if (TIMING && wtiming) twA += clock64() - tw0;
             ENS_TICK(0)   // A
             bar_sync(BAR_A, NTC);       // raw tiles complete; nobody in this CTA reads the halo rows of day x any more
             if (tid == 0) {             // (1)
@@ -590,10 +623,12 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
             }
             ENS_TICK(1)
 
+            if (TIMING && wtiming) tw0 = clock64();
             // ---------------- B: owned ocean cells, registers only
-            if (actB) {
+            auto phaseB = [&](auto nq_tag) {
+                constexpr int NQ = decltype(nq_tag)::value;
 #pragma unroll
-                for (int j = 0; j < KO; ++j) {
+                for (int j = 0; j < NQ; ++j) {
                     unsigned bq = 0u;
                     double2 sa = make_double2(0.0, 0.0), sd = sa;              // zeros when dynamicsInc == 0 (NESOSIM.py:287-288)
                     if (a.sw.dynamics) {
@@ -613,10 +648,10 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
                                 d0 = add(d0, mul(vd.x, wgt));
                                 d1 = add(d1, mul(vd.y, wgt));
                             }
-                        sa = make_double2(mask_nan(div_const_flagged(a0, a.conv_div, bq), false, false),
-                                          mask_nan(div_const_flagged(a1, a.conv_div, bq), false, false));
-                        sd = make_double2(mask_nan(div_const_flagged(d0, a.conv_div, bq), false, false),
-                                          mask_nan(div_const_flagged(d1, a.conv_div, bq), false, false));
+                        // (the raw planes are finite and bounded by the guard, so the sums are finite: the
+                        // non-finite -> NaN part of fill_nan_no_negative cannot trigger on an ocean cell)
+                        sa = make_double2(div_const_bare(a0, a.conv_div), div_const_bare(a1, a.conv_div));
+                        sd = make_double2(div_const_bare(d0, a.conv_div), div_const_bare(d1, a.conv_div));
                     }
                     const double h0 = r_h0[j], h1 = r_h1[j];
                     const double W = pW[j];
@@ -644,10 +679,16 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
                     r_h0[j] = mask_nan(t0, false, true);   // NESOSIM.py:332-333
                     r_h1[j] = mask_nan(t1, false, true);
                     r_dn[j] = density_ocean_flagged(r_h0[j], r_h1[j], a.k, bq);
+                    bq |= out_of_guard(r_h0[j]) | out_of_guard(r_h1[j]);
                     badacc |= bq & (flags >> (8 + j));
                 }
-            }
-            if (actA && x + 1 < steps) fetch_raw_inputs(x + 1);   // consumed in the next A
+            };
+#define ENS_B_CASE(n) \
+    if constexpr (KO >= n) { if (nqB == n) phaseB(std::integral_constant<int, n>{}); }
+            ENS_B_CASE(1) ENS_B_CASE(2) ENS_B_CASE(3) ENS_B_CASE(4) ENS_B_CASE(5) ENS_B_CASE(6)
+#undef ENS_B_CASE
+            if (TIMING && wtiming) twB += clock64() - tw0;
+            if ((nqA || hasE) && x + 1 < steps) fetch_raw_inputs(x + 1);   // consumed in the next A
             ENS_TICK(2)   // B compute
             ENS_TICK(3)
             bar_sync(BAR_DRAIN, NTH);       // the bulk stores of day x have finished READING the planes
@@ -655,7 +696,7 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
 
             // ---------------- publish: planes of day x+1 and the neighbours' halo rows
             bool waited_done = false;
-            if (actB) {
+            {
 #pragma unroll
                 for (int j = 0; j < KO; ++j) {
                     if (!((flags >> (8 + j)) & 1u)) continue;
@@ -744,6 +785,10 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
 #undef ENS_TICK
     if (TIMING && timing)
         for (int q = 0; q < (TIMING ? 8 : 1); ++q) a.timing[(long long)blockIdx.x * ENS_NTIMER + (dma_lane ? 8 : 0) + q] = tacc[q];
+    if (TIMING && wtiming) {
+        a.timing[(long long)blockIdx.x * ENS_NTIMER + 16 + (tid >> 5)] = twA;
+        a.timing[(long long)blockIdx.x * ENS_NTIMER + 40 + (tid >> 5)] = twB;
+    }
 }
 
 // host-side state of this path

@@ -325,7 +325,7 @@ constexpr size_t ENS_SMEM_CAP = 227 * 1024;
 // kernel walks.  A strip must satisfy the bulk-copy rules (16-byte aligned start, 16-byte multiple size), hold
 // at least ENS_MIN_ROWS rows (its top two and bottom two rows are its neighbours' halos) and fit shared memory.
 // Returns false if no such cut exists for this cluster size.
-bool try_strip_tables(nesosim_ctx *ctx, int cl, int cap_raw, int cap_ocean, StripTables &t,
+bool try_strip_tables(nesosim_ctx *ctx, int cl, int cap_raw, int cap_ocean, int cap_edge, StripTables &t,
                       std::vector<unsigned short> &codes, size_t &smem_bytes, double &day_cost) {
     const int ny = ctx->cfg.ny, nx = ctx->cfg.nx;
     const std::vector<uint8_t> &mask = ctx->mask_host;
@@ -358,7 +358,7 @@ bool try_strip_tables(nesosim_ctx *ctx, int cl, int cap_raw, int cap_ocean, Stri
         const long long raw = cdil[std::min(rb + 1, ny)] - cdil[std::max(ra - 1, 0)];   // (upper bound of the list length)
         if (ocean > cap_ocean || raw > cap_raw) return -1.0;
         // relative cost per day: an owned ocean cell ~3 raw entries of arithmetic; every cell is stored
-        return 3.0 * ocean + 1.0 * raw + 0.5 * rows * nx;
+        return 3.0 * ocean + 1.0 * raw;
     };
     const double INF = 1e300;
     std::vector<std::vector<double>> best(cl + 1, std::vector<double>(ny + 1, INF));
@@ -379,7 +379,7 @@ bool try_strip_tables(nesosim_ctx *ctx, int cl, int cap_raw, int cap_ocean, Stri
     for (int k = cl, r = ny; k >= 1; --k) { t.row0[k] = r; r = from[k][r]; }
     t.row0[0] = 0;
     codes.clear();
-    int max_ocean = 0, max_raw = 0, max_rows = 0, max_land = 0;
+    int max_ocean = 0, max_raw = 0, max_rows = 0, max_land = 0, max_edge = 0;
     for (int k = 0; k < cl; ++k) {
         const int ra = t.row0[k], rb = t.row0[k + 1];
         std::vector<unsigned short> ri, re, ocl, la;
@@ -421,7 +421,8 @@ bool try_strip_tables(nesosim_ctx *ctx, int cl, int cap_raw, int cap_ocean, Stri
         }
         append(hl, t.hland_off[k], t.hland_n[k]);
         t.halo_tx[k] = halo_ocean * 16;
-        max_raw = std::max(max_raw, t.raw_n[k]);
+        max_raw = std::max(max_raw, t.raw_int_n[k]);
+        max_edge = std::max(max_edge, t.raw_n[k] - t.raw_int_n[k]);
         max_rows = std::max(max_rows, rb - ra);
         max_land = std::max(max_land, (int)la.size());
         max_ocean = std::max(max_ocean, (int)ocl.size());
@@ -433,6 +434,7 @@ bool try_strip_tables(nesosim_ctx *ctx, int cl, int cap_raw, int cap_ocean, Stri
     t.land_alloc = max_land;
     smem_bytes = ens_layout(max_rows, nx, max_land).total;
     if (smem_bytes > ENS_SMEM_CAP) return false;
+    if (max_edge > cap_edge) return false;   // (one edge entry per thread)
     day_cost = best[cl][ny];
     return true;
 }
@@ -481,7 +483,7 @@ int build_strip_tables(nesosim_ctx *ctx) {
             std::vector<unsigned short> codes;
             size_t smem = 0;
             double day_cost = 0;
-            if (!try_strip_tables(ctx, cl, vars[vi].kr * vars[vi].ntc, vars[vi].ko * vars[vi].ntc, t, codes, smem, day_cost)) continue;
+            if (!try_strip_tables(ctx, cl, vars[vi].kr * vars[vi].ntc, vars[vi].ko * vars[vi].ntc, vars[vi].ntc, t, codes, smem, day_cost)) continue;
             const int ncl = max_active_clusters(&vars[vi], cl, smem);
             if (ncl < 1) continue;
             const int rounds = (ctx->cfg.n_members + ncl - 1) / ncl;
@@ -520,6 +522,12 @@ bool ensemble_eligible(nesosim_ctx *ctx, int first_step, int num_steps, const ne
         if (out_base(out, v) && ((uintptr_t)out_base(out, v) % 16)) { *why = "output array not 16-byte aligned"; return false; }
     if ((out->depth_member_stride % 2) || (out->plane_member_stride % 2)) { *why = "odd member stride"; return false; }
     if (!(ctx->g.dx.fast && ctx->g.two_dx.fast && ctx->conv_div.fast)) { *why = "a divisor without the exact fast-division proof"; return false; }
+    if (!(c.dx >= 1.0 && c.dx <= 536870912.0)) { *why = "dx outside [1, 2^29] m"; return false; }
+    for (int i = 0; i < 9; ++i) {
+        const double w = std::fabs(c.conv_weights[i]);
+        if (!(w == 0.0 || (w >= 9.5367431640625e-07 && w <= 1048576.0))) { *why = "kernel weight outside [2^-20, 2^20]"; return false; }
+    }
+    if (!(std::fabs(c.conv_divisor) >= 9.5367431640625e-07 && std::fabs(c.conv_divisor) <= 1048576.0)) { *why = "kernel divisor outside [2^-20, 2^20]"; return false; }
     if (build_strip_tables(ctx) != NESOSIM_OK) { *why = "no strip decomposition fits"; return false; }
     return true;
 }
@@ -547,6 +555,8 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     d.P = ctx->P; d.C = ctx->C; d.UV = ctx->UV;
     d.DA = DA; d.DB = DB; d.cumAcc = cumAcc; d.cumOc = cumOc;
     d.k = ctx->k; d.g = ctx->g; d.rho_new = ctx->rho_fresh_div;
+    d.status = ctx->flags_dev;
+    CU(cudaMemsetAsync(ctx->flags_dev, 0, sizeof(int), st));
     dim3 blk(32, 8), grid((c.nx + 31) / 32, (c.ny + 7) / 8, steps);
     derive_pointwise_kernel<<<grid, blk, 0, st>>>(d);
     derive_scan_kernel<<<(unsigned)((plane + 63) / 64), 64, 0, st>>>(DB, cumAcc, cumOc, plane, steps);
@@ -590,7 +600,7 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     a.sw = Switches{c.dynamicsInc == 1, c.leadlossInc == 1, c.windpackInc == 1, c.atmlossInc == 1, 0};
     a.st = e.tables;
     a.status = ctx->flags_dev;
-    CU(cudaMemsetAsync(ctx->flags_dev, 0, sizeof(int), st));
+    a.dbg = getenv("NESOSIM_ENS_DBG") ? atoi(getenv("NESOSIM_ENS_DBG")) : 0;
     a.timing = nullptr;
     if (dbg_timing) {
         CU(cudaMalloc(&a.timing, sizeof(long long) * ENS_NTIMER * ncl * cl));
@@ -616,6 +626,10 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
                     ncl, e.smem_bytes, kk, e.tables.row0[kk + 1] - e.tables.row0[kk], e.tables.ocean_n[kk], e.tables.land_n[kk],
                     e.tables.raw_n[kk]);
             for (int q = 0; q < 12; ++q) fprintf(stderr, " %s=%.0f", names[q], h[kk * ENS_NTIMER + q] / days);
+            fprintf(stderr, "\n[ens timing]   strip %d per-warp A:", kk);
+            for (int w = 0; w < v->ntc / 32 && w < 24; ++w) fprintf(stderr, " %.0f", h[kk * ENS_NTIMER + 16 + w] / days);
+            fprintf(stderr, "\n[ens timing]   strip %d per-warp B:", kk);
+            for (int w = 0; w < v->ntc / 32 && w < 24; ++w) fprintf(stderr, " %.0f", h[kk * ENS_NTIMER + 40 + w] / days);
             fprintf(stderr, "\n");
         }
     }

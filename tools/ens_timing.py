@@ -19,7 +19,7 @@ params = S.ensemble_params(M, seed=1)
 eng = SnowBudgetEngine(mask, T, 100000, n_members=M, atmlossInc=1)
 eng.set_path("ensemble")
 eng.set_forcing(F["precip"], F["conc"], F["wind"], F["drift"])
-sets = {"all": _lib.OUTPUT_NAMES, "density": ("density",)}
+sets = {"all": _lib.OUTPUT_NAMES, "no_cum": tuple(n for n in _lib.OUTPUT_NAMES if n not in ("snowAcc", "snowOcean")), "density": ("density",)}
 for label, names in sets.items():
     out = eng.alloc_outputs(names=names)
     os.environ.pop("NESOSIM_ENS_TIMING", None)
@@ -31,7 +31,7 @@ for label, names in sets.items():
         eng.run_season(params, ic, out)
         e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
-    nbytes = M * mask.size * (T - 1) * 8 * (12 if label == "all" else 1)
+    nbytes = M * mask.size * (T - 1) * 8 * {"all": 12, "no_cum": 10, "density": 1}[label]
     print("variant=%s cluster=%s M=%d outputs=%s: %.3f ms/season (best of %s) -> %.0f GB/s" % (
         os.environ.get("NESOSIM_ENS_VARIANT", "auto"), os.environ.get("NESOSIM_ENS_CLUSTER", "auto"), M, label,
         min(ts[1:]), ["%.2f" % t for t in ts], nbytes / min(ts[1:]) / 1e6), file=sys.stderr, flush=True)
