@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnesosim_b200.so")
+# NESOSIM_B200_LIB: development override (A/B timing of two builds); the default is the in-tree build
+LIB_PATH = os.environ.get("NESOSIM_B200_LIB") or os.path.join(_HERE, "libnesosim_b200.so")
 
 OK = 0
 ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NOMEM = -1, -2, -3, -4

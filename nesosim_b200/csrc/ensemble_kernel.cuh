@@ -148,7 +148,7 @@ __host__ __device__ inline EnsLayout ens_layout(int rows, int nx, int land_alloc
     L.off_coef = L.off_adv + 2 * L.tile_bytes;
     L.off_codes = L.off_coef + 10 * 8;
     L.off_mbar = (L.off_codes + (unsigned)land_alloc * 2u + 15u) / 16u * 16u;
-    L.total = L.off_mbar + 32;   // [0] staging loads, [8] halo pushes, [16] neighbours done reading
+    L.total = L.off_mbar + 32;   // [0] staging loads, [8] halo pushes, [16] neighbours done reading, [24] planes drained
     return L;
 }
 
@@ -212,6 +212,9 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
     const unsigned HOWN = 2u * ROWB;                   // own cell (lr,c) of h0: HOWN + (lr*nx+c)*8
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
     unsigned short *s_land_code = reinterpret_cast<unsigned short *>(smem + L.off_codes);
-    const unsigned mbar_stage = sbase + L.off_mbar, mbar_halo = mbar_stage + 8u, mbar_done = mbar_stage + 16u;
+    const unsigned mbar_stage = sbase + L.off_mbar, mbar_halo = mbar_stage + 8u, mbar_done = mbar_stage + 16u, mbar_drain = mbar_stage + 24u;
 
     auto LD = [&](unsigned off) -> double { return *reinterpret_cast<const double *>(smem + off); };
     auto LD2 = [&](unsigned off) -> double2 { return *reinterpret_cast<const double2 *>(smem + off); };
@@ -315,6 +318,7 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
     if (dma_lane) {
         mbar_init(mbar_stage, 1);
         mbar_init(mbar_halo, 1);
+        mbar_init(mbar_drain, 1);
         mbar_init(mbar_done, (k > 0 ? 1u : 0u) + (k < CL - 1 ? 1u : 0u) + (CL == 1 ? 1u : 0u));
     }
 
@@ -407,7 +411,7 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
     cluster_arrive_release();
     cluster_wait_acquire();
 
-    unsigned stage_parity = 0, halo_parity = 0, done_parity = 0;
+    unsigned stage_parity = 0, halo_parity = 0, done_parity = 0, drain_parity = 0;
     const bool want_cum = a.out[V_ACC] != nullptr || a.out[V_OCEAN] != nullptr;
 
     for (int m = cid; m < a.M; m += ncl) {
@@ -447,9 +451,9 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
                         if (a.out[V_ACC]) bulk_load(sbase + L.off_stage, a.cumAcc + go, bytes, mbar_stage);
                         if (a.out[V_OCEAN]) bulk_load(sbase + L.off_stage + (unsigned)L.PE * 8u, a.cumOc + go, bytes, mbar_stage);
                     }
+                    mbar_arrive(mbar_drain);     // compute warps may overwrite the planes
                 }
                 __syncwarp();
-                bar_arrive(BAR_DRAIN, NTH);      // compute warps may overwrite the planes
                 ENS_TICK(1)
                 bar_sync(BAR_STORE, NTH);        // planes of day x+1 are complete (and fenced for the async proxy)
                 ENS_TICK(2)                      // waiting for the compute warps
@@ -691,7 +695,10 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
             if ((nqA || hasE) && x + 1 < steps) fetch_raw_inputs(x + 1);   // consumed in the next A
             ENS_TICK(2)   // B compute
             ENS_TICK(3)
-            bar_sync(BAR_DRAIN, NTH);       // the bulk stores of day x have finished READING the planes
+            // the bulk stores of day x have finished READING the planes (no CTA barrier: a warp publishes as soon
+            // as its own cells are done, overlapping its shared-memory stores with the other warps' arithmetic)
+            mbar_wait(mbar_drain, drain_parity);
+            drain_parity ^= 1u;
             ENS_TICK(4)   // drain
 
             // ---------------- publish: planes of day x+1 and the neighbours' halo rows

@@ -357,8 +357,9 @@ bool try_strip_tables(nesosim_ctx *ctx, int cl, int cap_raw, int cap_ocean, int 
         const long long ocean = coc[rb] - coc[ra];
         const long long raw = cdil[std::min(rb + 1, ny)] - cdil[std::max(ra - 1, 0)];   // (upper bound of the list length)
         if (ocean > cap_ocean || raw > cap_raw) return -1.0;
-        // relative cost per day: an owned ocean cell ~3 raw entries of arithmetic; every cell is stored
-        return 3.0 * ocean + 1.0 * raw;
+        // relative cost per day (phase timers on B200): the dynamics phase scales with the raw-list length; the
+        // budget phase is a step function of ceil(ocean / threads), identical for every strip of a sensible cut
+        return 1.0 * raw + 0.3 * ocean;
     };
     const double INF = 1e300;
     std::vector<std::vector<double>> best(cl + 1, std::vector<double>(ny + 1, INF));
