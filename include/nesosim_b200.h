@@ -156,6 +156,10 @@ double nesosim_const_div_eval_host(double x, double c);
 /* Seasons the season-resident path had to hand back to the general kernels (see nesosim_run_season). */
 int64_t nesosim_rerun_count(const nesosim_ctx *ctx);
 
+/* Device time of the season-resident kernel's launches so far (CUDA events on the launching stream) and their
+ * number: what bench.py divides the algorithmic bytes per launch by for its roofline figure. */
+int nesosim_season_kernel_time(const nesosim_ctx *ctx, double *total_ms, int64_t *launches);
+
 /* Number of kernel launches this context has issued since creation (bench.py reports it). */
 int64_t nesosim_launch_count(const nesosim_ctx *ctx);
 

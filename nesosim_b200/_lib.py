@@ -71,6 +71,7 @@ _SIGNATURES = {
                                      C.c_void_p, C.c_void_p]),
     "nesosim_launch_count": (C.c_int64, [C.c_void_p]),
     "nesosim_rerun_count": (C.c_int64, [C.c_void_p]),
+    "nesosim_season_kernel_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "nesosim_set_path": (C.c_int, [C.c_void_p, C.c_int]),
     "nesosim_last_path": (C.c_int, [C.c_void_p]),
     "nesosim_const_div_is_fast": (C.c_int, [C.c_double]),

@@ -156,6 +156,9 @@ struct nesosim_ctx {
     GradConsts g;
     ConstDiv conv_div, rho_fresh_div;
     EnsembleState ens;              // season-resident ensemble path (ensemble_kernel.cuh)
+    cudaEvent_t ens_ev[2] = {nullptr, nullptr};   // around the season kernel, on its own stream
+    double ens_kernel_ms = 0.0;     // device time of every season-kernel launch so far ...
+    long long ens_kernel_launches = 0;   // ... and their number (bench.py: roofline of the dominant kernel)
     int ens_status = 0;             // flag read back from the last season-resident launch (1 = rerun needed)
     long long ens_reruns = 0;
     int path = 0;                   // 0 auto, 1 general per-day launches, 2 season-resident ensemble kernel
@@ -608,13 +611,26 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
         CU(cudaMemset(a.timing, 0, sizeof(long long) * ENS_NTIMER * ncl * cl));
     }
     cfg.gridDim = dim3(ncl * cl);
+    if (!ctx->ens_ev[0]) {
+        CU(cudaEventCreate(&ctx->ens_ev[0]));
+        CU(cudaEventCreate(&ctx->ens_ev[1]));
+    }
+    CU(cudaEventRecord(ctx->ens_ev[0], st));
     CU(cudaLaunchKernelEx(&cfg, kernel, a));
+    CU(cudaEventRecord(ctx->ens_ev[1], st));
     ctx->launches++;
     CU(cudaGetLastError());
     // The kernel only carries the fast divisions; if an operand left their proven range the season is redone by
     // the general kernels (run_members looks at ens_status).  Reading the flag needs the stream to finish.
     CU(cudaMemcpyAsync(&ctx->ens_status, ctx->flags_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ens_ev[0], ctx->ens_ev[1]) == cudaSuccess) {
+            ctx->ens_kernel_ms += ms;
+            ctx->ens_kernel_launches++;
+        }
+    }
     if (dbg_timing) {
         std::vector<long long> h(ENS_NTIMER * ncl * cl);
         CU(cudaMemcpy(h.data(), a.timing, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
@@ -721,6 +737,8 @@ int nesosim_destroy(nesosim_ctx *ctx) {
     if (!ctx) return NESOSIM_OK;
     cudaSetDevice(ctx->cfg.device);
     ensemble_release(ctx->ens);
+    for (int i = 0; i < 2; ++i)
+        if (ctx->ens_ev[i]) cudaEventDestroy(ctx->ens_ev[i]);
     cudaFree(ctx->mask_dev);
     cudaFree(ctx->coef_dev);
     cudaFree(ctx->scratch);
@@ -860,6 +878,12 @@ int nesosim_op_density(const double *depths_dev, const uint8_t *mask_dev, int64_
 
 int64_t nesosim_launch_count(const nesosim_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int64_t nesosim_rerun_count(const nesosim_ctx *ctx) { return ctx ? ctx->ens_reruns : 0; }
+int nesosim_season_kernel_time(const nesosim_ctx *ctx, double *total_ms, int64_t *launches) {
+    if (!ctx || !total_ms || !launches) return fail(NESOSIM_ERR_ARG, "NULL argument");
+    *total_ms = ctx->ens_kernel_ms;
+    *launches = ctx->ens_kernel_launches;
+    return NESOSIM_OK;
+}
 
 int nesosim_set_path(nesosim_ctx *ctx, int path) {
     if (!ctx || path < 0 || path > 2) return fail(NESOSIM_ERR_ARG, "path must be 0 (auto), 1 (per-day kernel) or 2 (season-resident)");

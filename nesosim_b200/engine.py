@@ -181,6 +181,12 @@ class SnowBudgetEngine:
         """Seasons the season-resident kernel handed back to the general kernels (operand-range flag)."""
         return int(self.lib.nesosim_rerun_count(self.handle))
 
+    def season_kernel_time(self):
+        """(total device ms, launches) of the season-resident kernel so far."""
+        ms, n = C.c_double(0), C.c_int64(0)
+        _lib.check(self.lib.nesosim_season_kernel_time(self.handle, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     PATHS = {"auto": 0, "general": 1, "ensemble": 2}
 
     def set_path(self, path):
