@@ -219,7 +219,8 @@ def run_ours(args):
     ny, nx = mask.shape
     forcing = S.make_season(mask, T, seed=SEED)
     ic = S.make_ic(mask, seed=SEED)
-    params = S.ensemble_params(M * world, seed=SEED)[rank * M:(rank + 1) * M]     # this rank's members
+    from nesosim_b200 import sharding
+    params = sharding.shard_params(S.ensemble_params(M * world, seed=SEED), rank, world)   # this rank's members
 
     if args.variant:
         os.environ["NESOSIM_ENS_VARIANT"] = args.variant

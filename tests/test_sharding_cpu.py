@@ -1,0 +1,75 @@
+"""Multi-GPU host logic on CPU: members/seasons are sharded with no data-path collective; two gloo ranks each run
+their members (through the CPU oracle here -- the GPU engine is exercised by the -m gpu tests) and gather a small
+per-member result; the union must equal the single-process run."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from nesosim_b200 import sharding
+from nesosim_b200 import synthetic as S
+from oracle import nesosim_oracle as O
+
+
+def test_member_ranges_partition_every_count():
+    for world in (1, 2, 3, 4, 8):
+        for M in (1, 7, 8, 128, 1024, 1027):
+            spans = [sharding.member_range(M, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == M
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    assert sharding.member_range(1024, 3, 8) == (384, 512)
+
+
+def test_season_assignment_round_robin():
+    years = list(range(1980, 2021))
+    got = [sharding.season_assignment(years, r, 8) for r in range(8)]
+    assert sorted(sum(got, [])) == years and got[0][:2] == [1980, 1988] and len(got[0]) == 6 and len(got[7]) == 5
+
+
+def _member_metric(forcing, ic, mask, row):
+    p = O.Params(windPackFactor=row[0], windPackThresh=row[1], leadLossFactor=row[2], atmLossFactor=row[3])
+    out = O.run_season(forcing, ic, mask, 100000, p, O.Flags(atmlossInc=1))
+    return float(np.nansum(out["snowDepths"][-1]))
+
+
+def _worker(rank, world, port, M, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mask = S.region_mask(shape=(14, 12), kind="disc")
+    forcing = S.make_season(mask, 5, seed=3)
+    ic = S.make_ic(mask, seed=3)
+    params = S.ensemble_params(M, seed=3)
+    mine = sharding.shard_params(params, rank, world)
+    local = torch.tensor([_member_metric(forcing, ic, mask, row) for row in mine], dtype=torch.float64)
+    allv = sharding.gather_member_results(local, M, rank, world)
+    if rank == 0:
+        q.put(allv.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gloo_ranks_reproduce_the_single_process_ensemble():
+    M, world = 5, 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, M, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    mask = S.region_mask(shape=(14, 12), kind="disc")
+    forcing = S.make_season(mask, 5, seed=3)
+    ic = S.make_ic(mask, seed=3)
+    params = S.ensemble_params(M, seed=3)
+    exp = np.array([_member_metric(forcing, ic, mask, row) for row in params])
+    assert np.array_equal(got, exp)
