@@ -205,6 +205,32 @@ def test_ensemble_kernel_hands_out_of_range_operands_to_the_general_kernels(cuda
             assert_parity(out[name][m], ref[name], "%s[%d]" % (name, m))
 
 
+def test_ensemble_kernel_with_drift_defined_over_land(cuda):
+    """Real drift products are NaN over land, which lets the season kernel compute the land entries of its raw lists
+    on day 0 only; a forcing with finite drift everywhere must switch that shortcut off (pre-pass flag)."""
+    from nesosim_b200.engine import SnowBudgetEngine
+    mask = S.region_mask(dx=100000)
+    T, M = 7, 3
+    forcing = S.make_season(mask, T, seed=37)
+    rng = np.random.default_rng(37)
+    d = forcing["drift"]
+    forcing["drift"] = np.where(np.isnan(d), 0.05 * rng.standard_normal(d.shape), d)
+    forcing["drift"][3] = np.nan                       # one missing-drift day in between
+    ic = S.make_ic(mask, seed=37) + 0.01               # snow on land in the initial condition as well
+    params = S.ensemble_params(M, seed=37)
+    for path in PATHS:
+        eng = SnowBudgetEngine(mask, T, 100000, n_members=M, atmlossInc=1)
+        eng.set_path(path)
+        eng.set_forcing(forcing["precip"], forcing["conc"], forcing["wind"], forcing["drift"])
+        out = {k: v.cpu().numpy() for k, v in eng.run_season(params, ic).items()}
+        assert eng.rerun_count() == 0
+        for m in range(M):
+            ref = O.run_season(forcing, ic, mask, 100000, oracle_params(params[m]), O.Flags(atmlossInc=1))
+            for name in out:
+                assert_parity(out[name][m], ref[name], "%s[%d] %s" % (name, m, path))
+        eng.close()
+
+
 def test_step_day_matches_calc_budget(cuda):
     """nesosim_step_day has calcBudget's in-place contract (NESOSIM.py:224-347)."""
     from nesosim_b200.engine import SnowBudgetEngine
