@@ -1,0 +1,141 @@
+"""Domain decomposition of one season over several ranks, for grids too large to be worth a single GPU (the 5 km
+pan-Arctic case of BASELINE.json; SURVEY.md §8e "Space").
+
+The fused dependency radius of one budget step is two cells (np.gradient r=1 followed by the 3x3 Gaussian r=1, reference
+``NESOSIM.py:204-213`` and ``:184-185``), and only the two depth layers cross cell boundaries.  So the grid is cut into
+contiguous row strips, every rank runs the ordinary engine on its strip EXTENDED by two ghost rows towards each
+neighbour, and after every day the ghost rows of ``snowDepths[x+1]`` are replaced by the neighbour's owned rows -- a
+(2 layers x 2 rows x nx) message per neighbour per day (57 KB at nx = 1785).  Nothing else is ever exchanged: the
+forcing ghost rows are staged once, accumulators never look sideways.  Owned rows come out value-identical to the
+single-domain run: inside the extended strip the stencils of the owned rows only ever touch real data, and the
+one-sided differences / zero padding the kernels apply at the edges of the LOCAL grid only reach the ghost rows --
+except on the first and last strip, where the local edge IS the global edge.
+
+The exchange uses ``torch.distributed`` point-to-point operations (NCCL over NVLink between the GPUs of a box; gloo in
+the CPU tests).  The stepping itself is behind a small interface so the same driver runs the GPU engine in production
+and the numpy oracle in the CPU test of the exchange logic.
+"""
+import numpy as np
+
+from . import sharding
+
+GHOST = 2
+
+
+def strip_rows(ny, rank, world):
+    """Owned global rows [lo, hi) of `rank`, and the extended range [elo, ehi) including ghost rows."""
+    lo, hi = sharding.member_range(ny, rank, world)
+    return lo, hi, max(lo - GHOST, 0), min(hi + GHOST, ny)
+
+
+class GpuStripStepper:
+    """One strip on one GPU through the C ABI (``nesosim_run_season`` one day at a time, general kernels)."""
+
+    def __init__(self, local_mask, num_days, dx, forcing_local, params_row, ic_local, device=0, **flags):
+        from .engine import SnowBudgetEngine
+        self.eng = SnowBudgetEngine(local_mask, num_days, dx, n_members=1, device=device, **flags)
+        self.eng.set_path("general")
+        self.eng.set_forcing(forcing_local["precip"], forcing_local["conc"], forcing_local["wind"], forcing_local["drift"],
+                             forcing_local.get("rho_clim"))
+        self.params = [list(params_row)]
+        self.ic = ic_local
+        self.out = self.eng.alloc_outputs()
+
+    def step(self, x):
+        self.eng.run_season(self.params, self.ic, self.out, first_step=x, num_steps=1)
+
+    def depths(self, slot):
+        """Writable view (2, rows, nx) of snowDepths[slot] (a torch tensor on the strip's device)."""
+        return self.out["snowDepths"][0, slot]
+
+    def result(self, rows):
+        import torch
+        torch.cuda.synchronize()
+        return {k: v[0][..., rows, :].cpu().numpy() for k, v in self.out.items()}
+
+
+def exchange_ghost_rows(depths, rank, world, top_ghost, bottom_ghost, group=None):
+    """Swap boundary rows of one (2, rows, nx) depth slot with the neighbouring ranks.
+
+    ``top_ghost`` / ``bottom_ghost``: number of ghost rows this strip has above / below (0 at the global edges).
+    Sends the first / last ``GHOST`` OWNED rows, receives into the ghost rows.  All four transfers are posted as one
+    batch so NCCL runs them as a single grouped operation."""
+    import torch
+    import torch.distributed as dist
+    ops, landing = [], []
+    nrows = depths.shape[1]
+    if rank > 0 and top_ghost:
+        send = depths[:, top_ghost:top_ghost + GHOST].contiguous()
+        recv = torch.empty_like(depths[:, :top_ghost].contiguous())
+        ops += [dist.P2POp(dist.isend, send, rank - 1, group=group), dist.P2POp(dist.irecv, recv, rank - 1, group=group)]
+        landing.append((slice(0, top_ghost), recv))
+    if rank < world - 1 and bottom_ghost:
+        send = depths[:, nrows - bottom_ghost - GHOST:nrows - bottom_ghost].contiguous()
+        recv = torch.empty_like(depths[:, nrows - bottom_ghost:].contiguous())
+        ops += [dist.P2POp(dist.isend, send, rank + 1, group=group), dist.P2POp(dist.irecv, recv, rank + 1, group=group)]
+        landing.append((slice(nrows - bottom_ghost, nrows), recv))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for rows, buf in landing:
+        depths[:, rows] = buf
+
+
+def slice_rows(forcing, elo, ehi):
+    out = {}
+    for k, v in forcing.items():
+        if v is None or k == "rho_clim":
+            out[k] = v
+        else:
+            out[k] = np.ascontiguousarray(v[..., elo:ehi, :])
+    return out
+
+
+def run_decomposed_season(mask, num_days, dx, forcing, params_row, ic, rank, world, make_stepper, group=None):
+    """This rank's part of one season: returns (lo, hi, {array: owned rows}).  ``forcing`` / ``ic`` / ``mask`` are the
+    GLOBAL arrays (each rank slices its rows; only the slices go to the device).  ``make_stepper(local_mask, num_days,
+    dx, forcing_local, params_row, ic_local)`` builds the strip stepper (``GpuStripStepper`` in production)."""
+    ny = mask.shape[0]
+    lo, hi, elo, ehi = strip_rows(ny, rank, world)
+    if hi - lo < GHOST:
+        raise ValueError("strips must own at least %d rows (ny=%d over %d ranks)" % (GHOST, ny, world))
+    stepper = make_stepper(np.ascontiguousarray(mask[elo:ehi]), num_days, dx, slice_rows(forcing, elo, ehi), params_row,
+                           None if ic is None else np.ascontiguousarray(ic[elo:ehi]))
+    top, bottom = lo - elo, ehi - hi
+    for x in range(num_days - 1):
+        stepper.step(x)
+        if world > 1:
+            exchange_ghost_rows(stepper.depths(x + 1), rank, world, top, bottom, group=group)
+    return lo, hi, stepper.result(slice(top, top + (hi - lo)))
+
+
+def run_decomposed_season_one_process(mask, num_days, dx, forcing, params_row, ic, n_strips, make_stepper):
+    """All strips in ONE process (one GPU), stepped day by day with the ghost rows copied between them directly: the
+    same decomposition and the same per-strip calls as the multi-rank driver, for boxes with fewer GPUs than strips
+    and for the single-GPU parity test.  Returns the assembled global arrays."""
+    ny = mask.shape[0]
+    strips = []
+    for r in range(n_strips):
+        lo, hi, elo, ehi = strip_rows(ny, r, n_strips)
+        st = make_stepper(np.ascontiguousarray(mask[elo:ehi]), num_days, dx, slice_rows(forcing, elo, ehi), params_row,
+                          None if ic is None else np.ascontiguousarray(ic[elo:ehi]))
+        strips.append((lo, hi, elo, ehi, st))
+    for x in range(num_days - 1):
+        for s in strips:
+            s[4].step(x)
+        for a, b in zip(strips[:-1], strips[1:]):           # a above b
+            da, db = a[4].depths(x + 1), b[4].depths(x + 1)
+            top_b, bot_a = b[0] - b[2], a[3] - a[1]
+            na = da.shape[1]
+            send_down = da[:, na - bot_a - GHOST:na - bot_a].clone()      # a's last owned rows -> b's top ghost rows
+            send_up = db[:, top_b:top_b + GHOST].clone()                  # b's first owned rows -> a's bottom ghost rows
+            db[:, :top_b] = send_down[:, GHOST - top_b:]
+            da[:, na - bot_a:] = send_up[:, :bot_a]
+    out = None
+    for lo, hi, elo, ehi, st in strips:
+        part = st.result(slice(lo - elo, lo - elo + (hi - lo)))
+        if out is None:
+            out = {k: np.empty(v.shape[:-2] + (ny, v.shape[-1]), dtype=v.dtype) for k, v in part.items()}
+        for k, v in part.items():
+            out[k][..., lo:hi, :] = v
+    return out

@@ -1,0 +1,120 @@
+"""Row-strip domain decomposition (nesosim_b200/domain.py): the exchange logic on CPU with the numpy oracle as the
+strip stepper (two gloo ranks, and several strips in one process), and the GPU engine as the stepper on one GPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from nesosim_b200 import domain
+from nesosim_b200 import synthetic as S
+from oracle import nesosim_oracle as O
+
+PARAMS = [5.8e-7, 5., 1.45e-7, 2.2e-8]
+NAMES = ("snowDepths", "density", "snowAcc", "snowOcean", "snowAdv", "snowDiv", "snowLead", "snowAtm",
+         "snowWindPackLoss", "snowWindPackGain", "snowWindPack")
+
+
+class OracleStripStepper:
+    """The CPU oracle on one extended strip, one day at a time (test stand-in for GpuStripStepper)."""
+
+    def __init__(self, local_mask, num_days, dx, forcing_local, params_row, ic_local):
+        self.mask, self.dx, self.f = local_mask, dx, forcing_local
+        self.p = O.Params(windPackFactor=params_row[0], windPackThresh=params_row[1], leadLossFactor=params_row[2],
+                          atmLossFactor=params_row[3])
+        self.fl = O.Flags(atmlossInc=1)
+        T, ny, nx = forcing_local["precip"].shape
+        self.s = O.gen_empty_arrays(T, ny, nx)
+        if ic_local is not None:
+            half = O.initial_depths(ic_local, forcing_local["conc"][0], self.p)
+            self.s["snowDepths"][0, 0] = half
+            self.s["snowDepths"][0, 1] = half
+        self._t = {}
+
+    def step(self, x):
+        f = self.f
+        O.calc_budget(self.s, f["conc"][x], f["precip"][x], f["drift"][x], f["wind"][x], np.full(f["conc"][x].shape, np.nan),
+                      self.mask, self.dx, x, self.p, self.fl)
+
+    def depths(self, slot):
+        return torch.from_numpy(self.s["snowDepths"][slot])      # shares memory with the numpy state
+
+    def result(self, rows):
+        return {k: self.s[k][..., rows, :].copy() for k in NAMES}
+
+
+def setup(ny=23, nx=17, T=7, seed=5):
+    mask = S.region_mask(shape=(ny, nx), kind="disc")
+    forcing = S.make_season(mask, T, seed=seed)
+    ic = S.make_ic(mask, seed=seed) * 2
+    p = O.Params(windPackFactor=PARAMS[0], windPackThresh=PARAMS[1], leadLossFactor=PARAMS[2], atmLossFactor=PARAMS[3])
+    ref = O.run_season(forcing, ic, mask, 50000, p, O.Flags(atmlossInc=1))
+    return mask, forcing, ic, ref
+
+
+def test_strip_rows_cover_the_grid_with_two_ghost_rows():
+    for ny, world in ((23, 2), (90, 3), (1785, 8)):
+        prev_hi = 0
+        for r in range(world):
+            lo, hi, elo, ehi = domain.strip_rows(ny, r, world)
+            assert lo == prev_hi and elo == max(lo - 2, 0) and ehi == min(hi + 2, ny)
+            prev_hi = hi
+        assert prev_hi == ny
+
+
+@pytest.mark.parametrize("n_strips", [2, 3, 5])
+def test_strips_in_one_process_reproduce_the_single_domain_run(n_strips):
+    mask, forcing, ic, ref = setup()
+    got = domain.run_decomposed_season_one_process(mask, 7, 50000, forcing, PARAMS, ic, n_strips, OracleStripStepper)
+    for k in NAMES:
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+
+
+def _rank(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mask, forcing, ic, _ = setup()
+    lo, hi, part = domain.run_decomposed_season(mask, 7, 50000, forcing, PARAMS, ic, rank, world, OracleStripStepper)
+    q.put((rank, lo, hi, part))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gloo_ranks_exchange_ghost_rows():
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rank, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    parts = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    _, _, _, ref = setup()
+    for rank, lo, hi, part in parts:
+        for k in NAMES:
+            assert np.array_equal(part[k], ref[k][..., lo:hi, :], equal_nan=True), (k, rank)
+
+
+@pytest.mark.gpu
+def test_gpu_strips_reproduce_the_single_domain_run(cuda):
+    mask = S.region_mask(dx=100000)
+    T = 6
+    forcing = S.make_season(mask, T, seed=11)
+    ic = S.make_ic(mask, seed=11)
+    p = O.Params(windPackFactor=PARAMS[0], windPackThresh=PARAMS[1], leadLossFactor=PARAMS[2], atmLossFactor=PARAMS[3])
+    ref = O.run_season(forcing, ic, mask, 100000, p, O.Flags(atmlossInc=1))
+
+    def make(local_mask, num_days, dx, forcing_local, params_row, ic_local):
+        return domain.GpuStripStepper(local_mask, num_days, dx, forcing_local, params_row, ic_local, atmlossInc=1)
+
+    got = domain.run_decomposed_season_one_process(mask, T, 100000, forcing, PARAMS, ic, 4, make)
+    for k in NAMES:
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
