@@ -360,9 +360,12 @@ bool try_strip_tables(nesosim_ctx *ctx, int cl, int cap_raw, int cap_ocean, int 
         const long long ocean = coc[rb] - coc[ra];
         const long long raw = cdil[std::min(rb + 1, ny)] - cdil[std::max(ra - 1, 0)];   // (upper bound of the list length)
         if (ocean > cap_ocean || raw > cap_raw) return -1.0;
-        // relative cost per day (phase timers on B200): the dynamics phase scales with the raw-list length; the
-        // budget phase is a step function of ceil(ocean / threads), identical for every strip of a sensible cut
-        return 1.0 * raw + 0.3 * ocean;
+        // relative cost per day: the dynamics phase scales with the raw-list length, the budget phase with the owned
+        // ocean cells, the bulk stores with the strip's cells.  NESOSIM_ENS_COST="w_raw,w_ocean,w_cells" overrides
+        // the weights (tuning aid).
+        double w[3] = {1.0, 0.3, 0.0};
+        if (const char *env = getenv("NESOSIM_ENS_COST")) sscanf(env, "%lf,%lf,%lf", &w[0], &w[1], &w[2]);
+        return w[0] * raw + w[1] * ocean + w[2] * rows * nx;
     };
     const double INF = 1e300;
     std::vector<std::vector<double>> best(cl + 1, std::vector<double>(ny + 1, INF));
