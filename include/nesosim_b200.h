@@ -141,6 +141,18 @@ int nesosim_op_fill_nan_no_negative(double *arr_dev, const uint8_t *mask_dev, in
 int nesosim_op_density(const double *depths_dev, const uint8_t *mask_dev, int64_t n, double rhoFresh,
                        double rhoOld, double minSnowD, double *density_dev, void *stream);
 
+/* Final-product diagnostics: the array preparation of OutputSnowModelFinal (utils.py:161-179) on what main hands it
+ * (NESOSIM.py:654: snowVol = h0+h1, snowDepth = snowVol/iceConc), fused into one pass and written as the float32
+ * fields the NetCDF file stores: every field np.around(x, 4) (= rint(x*1e4)/1e4 in fp64) then cast to float32;
+ * snow_volume, snow_depth and snow_density are NaN where iceConc < ice_conc_mask (skipped when ice_conc_mask <= 0),
+ * ice_concentration is then NaN where iceConc < 0.15.  Inputs are device arrays of one member: depths [T][2][plane],
+ * everything else [T][plane]; any output may be NULL.  96 B -> 24 B per cell-day on the way to the host. */
+int nesosim_final_products(const double *depths_dev, const double *density_dev, const double *conc_dev,
+                           const double *precip_dev, const double *wind_dev, int num_days, int64_t plane,
+                           double ice_conc_mask, float *snow_depth_dev, float *snow_volume_dev,
+                           float *snow_density_dev, float *ice_conc_dev, float *precip_out_dev, float *wind_out_dev,
+                           void *stream);
+
 /* Kernel path of nesosim_run_season: 0 = automatic (default), 1 = general per-day kernel (any grid),
  * 2 = season-resident cluster kernel (grids up to 96x96, variable density, whole season; error otherwise).
  * Both paths produce identical values.  nesosim_last_path reports which one the last season used. */

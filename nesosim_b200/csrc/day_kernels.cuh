@@ -245,6 +245,42 @@ __global__ void smooth_kernel(const __grid_constant__ SmoothArgs a) {
     a.out[(long long)gy * a.nx + gx] = res;
 }
 
+// ------------------------------------------------------------------ final products (OutputSnowModelFinal, utils.py:161-179)
+
+// np.around(x, 4): multiply by 10**4, round half to even, divide -- three fp64 operations, then the float32 cast
+// the NetCDF variable applies on assignment.
+__device__ __forceinline__ float around4_f32(double x) {
+    return __double2float_rn(__ddiv_rn(rint(__dmul_rn(x, 10000.0)), 10000.0));
+}
+
+struct FinalArgs {
+    const double *depths, *density, *conc, *precip, *wind;
+    long long plane, n;          // cells per day, cells per season (T*plane)
+    double ice_conc_mask;
+    float *snow_depth, *snow_volume, *snow_density, *ice_conc, *precip_out, *wind_out;
+};
+
+__global__ void final_products_kernel(const __grid_constant__ FinalArgs a) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+        const long long t = i / a.plane, c = i - t * a.plane;
+        const double h0 = a.depths[(2 * t) * a.plane + c], h1 = a.depths[(2 * t + 1) * a.plane + c];
+        const double C = a.conc[i];
+        double vol = add(h0, h1);                       // snowDepths[:, 0]+snowDepths[:, 1]   (NESOSIM.py:654)
+        double depth = __ddiv_rn(vol, C);               // .../iceConcDays  (0/0 and x/0 are data, masked below)
+        double dens = a.density ? a.density[i] : 0.0;
+        const bool masked = a.ice_conc_mask > 0.0 && C < a.ice_conc_mask;   // NaN < m is False
+        if (masked) vol = depth = dens = qnan();
+        double cc = C;
+        if (a.ice_conc_mask > 0.0 && C < 0.15) cc = qnan();
+        if (a.snow_volume) a.snow_volume[i] = around4_f32(vol);
+        if (a.snow_depth) a.snow_depth[i] = around4_f32(depth);
+        if (a.snow_density) a.snow_density[i] = around4_f32(dens);
+        if (a.ice_conc) a.ice_conc[i] = around4_f32(cc);
+        if (a.precip_out) a.precip_out[i] = around4_f32(a.precip[i]);
+        if (a.wind_out) a.wind_out[i] = around4_f32(a.wind[i]);
+    }
+}
+
 // ------------------------------------------------------------------ per-function kernels (known-answer tests)
 
 __global__ void op_dynamics_kernel(const double *drift, const double *h, int ny, int nx, double deltaT,

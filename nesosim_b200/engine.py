@@ -308,3 +308,24 @@ def op_density(depths, mask, rhoFresh=200., rhoOld=350., minSnowD=0.02, device=0
     _lib.check(lib.nesosim_op_density(h.data_ptr(), m.data_ptr(), rho.numel(), float(rhoFresh), float(rhoOld),
                                       float(minSnowD), rho.data_ptr(), _cur_stream(device)))
     return rho.cpu().numpy()
+
+
+FINAL_NAMES = ("snow_depth", "snow_volume", "snow_density", "ice_concentration", "precipitation", "wind_speed")
+
+
+def final_products(snowDepths, density, iceConc, precip, wind, ice_conc_mask=0.5, device=0):
+    """The float32 fields of ``final/NESOSIMv11_*.nc`` (``OutputSnowModelFinal``, utils.py:161-179, fed as ``main`` feeds
+    it, NESOSIM.py:654) computed in one fused pass on the GPU.  Inputs: one member's (T,2,ny,nx) depths and (T,ny,nx)
+    arrays, numpy or CUDA tensors; returns a dict of float32 CUDA tensors (T,ny,nx)."""
+    torch = _torch()
+    lib = _lib.load()
+    d = _cuda(snowDepths, device, torch.float64)
+    others = [_cuda(a, device, torch.float64) for a in (density, iceConc, precip, wind)]
+    T, _, ny, nx = d.shape
+    out = {n: torch.empty((T, ny, nx), dtype=torch.float32, device=d.device) for n in FINAL_NAMES}
+    _lib.check(lib.nesosim_final_products(d.data_ptr(), others[0].data_ptr(), others[1].data_ptr(), others[2].data_ptr(),
+                                          others[3].data_ptr(), T, ny * nx, float(ice_conc_mask),
+                                          out["snow_depth"].data_ptr(), out["snow_volume"].data_ptr(),
+                                          out["snow_density"].data_ptr(), out["ice_concentration"].data_ptr(),
+                                          out["precipitation"].data_ptr(), out["wind_speed"].data_ptr(), _cur_stream(device)))
+    return out
