@@ -146,9 +146,11 @@ int nesosim_op_density(const double *depths_dev, const uint8_t *mask_dev, int64_
  * fields the NetCDF file stores: every field np.around(x, 4) (= rint(x*1e4)/1e4 in fp64) then cast to float32;
  * snow_volume, snow_depth and snow_density are NaN where iceConc < ice_conc_mask (skipped when ice_conc_mask <= 0),
  * ice_concentration is then NaN where iceConc < 0.15.  Inputs are device arrays of one member: depths [T][2][plane],
- * everything else [T][plane]; any output may be NULL.  96 B -> 24 B per cell-day on the way to the host. */
+ * everything else [T][plane]; any output may be NULL.  96 B -> 24 B per cell-day on the way to the host.
+ * For an ensemble pass the members' stacked arrays as num_days = M*T and forcing_days = T: depths/density (and the
+ * outputs) then hold M*T days while conc/precip/wind hold T days that every member shares (0 = same as num_days). */
 int nesosim_final_products(const double *depths_dev, const double *density_dev, const double *conc_dev,
-                           const double *precip_dev, const double *wind_dev, int num_days, int64_t plane,
+                           const double *precip_dev, const double *wind_dev, int num_days, int forcing_days, int64_t plane,
                            double ice_conc_mask, float *snow_depth_dev, float *snow_volume_dev,
                            float *snow_density_dev, float *ice_conc_dev, float *precip_out_dev, float *wind_out_dev,
                            void *stream);

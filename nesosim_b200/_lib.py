@@ -69,7 +69,7 @@ _SIGNATURES = {
     "nesosim_op_fill_nan_no_negative": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "nesosim_op_density": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double,
                                      C.c_void_p, C.c_void_p]),
-    "nesosim_final_products": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_int64, C.c_double] + [C.c_void_p] * 7),
+    "nesosim_final_products": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_int64, C.c_double] + [C.c_void_p] * 7),
     "nesosim_launch_count": (C.c_int64, [C.c_void_p]),
     "nesosim_rerun_count": (C.c_int64, [C.c_void_p]),
     "nesosim_season_kernel_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

@@ -255,7 +255,8 @@ __device__ __forceinline__ float around4_f32(double x) {
 
 struct FinalArgs {
     const double *depths, *density, *conc, *precip, *wind;
-    long long plane, n;          // cells per day, cells per season (T*plane)
+    long long plane, n;          // cells per day, cells in all (days*plane)
+    long long forcing_days;      // conc/precip/wind repeat with this period (members sharing one forcing)
     double ice_conc_mask;
     float *snow_depth, *snow_volume, *snow_density, *ice_conc, *precip_out, *wind_out;
 };
@@ -264,7 +265,8 @@ __global__ void final_products_kernel(const __grid_constant__ FinalArgs a) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
         const long long t = i / a.plane, c = i - t * a.plane;
         const double h0 = a.depths[(2 * t) * a.plane + c], h1 = a.depths[(2 * t + 1) * a.plane + c];
-        const double C = a.conc[i];
+        const long long fi = (t % a.forcing_days) * a.plane + c;
+        const double C = a.conc[fi];
         double vol = add(h0, h1);                       // snowDepths[:, 0]+snowDepths[:, 1]   (NESOSIM.py:654)
         double depth = __ddiv_rn(vol, C);               // .../iceConcDays  (0/0 and x/0 are data, masked below)
         double dens = a.density ? a.density[i] : 0.0;
@@ -276,8 +278,8 @@ __global__ void final_products_kernel(const __grid_constant__ FinalArgs a) {
         if (a.snow_depth) a.snow_depth[i] = around4_f32(depth);
         if (a.snow_density) a.snow_density[i] = around4_f32(dens);
         if (a.ice_conc) a.ice_conc[i] = around4_f32(cc);
-        if (a.precip_out) a.precip_out[i] = around4_f32(a.precip[i]);
-        if (a.wind_out) a.wind_out[i] = around4_f32(a.wind[i]);
+        if (a.precip_out) a.precip_out[i] = around4_f32(a.precip[fi]);
+        if (a.wind_out) a.wind_out[i] = around4_f32(a.wind[fi]);
     }
 }
 

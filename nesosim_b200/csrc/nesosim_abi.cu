@@ -880,16 +880,18 @@ int nesosim_op_density(const double *depths_dev, const uint8_t *mask_dev, int64_
 }
 
 int nesosim_final_products(const double *depths_dev, const double *density_dev, const double *conc_dev,
-                           const double *precip_dev, const double *wind_dev, int num_days, int64_t plane,
+                           const double *precip_dev, const double *wind_dev, int num_days, int forcing_days, int64_t plane,
                            double ice_conc_mask, float *snow_depth_dev, float *snow_volume_dev,
                            float *snow_density_dev, float *ice_conc_dev, float *precip_out_dev, float *wind_out_dev,
                            void *stream) {
-    if (!depths_dev || !conc_dev || num_days < 1 || plane < 1) return fail(NESOSIM_ERR_ARG, "bad argument");
+    if (!depths_dev || !conc_dev || num_days < 1 || plane < 1 || forcing_days < 0) return fail(NESOSIM_ERR_ARG, "bad argument");
+    if (forcing_days == 0) forcing_days = num_days;
+    if (num_days % forcing_days) return fail(NESOSIM_ERR_ARG, "num_days must be a multiple of forcing_days");
     if (snow_density_dev && !density_dev) return fail(NESOSIM_ERR_ARG, "snow_density wanted but density is NULL");
     if ((precip_out_dev && !precip_dev) || (wind_out_dev && !wind_dev)) return fail(NESOSIM_ERR_ARG, "forcing output wanted but its input is NULL");
     FinalArgs a;
     a.depths = depths_dev; a.density = density_dev; a.conc = conc_dev; a.precip = precip_dev; a.wind = wind_dev;
-    a.plane = plane; a.n = (long long)num_days * plane; a.ice_conc_mask = ice_conc_mask;
+    a.plane = plane; a.n = (long long)num_days * plane; a.forcing_days = forcing_days; a.ice_conc_mask = ice_conc_mask;
     a.snow_depth = snow_depth_dev; a.snow_volume = snow_volume_dev; a.snow_density = snow_density_dev;
     a.ice_conc = ice_conc_dev; a.precip_out = precip_out_dev; a.wind_out = wind_out_dev;
     const unsigned blocks = (unsigned)std::min<long long>((a.n + 255) / 256, 148 * 16);

@@ -313,18 +313,23 @@ def op_density(depths, mask, rhoFresh=200., rhoOld=350., minSnowD=0.02, device=0
 FINAL_NAMES = ("snow_depth", "snow_volume", "snow_density", "ice_concentration", "precipitation", "wind_speed")
 
 
-def final_products(snowDepths, density, iceConc, precip, wind, ice_conc_mask=0.5, device=0):
+def final_products(snowDepths, density, iceConc, precip, wind, ice_conc_mask=0.5, device=0, out=None):
     """The float32 fields of ``final/NESOSIMv11_*.nc`` (``OutputSnowModelFinal``, utils.py:161-179, fed as ``main`` feeds
-    it, NESOSIM.py:654) computed in one fused pass on the GPU.  Inputs: one member's (T,2,ny,nx) depths and (T,ny,nx)
-    arrays, numpy or CUDA tensors; returns a dict of float32 CUDA tensors (T,ny,nx)."""
+    it, NESOSIM.py:654) computed in one fused pass on the GPU.  Inputs: (T,2,ny,nx) depths and (T,ny,nx) arrays of one
+    member, or an ensemble's (M,T,2,ny,nx) / (M,T,ny,nx) depths and density with the (T,ny,nx) forcing all members
+    share; numpy or CUDA tensors.  Returns a dict of float32 CUDA tensors shaped like ``density``."""
     torch = _torch()
     lib = _lib.load()
     d = _cuda(snowDepths, device, torch.float64)
-    others = [_cuda(a, device, torch.float64) for a in (density, iceConc, precip, wind)]
-    T, _, ny, nx = d.shape
-    out = {n: torch.empty((T, ny, nx), dtype=torch.float32, device=d.device) for n in FINAL_NAMES}
-    _lib.check(lib.nesosim_final_products(d.data_ptr(), others[0].data_ptr(), others[1].data_ptr(), others[2].data_ptr(),
-                                          others[3].data_ptr(), T, ny * nx, float(ice_conc_mask),
+    rho = _cuda(density, device, torch.float64)
+    forcing = [_cuda(a, device, torch.float64) for a in (iceConc, precip, wind)]
+    T, ny, nx = forcing[0].shape
+    days = rho.numel() // (ny * nx)
+    assert d.numel() == 2 * rho.numel() and days % T == 0
+    if out is None:
+        out = {n: torch.empty(tuple(rho.shape), dtype=torch.float32, device=d.device) for n in FINAL_NAMES}
+    _lib.check(lib.nesosim_final_products(d.data_ptr(), rho.data_ptr(), forcing[0].data_ptr(), forcing[1].data_ptr(),
+                                          forcing[2].data_ptr(), days, T, ny * nx, float(ice_conc_mask),
                                           out["snow_depth"].data_ptr(), out["snow_volume"].data_ptr(),
                                           out["snow_density"].data_ptr(), out["ice_concentration"].data_ptr(),
                                           out["precipitation"].data_ptr(), out["wind_speed"].data_ptr(), _cur_stream(device)))

@@ -115,6 +115,14 @@ def test_gpu_final_products_match_oracle(cuda):
         got = {k: v.cpu().numpy() for k, v in E.final_products(h, dens, conc, precip, wind, ice_conc_mask=m).items()}
         for k in exp:
             assert same32(got[k], exp[k]), (k, m)
+    # an ensemble: members stacked, one shared forcing
+    h3 = np.stack([h, h * 0.5, h * 2.0])
+    d3 = np.stack([dens, dens, dens])
+    got = {k: v.cpu().numpy() for k, v in E.final_products(h3, d3, conc, precip, wind).items()}
+    for m in range(3):
+        exp = FP.final_fields(h3[m], d3[m], conc, precip, wind)
+        for k in exp:
+            assert same32(got[k][m], exp[k]), (k, m)
     # straight from a season still resident on the device
     from nesosim_b200.engine import SnowBudgetEngine
     mask = S.region_mask(dx=100000)
