@@ -53,6 +53,31 @@ day_step_kernel(const __grid_constant__ DayArgs a) {
     const double *h0p = a.prev[V_H0] + (long long)m * a.prev_stride[V_H0];
     const double *h1p = a.prev[V_H1] + (long long)m * a.prev_stride[V_H1];
 
+    // The point-wise inputs of this thread's cells (forcing, mask, yesterday's nine accumulators) are requested
+    // before anything else: they land while the tiles are staged and the raw dynamics computed, instead of each
+    // load waiting in front of its one consumer behind the previous store.
+    constexpr int CPT = TY / (DAY_THREADS / TX);   // cells per thread
+    const int ptx = tid & (TX - 1), pgx = x0 + ptx;
+    double pf_P[CPT], pf_C[CPT], pf_W[CPT], pf_prev[CPT][9];
+    bool pf_land[CPT];
+#pragma unroll
+    for (int rr = 0; rr < CPT; ++rr) {
+        const int gy = y0 + (tid / TX) + rr * (DAY_THREADS / TX);
+        pf_P[rr] = pf_C[rr] = pf_W[rr] = 0.0;
+        pf_land[rr] = true;
+#pragma unroll
+        for (int v = 0; v < 9; ++v) pf_prev[rr][v] = 0.0;
+        if (pgx < nx && gy < ny) {
+            const long long o = (long long)gy * nx + pgx;
+            pf_P[rr] = __ldg(a.P + o);
+            pf_C[rr] = __ldg(a.C + o);
+            pf_W[rr] = __ldg(a.W + o);
+            pf_land[rr] = is_land(__ldg(a.mask + o));
+#pragma unroll
+            for (int v = 0; v < 9; ++v) pf_prev[rr][v] = a.prev[V_ACC + v][(long long)m * a.prev_stride[V_ACC + v] + o];
+        }
+    }
+
     if (a.sw.dynamics) {
         for (int i = tid; i < (TY + 4) * (TX + 4); i += DAY_THREADS) {
             const int r = i / (TX + 4), c = i - r * (TX + 4);
@@ -108,7 +133,7 @@ day_step_kernel(const __grid_constant__ DayArgs a) {
         const int gy = y0 + ty;
         if (gy >= ny) break;
         const long long o = (long long)gy * nx + gx;
-        const bool land = is_land(__ldg(a.mask + o));
+        const bool land = pf_land[rr];
 
         double adv0 = 0.0, adv1 = 0.0, div0 = 0.0, div1 = 0.0, h0, h1;
         if (a.sw.dynamics) {
@@ -126,7 +151,7 @@ day_step_kernel(const __grid_constant__ DayArgs a) {
             h1 = h1p[o];
         }
 
-        const double P = __ldg(a.P + o), C = __ldg(a.C + o), W = __ldg(a.W + o);
+        const double P = pf_P[rr], C = pf_C[rr], W = pf_W[rr];
         const double pd = div_const(P, a.rho_new);           // precipDayT/snowDensityNew (NESOSIM.py:260)
         const double acc = mul(pd, C);                       // NESOSIM.py:263
         const double oc = -mul(pd, sub(1.0, C));             // NESOSIM.py:267
@@ -136,7 +161,7 @@ day_step_kernel(const __grid_constant__ DayArgs a) {
         double wpl = 0.0, wpg = 0.0, wpn = 0.0;
         if (a.sw.windpack) wind_packing(wt, h0, mc, a.k, wpl, wpg, wpn);
 
-        auto prev = [&](int v) { return a.prev[v][(long long)m * a.prev_stride[v] + o]; };
+        auto prev = [&](int v) { return pf_prev[rr][v - V_ACC]; };
         auto store = [&](int v, double val) {
             if (a.next[v]) a.next[v][(long long)m * a.next_stride[v] + o] = val;
         };
