@@ -80,39 +80,69 @@ def _cpu_member_season(args):
     return time.perf_counter() - t0
 
 
-def cpu_baseline(members_per_core=1, cores=None, num_days=NUM_DAYS):
-    """Process-parallel over members on all host cores; returns (cell-days/s, cores, sample text, seconds)."""
-    import multiprocessing as mp
-    from nesosim_b200 import synthetic as S
-    cores = cores or os.cpu_count() or 1
-    n = cores * members_per_core
-    params = S.ensemble_params(n, seed=SEED)
-    jobs = [(SEED, params[i], num_days) for i in range(n)]
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(cores) as pool:
-        pool.map(_cpu_member_season, jobs[:cores])          # warm the workers (imports, forcing cache)
+class CpuPool:
+    """One worker process per host core, each holding the synthetic forcing; reused across steps."""
+
+    def __init__(self, cores=None, num_days=NUM_DAYS):
+        import multiprocessing as mp
+        self.cores = cores or os.cpu_count() or 1
+        self.num_days = num_days
+        self.pool = mp.get_context("spawn").Pool(self.cores)
+        from nesosim_b200 import synthetic as S
+        self.params = S.ensemble_params(self.cores * 8, seed=SEED)
+        self.pool.map(_cpu_member_season, [(SEED, self.params[i], num_days) for i in range(self.cores)])   # warm the workers
+
+    def step(self, members_per_core=1):
+        """One bounded sample: members_per_core member-seasons on every core.  Returns (cell-days/s, seconds, text)."""
+        n = self.cores * members_per_core
+        jobs = [(SEED, self.params[i % len(self.params)], self.num_days) for i in range(n)]
         t0 = time.perf_counter()
-        pool.map(_cpu_member_season, jobs)
+        self.pool.map(_cpu_member_season, jobs)
         dt = time.perf_counter() - t0
-    cells = 8100 * (num_days - 1) * n
-    return cells / dt, cores, "%d member-seasons (90x90x%d steps each), %d processes" % (n, num_days - 1, cores), dt
+        cells = 8100 * (self.num_days - 1) * n
+        return cells / dt, dt, "%d member-seasons (90x90x%d steps each), %d processes" % (n, self.num_days - 1, self.cores)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_baseline(members_per_core=1, cores=None, num_days=NUM_DAYS, target_seconds=12.0):
+    """Process-parallel over members on all host cores, sized to about `target_seconds` of CPU work per core;
+    returns (cell-days/s, cores, sample text, seconds)."""
+    pool = CpuPool(cores, num_days)
+    try:
+        v, dt, sample = pool.step(members_per_core)
+        reps = max(1, min(32, int(target_seconds / max(dt, 1e-3))))
+        if reps > 1:
+            v, dt, sample = pool.step(members_per_core * reps)
+        return v, pool.cores, sample, dt
+    finally:
+        pool.close()
 
 
 def run_reference(args):
+    """The reference's CPU path (the numpy port of its calcBudget loop: the reference itself is pure Python whose
+    dependencies are absent) on all host cores.  One step = one bounded sample of the workload, sized so that
+    steps + warmup stay within about two minutes."""
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    vals = []
-    cores = os.cpu_count() or 1
-    per_core = 1
-    for _ in range(args.warmup and 1):
-        cpu_baseline(per_core, cores)
-    t_total = 0.0
-    sample = ""
-    for _ in range(args.steps):
-        v, cores, sample, dt = cpu_baseline(per_core, cores)
-        vals.append(v)
-        t_total += dt
+    pool = CpuPool()
+    try:
+        _, dt1, _ = pool.step(1)
+        per_step = 110.0 / max(args.steps + args.warmup, 1)
+        mpc = max(1, min(32, int(per_step / max(dt1, 1e-3))))
+        for _ in range(max(args.warmup, 0)):
+            pool.step(mpc)
+        vals, t_total, sample = [], 0.0, ""
+        for _ in range(args.steps):
+            v, dt, sample = pool.step(mpc)
+            vals.append(v)
+            t_total += dt
+        cores = pool.cores
+    finally:
+        pool.close()
     value = float(np.mean(vals))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(args.steps, 1),

@@ -373,3 +373,14 @@ def main(year1, month1, day1, year2, month2, day2, outPathT='.', forcingPathT='.
                                 snowDiv[x + 1], snowAdv[x + 1], snowLead[x + 1], snowAtm[x + 1], snowWindPack[x + 1],
                                 snowWindPackLoss[x + 1], snowWindPackGain[x + 1], density[x + 1], dates[-1], figpath,
                                 totalOutStr=saveStr)
+
+
+def run_multiseason(yearS, yearE, month1, day1, month2, day2, rank=0, world=1, **main_kwargs):
+    """The loop of the reference's ``run_multiseason.py`` (``source/run_multiseason.py:39-50``: one independent
+    ``main`` per start year, year2 = year1 + 1), with the seasons dealt round-robin over ``world`` ranks -- one process
+    per GPU, no communication.  Returns the start years this rank ran."""
+    from . import sharding
+    mine = sharding.season_assignment(list(range(yearS, yearE + 1)), rank, world)
+    for y in mine:
+        main(year1=y, month1=month1, day1=day1, year2=y + 1, month2=month2, day2=day2, **main_kwargs)
+    return mine
