@@ -83,6 +83,85 @@ def test_season_100km_multiseason_params_ensemble(cuda, path):
     assert not np.array_equal(got["snowDepths"][1], got["snowDepths"][2], equal_nan=True)
 
 
+@pytest.mark.parametrize("case", ["oneseason", "multiseason"])
+@pytest.mark.parametrize("path", PATHS)
+def test_full_season_against_reference_digest(cuda, path, case):
+    """A full Aug 15 - May 1 season (260 days) on the 100 km grid against the digest the REFERENCE's own calcBudget
+    loop produced for it (tests/golden/season_100km_digest.npz, made by tests/golden/make_golden.py)."""
+    from golden_util import OUT_NAMES, assert_identical, canon_sha, load
+    from nesosim_b200.engine import SnowBudgetEngine
+    g = load("season_100km_digest.npz")
+    mask = S.region_mask(dx=100000)
+    T, seed = int(g["T"]), int(g["seed"])
+    F = S.make_season(mask, T, seed=seed)
+    ic = S.make_ic(mask, seed=seed)
+    for k in ("precip", "conc", "wind", "drift"):
+        if canon_sha(F[k]) != str(g["in_sha__" + k]):
+            pytest.skip("synthetic generator output differs from the fixture (numpy/scipy version)")
+    eng = SnowBudgetEngine(mask, T, 100000, n_members=1, atmlossInc=int(case == "multiseason"))
+    eng.set_path(path)
+    eng.set_forcing(F["precip"], F["conc"], F["wind"], F["drift"])
+    out = {k: v[0].cpu().numpy() for k, v in eng.run_season([g[case + "__params"]], ic).items()}
+    assert eng.last_path() == path and eng.rerun_count() == 0
+    for name in OUT_NAMES:
+        assert_identical(out[name][-1], g[case + "__last__" + name], name + "[-1]")
+        assert_identical(out[name][60], g[case + "__day60__" + name], name + "[60]")
+        assert canon_sha(out[name]) == str(g[case + "__sha__" + name]), name
+
+
+def test_full_size_ensemble_properties(cuda):
+    """BASELINE's per-GPU shard at full size (128 members x 260 days x 90x90; 25.9 GB of outputs): too large for the
+    CPU oracle, so size-independent properties -- determinism, member-independence of the accumulation planes,
+    identical members for identical parameters, land mask on every day, and agreement of a sample of members with
+    the general kernels (themselves checked against the oracle above)."""
+    from nesosim_b200.engine import SnowBudgetEngine
+    torch = cuda
+    mask = S.region_mask(dx=100000)
+    T, M = 260, 128
+    F = S.make_season(mask, T, seed=2024)
+    ic = S.make_ic(mask, seed=2024)
+    params = S.ensemble_params(M, seed=2024)
+    params[77] = params[3]                                   # two members with the same parameter set
+    eng = SnowBudgetEngine(mask, T, 100000, n_members=M, atmlossInc=1)
+    eng.set_path("ensemble")
+    eng.set_forcing(F["precip"], F["conc"], F["wind"], F["drift"])
+    out = eng.run_season(params, ic)
+    assert eng.rerun_count() == 0
+
+    def same(a, b):
+        return bool(((a == b) | (torch.isnan(a) & torch.isnan(b))).all())
+
+    sums = {k: torch.nan_to_num(v, nan=3.0).sum(dtype=torch.float64).item() for k, v in out.items()}
+    out2 = eng.run_season(params, ic)                        # determinism: a second run is identical
+    for k in out:
+        assert torch.nan_to_num(out2[k], nan=3.0).sum(dtype=torch.float64).item() == sums[k], k
+    assert same(out["snowDepths"], out2["snowDepths"])
+    del out2
+    for k in ("snowAcc", "snowOcean"):                        # member-independent planes
+        assert same(out[k], out[k][:1].expand_as(out[k])), k
+    for k in out:                                             # identical parameters, identical members
+        assert same(out[k][77], out[k][3]), k
+    assert not same(out["snowDepths"][5], out["snowDepths"][6])
+    land = torch.from_numpy((mask > 10) | (mask < 1)).cuda()
+    h = out["snowDepths"]
+    assert bool(torch.isnan(h[:, 1:, :, land]).all())          # land is NaN from slot 1 on
+    ho = h[:, :, :, ~land]
+    assert bool(((ho >= 0) | torch.isnan(ho)).all())           # fill_nan_no_negative: no negative depth survives
+    assert float(torch.isnan(ho).double().mean()) < 0.05       # (NaN only where the forcing itself is NaN)
+    dens = out["density"][:, 1:]
+    ok = torch.isnan(dens) | ((dens >= 200.0) & (dens <= 350.0))
+    assert bool(ok.all())
+    # a sample of members through the general kernels
+    pick = [0, 3, 64, 127]
+    eng2 = SnowBudgetEngine(mask, T, 100000, n_members=len(pick), atmlossInc=1)
+    eng2.set_path("general")
+    eng2.set_forcing(F["precip"], F["conc"], F["wind"], F["drift"])
+    ref = eng2.run_season(params[pick], ic)
+    for k in out:
+        for i, m in enumerate(pick):
+            assert same(out[k][m], ref[k][i]), (k, m)
+
+
 @pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("flags", [dict(dynamicsInc=0), dict(leadlossInc=0, atmlossInc=1), dict(windpackInc=0),
                                    dict(dynamicsInc=0, leadlossInc=0, windpackInc=0, atmlossInc=0)])
