@@ -89,6 +89,15 @@ int nesosim_destroy(nesosim_ctx *ctx);
 int nesosim_set_forcing(nesosim_ctx *ctx, const double *precip_dev, const double *conc_dev,
                         const double *wind_dev, const double *drift_dev, const double *rho_clim_dev);
 
+/* A batch of seasons in one context (the loop of run_multiseason.py:39-50 as one native call): `n_sets` independent
+ * forcing stacks laid out [n_sets][T][ny][nx] (drift [n_sets][T][2][ny][nx]); member m runs on stack
+ * member_set_host[m] for set_days_host[set] days (2 <= days <= T: seasons of different length, e.g. leap years).  Every
+ * later nesosim_run_season advances each member through ITS season; output slots beyond a member's last day are left
+ * untouched.  densityType='variable' only.  nesosim_set_forcing returns the context to a single shared season. */
+int nesosim_set_forcing_sets(nesosim_ctx *ctx, int n_sets, const double *precip_dev, const double *conc_dev,
+                             const double *wind_dev, const double *drift_dev, const int32_t *member_set_host,
+                             const int32_t *set_days_host);
+
 /* The season: IC handling of main (NESOSIM.py:604-609; ic_dev = [ny][nx] total depth shared by all members,
  * or [M][ny][nx] when ic_per_member != 0, or NULL for zero depth) when first_step == 0, then steps
  * x = first_step .. first_step+num_steps-1 of `for x in range(numDays-1): calcBudget(...)`

@@ -52,6 +52,7 @@ _SIGNATURES = {
     "nesosim_create": (C.c_int, [C.POINTER(Config), C.c_void_p, C.POINTER(C.c_void_p)]),
     "nesosim_destroy": (C.c_int, [C.c_void_p]),
     "nesosim_set_forcing": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5),
+    "nesosim_set_forcing_sets": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "nesosim_run_season": (C.c_int, [C.c_void_p, C.POINTER(MemberParams), C.c_void_p, C.c_int,
                                      C.POINTER(Outputs), C.c_int, C.c_int, C.c_void_p]),
     "nesosim_step_day": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

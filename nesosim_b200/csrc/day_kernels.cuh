@@ -33,6 +33,11 @@ struct DayArgs {
     ConstDiv rho_new;                      // fresh-snow density of this step (200 or the clim value)
     double w[9];                           // 3x3 kernel, row-major
     Switches sw;
+    // forcing sets (multi-season batches): member m reads its planes `member_set[m] * set_stride` elements further
+    // (2x that for the drift pair) and sits out once `x` reaches its season's step count.  NULL = one shared season.
+    const int *member_set, *set_steps;
+    long long set_stride;
+    int x;
 };
 
 constexpr int TX = 32;
@@ -50,6 +55,10 @@ day_step_kernel(const __grid_constant__ DayArgs a) {
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
     const int tid = threadIdx.x;
     const int ny = a.ny, nx = a.nx;
+    const int fset = a.member_set ? a.member_set[m] : 0;
+    if (a.set_steps && a.x >= a.set_steps[fset]) return;      // this member's season is over (whole CTA)
+    const long long fo = (long long)fset * a.set_stride;
+    const double *aP = a.P + fo, *aC = a.C + fo, *aW = a.W + fo, *aU = a.U + 2 * fo, *aV = a.V + 2 * fo;
     const double *h0p = a.prev[V_H0] + (long long)m * a.prev_stride[V_H0];
     const double *h1p = a.prev[V_H1] + (long long)m * a.prev_stride[V_H1];
 
@@ -69,9 +78,9 @@ day_step_kernel(const __grid_constant__ DayArgs a) {
         for (int v = 0; v < 9; ++v) pf_prev[rr][v] = 0.0;
         if (pgx < nx && gy < ny) {
             const long long o = (long long)gy * nx + pgx;
-            pf_P[rr] = __ldg(a.P + o);
-            pf_C[rr] = __ldg(a.C + o);
-            pf_W[rr] = __ldg(a.W + o);
+            pf_P[rr] = __ldg(aP + o);
+            pf_C[rr] = __ldg(aC + o);
+            pf_W[rr] = __ldg(aW + o);
             pf_land[rr] = is_land(__ldg(a.mask + o));
 #pragma unroll
             for (int v = 0; v < 9; ++v) pf_prev[rr][v] = a.prev[V_ACC + v][(long long)m * a.prev_stride[V_ACC + v] + o];
@@ -87,8 +96,8 @@ day_step_kernel(const __grid_constant__ DayArgs a) {
                 const long long o = (long long)gy * nx + gx;
                 h0 = h0p[o];
                 h1 = h1p[o];
-                ut = mul(__ldg(a.U + o), a.k.deltaT);   // driftGday[0]*deltaT (NESOSIM.py:204,210)
-                vt = mul(__ldg(a.V + o), a.k.deltaT);
+                ut = mul(__ldg(aU + o), a.k.deltaT);   // driftGday[0]*deltaT (NESOSIM.py:204,210)
+                vt = mul(__ldg(aV + o), a.k.deltaT);
             }
             s_h[0][r][c] = h0;
             s_h[1][r][c] = h1;
@@ -195,6 +204,8 @@ struct InitArgs {
     const double *ic;         // NULL -> zero depth
     long long ic_stride;      // 0 (shared) or plane (per member)
     const double *conc0;      // first day's concentration
+    const int *member_set;    // forcing set of each member (NULL: one shared season)
+    long long set_stride;     // elements between the sets' concentration stacks
     double minConc;
     double *slot0[NVAR];
     long long stride[NVAR];
@@ -207,7 +218,7 @@ __global__ void init_slot0_kernel(const __grid_constant__ InitArgs a) {
     double half = 0.0;
     if (a.ic) {
         double v = a.ic[(long long)m * a.ic_stride + o];
-        if (__ldg(a.conc0 + o) < a.minConc) v = 0.0;
+        if (__ldg(a.conc0 + (a.member_set ? a.member_set[m] * a.set_stride : 0) + o) < a.minConc) v = 0.0;
         half = mul(v, 0.5);
     }
 #pragma unroll

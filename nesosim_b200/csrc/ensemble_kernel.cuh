@@ -46,7 +46,7 @@ namespace cg = cooperative_groups;
 // cumAcc[x][cell], cumOc[x][cell] = snowAcc[x+1], snowOcean[x+1]   running sums (NESOSIM.py:264,268)
 
 struct DeriveArgs {
-    int ny, nx, steps;                 // steps = T-1
+    int ny, nx, steps, T, sets;        // steps = T-1; `sets` independent forcing sets [set][T][...] (1 = plain season)
     const double *P, *C, *UV;          // [T][plane], [T][plane], [T][2][plane]
     double2 *DA;                       // [steps][plane][2]
     double2 *DB;                       // [steps][plane]
@@ -60,31 +60,40 @@ struct DeriveArgs {
 __global__ void derive_pointwise_kernel(const __grid_constant__ DeriveArgs a) {
     const int gx = blockIdx.x * blockDim.x + threadIdx.x;
     const int gy = blockIdx.y * blockDim.y + threadIdx.y;
-    const int x = blockIdx.z;
+    const int set = blockIdx.z / a.steps, x = blockIdx.z - set * a.steps;
     if (gx >= a.nx || gy >= a.ny) return;
     const long long plane = (long long)a.ny * a.nx, o = (long long)gy * a.nx + gx;
-    const double *U = a.UV + (long long)x * 2 * plane, *V = U + plane;
+    const long long fin = ((long long)set * a.T + x) * plane;       // this day in the [set][T] forcing stacks
+    const long long fout = ((long long)set * a.steps + x) * plane;  // ... and in the [set][steps] derived stacks
+    const double *U = a.UV + fin * 2, *V = U + plane;
     const int xm = max(gx - 1, 0), xp = min(gx + 1, a.nx - 1), ym = max(gy - 1, 0), yp = min(gy + 1, a.ny - 1);
     auto ut = [&](int r, int c) { return mul(U[(long long)r * a.nx + c], a.k.deltaT); };
     auto vt = [&](int r, int c) { return mul(V[(long long)r * a.nx + c], a.k.deltaT); };
     const double utc = ut(gy, gx), vtc = vt(gy, gx);
-    double2 *da = a.DA + ((long long)x * plane + o) * 2;
+    double2 *da = a.DA + (fout + o) * 2;
     const double gxu = gradient1d(ut(gy, xm), utc, ut(gy, xp), gx, a.nx, a.g);
     const double gyv = gradient1d(vt(ym, gx), vtc, vt(yp, gx), gy, a.ny, a.g);
     da[0] = make_double2(utc, vtc);
     da[1] = make_double2(gxu, gyv);
     if (out_of_guard(utc) | out_of_guard(vtc) | out_of_guard(gxu) | out_of_guard(gyv)) atomicOr(a.status, 1);
-    const double C = a.C[(long long)x * plane + o];
-    const double pd = div_const(a.P[(long long)x * plane + o], a.rho_new);
+    const double C = a.C[fin + o];
+    const double pd = div_const(a.P[fin + o], a.rho_new);
     const double omc = sub(1.0, C);
-    a.DB[(long long)x * plane + o] = make_double2(mul(pd, C), omc);
-    a.cumOc[(long long)x * plane + o] = -mul(pd, omc);   // parks oc until the scan
+    a.DB[fout + o] = make_double2(mul(pd, C), omc);
+    a.cumOc[fout + o] = -mul(pd, omc);   // parks oc until the scan
 }
 
 // One thread per cell, sequential in time, loads batched 8 days ahead (add-latency bound, not load-latency bound).
-__global__ void derive_scan_kernel(const double2 *DB, double *cumAcc, double *cumOc, long long plane, int steps) {
-    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= plane) return;
+__global__ void derive_scan_kernel(const double2 *DB, double *cumAcc, double *cumOc, long long plane, int steps, int sets) {
+    long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= plane * sets) return;
+    {   // one thread per (set, cell): move to the set's stack
+        const long long set = o / plane;
+        o -= set * plane;
+        DB += set * steps * plane;
+        cumAcc += set * steps * plane;
+        cumOc += set * steps * plane;
+    }
     double sa = 0.0, so = 0.0;
     constexpr int B = 8;
     for (int x0 = 0; x0 < steps; x0 += B) {
@@ -174,6 +183,9 @@ struct EnsArgs {
     const double *ic;                  // NULL -> zero depth
     long long ic_stride;               // 0 shared, plane per member
     const double *conc0;
+    // forcing sets (multi-season batches): member m uses set member_set[m] of `sets` stacked seasons and runs
+    // set_steps[set] steps; NULL = every member uses the one season and runs T-1 steps
+    const int *member_set, *set_steps;
     double *out[NVAR];                 // member 0, slot 0 of each array (NULL: not stored)
     long long mstride[NVAR];
     const MemberCoef *coef;
@@ -278,7 +290,9 @@ __device__ __forceinline__ void st_cluster(unsigned addr, double v) {
 // reading their halo rows" -- each CTA, after its phase A, arrives (relaxed) on its neighbours' barrier; only the
 // threads that push wait on it; (2) "my neighbours' halo cells of day x+1 have landed" -- the barrier counts the
 // bytes they deliver with st.async.  Cluster-wide barriers are used once per member only.
-template <int NTC, int KR, int KO, bool TIMING>
+// SETS: members may use different forcing sets / season lengths (compiled apart so that the plain ensemble keeps its
+// parameter-bank pointers and its uniform trip count)
+template <int NTC, int KR, int KO, bool TIMING, bool SETS>
 __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
     constexpr int SXR = ENS_SXR;
     constexpr int NTH = NTC + 32;
@@ -307,7 +321,7 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
     const int tid = threadIdx.x;
     const bool comp = tid < NTC;       // compute thread; the last warp is the DMA warp
     const bool dma_lane = (tid == NTC);
-    const int steps = a.T - 1;
+    const int max_steps = a.T - 1;
 
     const int n_raw_int = a.st.raw_int_n[k], n_raw = a.st.raw_n[k];
     const int n_ocean = a.st.ocean_n[k], n_land = a.st.land_n[k];
@@ -415,6 +429,12 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
     const bool want_cum = a.out[V_ACC] != nullptr || a.out[V_OCEAN] != nullptr;
 
     for (int m = cid; m < a.M; m += ncl) {
+        // this member's forcing set and season length
+        const int fset = SETS ? a.member_set[m] : 0;
+        const int steps = SETS ? a.set_steps[fset] : max_steps;
+        const long long set_d = SETS ? (long long)fset * max_steps * plane : 0, set_f = SETS ? (long long)fset * a.T * plane : 0;
+        const double2 *mDA = a.DA + set_d * 2, *mDB = a.DB + set_d;
+        const double *mCumAcc = a.cumAcc + set_d, *mCumOc = a.cumOc + set_d, *mW = a.W + set_f, *mConc0 = a.conc0 + set_f;
         // output address of variable v, time slot `slot` of member m, first cell of this strip
         const long long mo_plane = (long long)m * a.mstride[V_DENS] + (long long)ra * nx;
         const long long mo_depth = (long long)m * a.mstride[V_H0] + (long long)ra * nx;
@@ -436,11 +456,11 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
                     if (x + PF_DAYS < steps && !(a.dbg & 2)) {   // pull the forcing of day x+PF_DAYS into L2
                         const long long gp = (long long)(x + PF_DAYS) * plane;
                         const int r0 = ra > 0 ? ra - 1 : ra, r1 = rb < ny ? rb + 1 : rb;
-                        if (a.sw.dynamics) l2_prefetch(a.DA + (gp + (long long)r0 * nx) * 2, (unsigned)((r1 - r0) * nx) * 32u);
-                        l2_prefetch(a.DB + gp + go_own, (unsigned)ncell * 16u);
-                        l2_prefetch(a.W + gp + go_own, (unsigned)ncell * 8u);
-                        if (a.out[V_ACC]) l2_prefetch(a.cumAcc + gp + go_own, (unsigned)ncell * 8u);
-                        if (a.out[V_OCEAN]) l2_prefetch(a.cumOc + gp + go_own, (unsigned)ncell * 8u);
+                        if (a.sw.dynamics) l2_prefetch(mDA + (gp + (long long)r0 * nx) * 2, (unsigned)((r1 - r0) * nx) * 32u);
+                        l2_prefetch(mDB + gp + go_own, (unsigned)ncell * 16u);
+                        l2_prefetch(mW + gp + go_own, (unsigned)ncell * 8u);
+                        if (a.out[V_ACC]) l2_prefetch(mCumAcc + gp + go_own, (unsigned)ncell * 8u);
+                        if (a.out[V_OCEAN]) l2_prefetch(mCumOc + gp + go_own, (unsigned)ncell * 8u);
                     }
                     bulk_wait_read<0>();         // day x-1: planes and staging rows have been read
                     ENS_TICK(0)                  // drain
@@ -448,8 +468,8 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
                         const unsigned bytes = (unsigned)ncell * 8u;
                         const long long go = (long long)x * plane + go_own;
                         mbar_expect_tx(mbar_stage, (a.out[V_ACC] ? bytes : 0u) + (a.out[V_OCEAN] ? bytes : 0u));
-                        if (a.out[V_ACC]) bulk_load(sbase + L.off_stage, a.cumAcc + go, bytes, mbar_stage);
-                        if (a.out[V_OCEAN]) bulk_load(sbase + L.off_stage + (unsigned)L.PE * 8u, a.cumOc + go, bytes, mbar_stage);
+                        if (a.out[V_ACC]) bulk_load(sbase + L.off_stage, mCumAcc + go, bytes, mbar_stage);
+                        if (a.out[V_OCEAN]) bulk_load(sbase + L.off_stage + (unsigned)L.PE * 8u, mCumOc + go, bytes, mbar_stage);
                     }
                     mbar_arrive(mbar_drain);     // compute warps may overwrite the planes
                 }
@@ -497,7 +517,7 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
             double half = 0.0;
             if (a.ic) {
                 double v = a.ic[(long long)m * a.ic_stride + o];
-                if (a.conc0[o] < a.k.minConc) v = 0.0;
+                if (mConc0[o] < a.k.minConc) v = 0.0;
                 half = mul(v, 0.5);
             }
             badacc |= out_of_guard(half);
@@ -532,7 +552,7 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
         double pW[KO];
         auto fetch_raw_inputs = [&](int x) {
             if (a.dbg & 1) x = 0;
-            const char *base = reinterpret_cast<const char *>(a.DA) + ((long long)x * plane + go_raw) * 32;
+            const char *base = reinterpret_cast<const char *>(mDA) + ((long long)x * plane + go_raw) * 32;
 #pragma unroll
             for (int q = 0; q <= KR; ++q) {
                 if ((q < KR) ? (q < nqA) : hasE) {
@@ -544,8 +564,8 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
         };
         auto fetch_cell_inputs = [&](int x) {
             if (a.dbg & 1) x = 0;
-            const char *bb = reinterpret_cast<const char *>(a.DB) + ((long long)x * plane + go_own) * 16;
-            const char *bw = reinterpret_cast<const char *>(a.W) + ((long long)x * plane + go_own) * 8;
+            const char *bb = reinterpret_cast<const char *>(mDB) + ((long long)x * plane + go_own) * 16;
+            const char *bw = reinterpret_cast<const char *>(mW) + ((long long)x * plane + go_own) * 8;
 #pragma unroll
             for (int j = 0; j < KO; ++j) {
                 if (j < nqB) {
@@ -745,8 +765,8 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
                     if (x == 0) {
                         const long long o = go_own + (long long)lr * nx + c;
                         const double h0 = LD(HOWN + ci);
-                        const double W = __ldg(a.W + o);
-                        const double omc = __ldg(a.DB + o).y;
+                        const double W = __ldg(mW + o);
+                        const double omc = __ldg(mDB + o).y;
                         const double wt = wind_flag(W, mc.wpt);
                         vLead = add(0.0, a.sw.leadloss ? -mul(mul(mul(mul(mul(wt, mc.llf), a.k.deltaT), h0), W), omc) : 0.0);
                         vAtm = add(0.0, a.sw.atmloss ? atm_loss(wt, h0, W, mc, a.k) : 0.0);

@@ -159,6 +159,8 @@ struct nesosim_ctx {
     cudaEvent_t ens_ev[2] = {nullptr, nullptr};   // around the season kernel, on its own stream
     double ens_kernel_ms = 0.0;     // device time of every season-kernel launch so far ...
     long long ens_kernel_launches = 0;   // ... and their number (bench.py: roofline of the dominant kernel)
+    int n_sets = 1;                 // forcing sets (nesosim_set_forcing_sets); 1 = plain season
+    int *member_set_dev = nullptr, *set_steps_dev = nullptr;
     int ens_status = 0;             // flag read back from the last season-resident launch (1 = rerun needed)
     long long ens_reruns = 0;
     int path = 0;                   // 0 auto, 1 general per-day launches, 2 season-resident ensemble kernel
@@ -270,6 +272,10 @@ int launch_day(nesosim_ctx *ctx, int x, const double *P, const double *C, const 
     std::memcpy(a.w, ctx->cfg.conv_weights, sizeof(a.w));
     a.sw = Switches{ctx->cfg.dynamicsInc == 1, ctx->cfg.leadlossInc == 1, ctx->cfg.windpackInc == 1,
                     ctx->cfg.atmlossInc == 1, ctx->cfg.density_clim != 0};
+    a.member_set = ctx->member_set_dev ? ctx->member_set_dev + m0 : nullptr;
+    a.set_steps = ctx->set_steps_dev;
+    a.set_stride = (long long)ctx->cfg.num_days * ctx->plane;
+    a.x = x;
     dim3 grid((a.nx + TX - 1) / TX, (a.ny + TY - 1) / TY, mcount);
     day_step_kernel<<<grid, DAY_THREADS, 0, st>>>(a);
     ctx->launches++;
@@ -284,6 +290,8 @@ int launch_init(nesosim_ctx *ctx, const double *ic, int ic_per_member, const dou
     a.ic = (ic && ic_per_member) ? ic + (long long)m0 * ctx->plane : ic;
     a.ic_stride = ic_per_member ? ctx->plane : 0;
     a.conc0 = conc0;
+    a.member_set = ctx->member_set_dev ? ctx->member_set_dev + m0 : nullptr;
+    a.set_stride = (long long)ctx->cfg.num_days * ctx->plane;
     a.minConc = ctx->cfg.minConc;
     for (int v = 0; v < NVAR; ++v) {
         double *p;
@@ -311,9 +319,11 @@ struct EnsVariant {
     int ntc, kr, ko;
     void (*kernel)(const EnsArgs);
     void (*kernel_timing)(const EnsArgs);
+    void (*kernel_sets)(const EnsArgs);    // members on different forcing sets (nesosim_set_forcing_sets)
 };
 #define ENS_V(ntc, kr, ko) \
-    {"t" #ntc "r" #kr "o" #ko, ntc, kr, ko, ensemble_season_kernel<ntc, kr, ko, false>, ensemble_season_kernel<ntc, kr, ko, true>}
+    {"t" #ntc "r" #kr "o" #ko, ntc, kr, ko, ensemble_season_kernel<ntc, kr, ko, false, false>, ensemble_season_kernel<ntc, kr, ko, true, false>, \
+     ensemble_season_kernel<ntc, kr, ko, false, true>}
 const EnsVariant *ens_variants(int *n) {
     static const EnsVariant v[] = {
         ENS_V(352, 3, 2), ENS_V(224, 4, 3), ENS_V(480, 2, 2), ENS_V(608, 2, 1), ENS_V(480, 2, 1), ENS_V(736, 2, 1), ENS_V(352, 6, 5),
@@ -545,7 +555,7 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     const long long plane = ctx->plane;
     const int steps = c.num_days - 1;
     EnsembleState &e = ctx->ens;
-    const size_t cells = (size_t)steps * plane;
+    const size_t cells = (size_t)steps * plane * ctx->n_sets;
     const size_t need = cells * (2 + 1 + 1) * sizeof(double2);
     if (e.derived_bytes < need) {
         cudaFree(e.derived);
@@ -558,15 +568,15 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     double *cumAcc = (double *)(DB + cells), *cumOc = cumAcc + cells;
     // member-independent pre-pass: part of the season, recomputed on every call
     DeriveArgs d;
-    d.ny = c.ny; d.nx = c.nx; d.steps = steps;
+    d.ny = c.ny; d.nx = c.nx; d.steps = steps; d.T = c.num_days; d.sets = ctx->n_sets;
     d.P = ctx->P; d.C = ctx->C; d.UV = ctx->UV;
     d.DA = DA; d.DB = DB; d.cumAcc = cumAcc; d.cumOc = cumOc;
     d.k = ctx->k; d.g = ctx->g; d.rho_new = ctx->rho_fresh_div;
     d.status = ctx->flags_dev;
     CU(cudaMemsetAsync(ctx->flags_dev, 0, sizeof(int), st));
-    dim3 blk(32, 8), grid((c.nx + 31) / 32, (c.ny + 7) / 8, steps);
+    dim3 blk(32, 8), grid((c.nx + 31) / 32, (c.ny + 7) / 8, steps * ctx->n_sets);
     derive_pointwise_kernel<<<grid, blk, 0, st>>>(d);
-    derive_scan_kernel<<<(unsigned)((plane + 63) / 64), 64, 0, st>>>(DB, cumAcc, cumOc, plane, steps);
+    derive_scan_kernel<<<(unsigned)((plane * ctx->n_sets + 63) / 64), 64, 0, st>>>(DB, cumAcc, cumOc, plane, steps, ctx->n_sets);
     ctx->launches += 2;
     CU(cudaGetLastError());
 
@@ -574,7 +584,7 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     const EnsVariant *v = &ens_variants(&nv_)[e.variant];
     const int cl = e.tables.cluster;
     const bool dbg_timing = getenv("NESOSIM_ENS_TIMING") != nullptr;   // debug aid: per-phase cycle totals to stderr
-    void (*kernel)(const EnsArgs) = dbg_timing ? v->kernel_timing : v->kernel;
+    void (*kernel)(const EnsArgs) = ctx->member_set_dev ? v->kernel_sets : (dbg_timing ? v->kernel_timing : v->kernel);
     CU(cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem_bytes));
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[1];
@@ -596,6 +606,8 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     a.ic = (ic_dev && ic_per_member) ? ic_dev + (long long)m0 * plane : ic_dev;
     a.ic_stride = ic_per_member ? plane : 0;
     a.conc0 = ctx->C;
+    a.member_set = ctx->member_set_dev ? ctx->member_set_dev + m0 : nullptr;
+    a.set_steps = ctx->set_steps_dev;
     for (int vv = 0; vv < NVAR; ++vv) {
         double *base = out_base(out, vv);
         a.out[vv] = base ? base + (vv == V_H1 ? plane : 0) : nullptr;
@@ -609,7 +621,7 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     a.status = ctx->flags_dev;
     a.dbg = getenv("NESOSIM_ENS_DBG") ? atoi(getenv("NESOSIM_ENS_DBG")) : 0;
     a.timing = nullptr;
-    if (dbg_timing) {
+    if (dbg_timing && !ctx->member_set_dev) {
         CU(cudaMalloc(&a.timing, sizeof(long long) * ENS_NTIMER * ncl * cl));
         CU(cudaMemset(a.timing, 0, sizeof(long long) * ENS_NTIMER * ncl * cl));
     }
@@ -634,7 +646,7 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
             ctx->ens_kernel_launches++;
         }
     }
-    if (dbg_timing) {
+    if (dbg_timing && !ctx->member_set_dev) {
         std::vector<long long> h(ENS_NTIMER * ncl * cl);
         CU(cudaMemcpy(h.data(), a.timing, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(a.timing);
@@ -746,6 +758,8 @@ int nesosim_destroy(nesosim_ctx *ctx) {
     cudaFree(ctx->coef_dev);
     cudaFree(ctx->scratch);
     cudaFree(ctx->flags_dev);
+    cudaFree(ctx->member_set_dev);
+    cudaFree(ctx->set_steps_dev);
     cudaFree(ctx->hp.forcing);
     cudaFree(ctx->hp.ic);
     for (int i = 0; i < 2; ++i) {
@@ -771,6 +785,33 @@ int nesosim_set_forcing(nesosim_ctx *ctx, const double *precip_dev, const double
         CU(cudaMemcpy(ctx->rho_clim_host.data(), rho_clim_dev, sizeof(double) * ctx->cfg.num_days, cudaMemcpyDeviceToHost));
     }
     ctx->ens.derived_valid = false;
+    ctx->n_sets = 1;
+    cudaFree(ctx->member_set_dev);
+    cudaFree(ctx->set_steps_dev);
+    ctx->member_set_dev = ctx->set_steps_dev = nullptr;
+    return NESOSIM_OK;
+}
+
+int nesosim_set_forcing_sets(nesosim_ctx *ctx, int n_sets, const double *precip_dev, const double *conc_dev,
+                             const double *wind_dev, const double *drift_dev, const int32_t *member_set_host,
+                             const int32_t *set_days_host) {
+    if (!ctx || !member_set_host || !set_days_host || n_sets < 1) return fail(NESOSIM_ERR_ARG, "bad argument");
+    if (ctx->cfg.density_clim) return fail(NESOSIM_ERR_ARG, "forcing sets support densityType='variable' only");
+    int rc = nesosim_set_forcing(ctx, precip_dev, conc_dev, wind_dev, drift_dev, nullptr);
+    if (rc) return rc;
+    const int M = ctx->cfg.n_members, T = ctx->cfg.num_days;
+    std::vector<int> steps(n_sets);
+    for (int s = 0; s < n_sets; ++s) {
+        if (set_days_host[s] < 2 || set_days_host[s] > T) return fail(NESOSIM_ERR_ARG, "set_days must be in [2, num_days]");
+        steps[s] = set_days_host[s] - 1;
+    }
+    for (int m = 0; m < M; ++m)
+        if (member_set_host[m] < 0 || member_set_host[m] >= n_sets) return fail(NESOSIM_ERR_ARG, "member_set entry outside [0, n_sets)");
+    CU(cudaMalloc(&ctx->member_set_dev, sizeof(int) * M));
+    CU(cudaMalloc(&ctx->set_steps_dev, sizeof(int) * n_sets));
+    CU(cudaMemcpy(ctx->member_set_dev, member_set_host, sizeof(int) * M, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->set_steps_dev, steps.data(), sizeof(int) * n_sets, cudaMemcpyHostToDevice));
+    ctx->n_sets = n_sets;
     return NESOSIM_OK;
 }
 

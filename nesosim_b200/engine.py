@@ -119,6 +119,20 @@ class SnowBudgetEngine:
         _lib.check(self.lib.nesosim_set_forcing(self.handle, f[0].data_ptr(), f[1].data_ptr(), f[2].data_ptr(),
                                                 f[3].data_ptr(), None if rc is None else rc.data_ptr()))
 
+    def set_forcing_sets(self, precip, conc, wind, drift, member_set, set_days):
+        """A batch of independent seasons: forcing (S,T,ny,nx) / drift (S,T,2,ny,nx); member m runs season
+        ``member_set[m]`` for ``set_days[s]`` days (run_multiseason.py as one call; see nesosim_set_forcing_sets)."""
+        f = [self._dev(precip), self._dev(conc), self._dev(wind), self._dev(drift)]
+        S = f[0].shape[0]
+        assert tuple(f[0].shape) == (S, self.T, self.ny, self.nx) and tuple(f[3].shape) == (S, self.T, 2, self.ny, self.nx)
+        ms = np.ascontiguousarray(member_set, dtype=np.int32)
+        sd = np.ascontiguousarray(set_days, dtype=np.int32)
+        assert ms.shape == (self.M,) and sd.shape == (S,)
+        self._forcing = f
+        _lib.check(self.lib.nesosim_set_forcing_sets(self.handle, S, f[0].data_ptr(), f[1].data_ptr(), f[2].data_ptr(),
+                                                     f[3].data_ptr(), ms.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                     sd.ctypes.data_as(C.POINTER(C.c_int32))))
+
     def alloc_outputs(self, names=_lib.OUTPUT_NAMES, zero=False):
         """Device tensors shaped like genEmptyArrays (NESOSIM.py:350-376) with a leading member axis."""
         torch = _torch()

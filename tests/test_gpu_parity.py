@@ -310,6 +310,41 @@ def test_ensemble_kernel_with_drift_defined_over_land(cuda):
         eng.close()
 
 
+@pytest.mark.parametrize("path", PATHS)
+def test_batch_of_seasons_with_their_own_forcing_and_length(cuda, path):
+    """run_multiseason.py as one native call: three seasons of different length stacked in one context, five members
+    spread over them; every member must equal the oracle run on its own season."""
+    from nesosim_b200.engine import SnowBudgetEngine
+    mask = S.region_mask(dx=100000)
+    T, days = 12, [12, 9, 11]
+    seasons = [S.make_season(mask, T, seed=50 + i) for i in range(3)]
+    stack = {k: np.stack([f[k] for f in seasons]) for k in ("precip", "conc", "wind", "drift")}
+    member_set = [0, 1, 2, 1, 0]
+    M = len(member_set)
+    params = S.ensemble_params(M, seed=51)
+    ic = S.make_ic(mask, seed=52)[None] * np.linspace(0.5, 2.0, M)[:, None, None]
+    eng = SnowBudgetEngine(mask, T, 100000, n_members=M, atmlossInc=1)
+    eng.set_path(path)
+    eng.set_forcing_sets(stack["precip"], stack["conc"], stack["wind"], stack["drift"], member_set, days)
+    out = eng.alloc_outputs()
+    for t in out.values():
+        t.fill_(-5.0)                                  # slots past a member's last day must stay untouched
+    out = {k: v.cpu().numpy() for k, v in eng.run_season(params, ic, out).items()}
+    assert eng.last_path() == path
+    for m in range(M):
+        s_ = member_set[m]
+        d = days[s_]
+        f = {k: v[:d] for k, v in seasons[s_].items()}
+        ref = O.run_season(f, ic[m], mask, 100000, oracle_params(params[m]), O.Flags(atmlossInc=1))
+        for name in out:
+            assert_parity(out[name][m][:d], ref[name], "%s[%d] %s" % (name, m, path))
+            assert (out[name][m][d:] == -5.0).all(), name
+    eng.set_forcing(seasons[0]["precip"], seasons[0]["conc"], seasons[0]["wind"], seasons[0]["drift"])   # back to one season
+    again = {k: v.cpu().numpy() for k, v in eng.run_season(params, ic).items()}
+    ref = O.run_season(seasons[0], ic[1], mask, 100000, oracle_params(params[1]), O.Flags(atmlossInc=1))
+    assert_parity(again["snowDepths"][1], ref["snowDepths"], "single season after a batch")
+
+
 def test_step_day_matches_calc_budget(cuda):
     """nesosim_step_day has calcBudget's in-place contract (NESOSIM.py:224-347)."""
     from nesosim_b200.engine import SnowBudgetEngine
