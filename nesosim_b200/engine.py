@@ -29,10 +29,10 @@ def gaussian_kernel_3x3(stddev=1.0, size=3):
     return (1. / (2 * np.pi * s * s)) * np.exp(-((a * x ** 2) + (0.0 * x * y) + (c * y ** 2)))
 
 
-def conv_constants(variant="post_divide"):
+def conv_constants(variant="post_divide", stddev=1.0):
     """(weights[9], divisor) handed to the device.  ``post_divide`` = astropy 3.1-4.x order (raw kernel, then
     ``result /= kernel.sum()``); ``pre_normalised`` = kernel divided by its sum first (divisor 1)."""
-    g = gaussian_kernel_3x3()
+    g = gaussian_kernel_3x3(stddev)
     ksum = g.sum()
     if variant == "post_divide":
         return g.reshape(-1).copy(), float(ksum)
@@ -261,13 +261,14 @@ def _cur_stream(device=0):
     return C.c_void_p(_torch().cuda.current_stream(device).cuda_stream)
 
 
-def smooth(arr, conv_variant="post_divide", device=0):
-    """``smooth_snow`` (NESOSIM.py:170-187) on the GPU; numpy in, numpy out (new array, as the reference)."""
+def smooth(arr, conv_variant="post_divide", device=0, stddev=1.0):
+    """``smooth_snow`` (NESOSIM.py:170-187) on the GPU; numpy in, numpy out (new array, as the reference).
+    ``stddev`` is the Gaussian's sigma (1 in smooth_snow; ``sigma_factor`` in utils.int_smooth_drifts_v2/v3)."""
     torch = _torch()
     lib = _lib.load()
     a = _cuda(np.asarray(arr, dtype=np.float64), device)
     out = torch.empty_like(a)
-    w, div = conv_constants(conv_variant)
+    w, div = conv_constants(conv_variant, stddev)
     wc = (C.c_double * 9)(*w.tolist())
     _lib.check(lib.nesosim_smooth(a.data_ptr(), out.data_ptr(), a.shape[0], a.shape[1], wc, div, _cur_stream(device)))
     return out.cpu().numpy()
@@ -347,4 +348,20 @@ def final_products(snowDepths, density, iceConc, precip, wind, ice_conc_mask=0.5
                                           out["snow_depth"].data_ptr(), out["snow_volume"].data_ptr(),
                                           out["snow_density"].data_ptr(), out["ice_concentration"].data_ptr(),
                                           out["precipitation"].data_ptr(), out["wind_speed"].data_ptr(), _cur_stream(device)))
+    return out
+
+
+def smooth_gridded_drift(driftFGx, driftFGy, sigma_factor=1, x_size_val=3, conv_variant="post_divide", device=0):
+    """The smoothing tail of the reference's offline drift regridders ``utils.int_smooth_drifts_v2/v3``
+    (utils.py:283-291, 328-336): ``convolve(component, Gaussian2DKernel(sigma_factor, x_size=3))`` -- here NaNs DO reach
+    the convolution, so astropy's NaN-interpolating branch runs -- then masked where the gridded input was NaN.
+    Returns the (2, nx, ny) masked array the reference returns.  (The Delaunay / griddata interpolation before it
+    stays on the CPU.)"""
+    import numpy.ma as ma
+    if int(x_size_val) != 3:
+        raise ValueError("the native smoother is the reference's 3x3 kernel (x_size_val=3)")
+    out = ma.masked_all((2,) + tuple(np.shape(driftFGx)))
+    for i, comp in enumerate((driftFGx, driftFGy)):
+        comp = np.asarray(comp, dtype=np.float64)
+        out[i] = ma.masked_where(np.isnan(comp), smooth(comp, conv_variant, device, stddev=float(sigma_factor)))
     return out

@@ -449,6 +449,51 @@ def test_smooth_plain_and_nan_branch(cuda):
     assert_parity(E.smooth(b, "pre_normalised"), convolve_fill0(b, g, "pre_normalised"), "pre-normalised")
 
 
+def test_drift_smoothing_tail_of_the_offline_regridders(cuda):
+    """utils.int_smooth_drifts_v2/v3 (utils.py:283-291): sigma 0.5 and 1 kernels, NaNs present (interpolating branch),
+    result masked where the gridded input was NaN."""
+    from nesosim_b200 import engine as E
+    rng = np.random.default_rng(4)
+    gx = 0.1 * rng.standard_normal((41, 37))
+    gy = 0.1 * rng.standard_normal((41, 37))
+    gx[:6, :] = np.nan
+    gy[:6, :] = np.nan                  # outside the convex hull of the source grid
+    gx[20:24, 10:14] = np.nan
+    gy[30, 30] = np.nan
+    for sigma in (1, 0.5):
+        got = E.smooth_gridded_drift(gx, gy, sigma_factor=sigma)
+        k = gaussian2d_kernel(x_stddev=sigma, y_stddev=sigma, x_size=3, y_size=3)
+        for i, comp in enumerate((gx, gy)):
+            ref = np.ma.masked_where(np.isnan(comp), convolve_fill0(comp, k))
+            assert np.array_equal(np.ma.getmaskarray(got[i]), np.ma.getmaskarray(ref))
+            assert np.array_equal(got[i].compressed(), ref.compressed())
+
+
+def test_ensemble_driver_reduces_on_the_device(cuda):
+    """N3: per-member misfit against point observations, only snowDepths computed, nothing but M scalars leaves."""
+    from nesosim_b200 import ensemble as ENS
+    mask = S.region_mask(dx=100000)
+    T, M = 10, 6
+    forcing = S.make_season(mask, T, seed=61)
+    ic = S.make_ic(mask, seed=61) * 3
+    params = S.ensemble_params(M, seed=61)
+    rng = np.random.default_rng(61)
+    ocean = np.argwhere((mask <= 10) & (mask >= 1))
+    pick = ocean[rng.choice(len(ocean), 200, replace=False)]
+    day = rng.integers(1, T, 200)
+    obs = (day, pick[:, 0], pick[:, 1], 0.2 * rng.random(200))
+    mis, used = ENS.run_ensemble(mask, forcing, ic, params, 100000, obs, atmlossInc=1)
+    for m in range(M):
+        ref = O.run_season(forcing, ic, mask, 100000, oracle_params(params[m]), O.Flags(atmlossInc=1))
+        with np.errstate(all="ignore"):
+            model = (ref["snowDepths"][day, 0, pick[:, 0], pick[:, 1]] + ref["snowDepths"][day, 1, pick[:, 0], pick[:, 1]]) \
+                / forcing["conc"][day, pick[:, 0], pick[:, 1]]
+        d = model - obs[3]
+        ok = np.isfinite(d)
+        assert used[m] == ok.sum() and used[m] > 20
+        assert np.isclose(mis[m], np.sum(d[ok] ** 2), rtol=1e-12)
+
+
 def test_op_dynamics(cuda):
     from nesosim_b200 import engine as E
     rng = np.random.default_rng(1)
