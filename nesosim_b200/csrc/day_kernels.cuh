@@ -44,13 +44,12 @@ constexpr int TX = 32;
 constexpr int TY = 16;
 constexpr int DAY_THREADS = 256;
 
-__global__ void __launch_bounds__(DAY_THREADS)
-day_step_kernel(const __grid_constant__ DayArgs a) {
-    __shared__ double s_h[2][TY + 4][TX + 4];
-    __shared__ double s_ut[TY + 4][TX + 4];
-    __shared__ double s_vt[TY + 4][TX + 4];
-    __shared__ double s_raw[4][TY + 2][TX + 2];   // adv0, adv1, div0, div1 after the NaN->0 fill
-
+// INTERIOR: the tile with its two-cell halo lies inside the grid and none of its raw-dynamics cells is a grid-edge
+// cell, so there are no bounds tests, every difference is centred and the divisor is a launch constant (the
+// overwhelming majority of the CTAs on the 25 km and 5 km grids).
+template <bool INTERIOR>
+__device__ __forceinline__ void day_step_body(const DayArgs &a, double (&s_h)[2][TY + 4][TX + 4], double (&s_ut)[TY + 4][TX + 4],
+                                              double (&s_vt)[TY + 4][TX + 4], double (&s_raw)[4][TY + 2][TX + 2]) {
     const int m = blockIdx.z;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
     const int tid = threadIdx.x;
@@ -76,7 +75,7 @@ day_step_kernel(const __grid_constant__ DayArgs a) {
         pf_land[rr] = true;
 #pragma unroll
         for (int v = 0; v < 9; ++v) pf_prev[rr][v] = 0.0;
-        if (pgx < nx && gy < ny) {
+        if (INTERIOR || (pgx < nx && gy < ny)) {
             const long long o = (long long)gy * nx + pgx;
             pf_P[rr] = __ldg(aP + o);
             pf_C[rr] = __ldg(aC + o);
@@ -92,7 +91,7 @@ day_step_kernel(const __grid_constant__ DayArgs a) {
             const int r = i / (TX + 4), c = i - r * (TX + 4);
             const int gy = y0 + r - 2, gx = x0 + c - 2;
             double h0 = 0.0, h1 = 0.0, ut = 0.0, vt = 0.0;
-            if (gy >= 0 && gy < ny && gx >= 0 && gx < nx) {
+            if (INTERIOR || (gy >= 0 && gy < ny && gx >= 0 && gx < nx)) {
                 const long long o = (long long)gy * nx + gx;
                 h0 = h0p[o];
                 h1 = h1p[o];
@@ -109,16 +108,20 @@ day_step_kernel(const __grid_constant__ DayArgs a) {
             const int r = i / (TX + 2), c = i - r * (TX + 2);
             const int gy = y0 + r - 1, gx = x0 + c - 1;
             double adv0 = 0.0, adv1 = 0.0, div0 = 0.0, div1 = 0.0;   // zero padding of convolve(boundary='fill')
-            if (gy >= 0 && gy < ny && gx >= 0 && gx < nx) {
+            if (INTERIOR || (gy >= 0 && gy < ny && gx >= 0 && gx < nx)) {
                 const int sr = r + 1, sc = c + 1;
                 const double ut = s_ut[sr][sc], vt = s_vt[sr][sc];
-                const double gxu = gradient1d(s_ut[sr][sc - 1], ut, s_ut[sr][sc + 1], gx, nx, a.g);
-                const double gyv = gradient1d(s_vt[sr - 1][sc], vt, s_vt[sr + 1][sc], gy, ny, a.g);
+                // centred difference with the constant divisor 2.*dx where no cell of the tile is a grid-edge cell
+                auto grad = [&](double fm, double fc, double fp, int idx, int n) {
+                    return INTERIOR ? div_const(sub(fp, fm), a.g.two_dx) : gradient1d(fm, fc, fp, idx, n, a.g);
+                };
+                const double gxu = grad(s_ut[sr][sc - 1], ut, s_ut[sr][sc + 1], gx, nx);
+                const double gyv = grad(s_vt[sr - 1][sc], vt, s_vt[sr + 1][sc], gy, ny);
 #pragma unroll
                 for (int l = 0; l < 2; ++l) {
                     const double h = s_h[l][sr][sc];
-                    const double gxh = gradient1d(s_h[l][sr][sc - 1], h, s_h[l][sr][sc + 1], gx, nx, a.g);
-                    const double gyh = gradient1d(s_h[l][sr - 1][sc], h, s_h[l][sr + 1][sc], gy, ny, a.g);
+                    const double gxh = grad(s_h[l][sr][sc - 1], h, s_h[l][sr][sc + 1], gx, nx);
+                    const double gyh = grad(s_h[l][sr - 1][sc], h, s_h[l][sr + 1][sc], gy, ny);
                     const double dv = zero_if_nonfinite(div_term(h, gxu, gyv));
                     const double ad = zero_if_nonfinite(adv_term(ut, vt, gxh, gyh));
                     if (l == 0) { adv0 = ad; div0 = dv; } else { adv1 = ad; div1 = dv; }
@@ -135,12 +138,12 @@ day_step_kernel(const __grid_constant__ DayArgs a) {
     const MemberCoef mc = a.coef[m];
     const int tx = tid & (TX - 1);
     const int gx = x0 + tx;
-    if (gx >= nx) return;
+    if (!INTERIOR && gx >= nx) return;
 #pragma unroll
     for (int rr = 0; rr < TY / (DAY_THREADS / TX); ++rr) {
         const int ty = (tid / TX) + rr * (DAY_THREADS / TX);
         const int gy = y0 + ty;
-        if (gy >= ny) break;
+        if (!INTERIOR && gy >= ny) break;
         const long long o = (long long)gy * nx + gx;
         const bool land = pf_land[rr];
 
@@ -195,6 +198,18 @@ day_step_kernel(const __grid_constant__ DayArgs a) {
                                      : density_variable(h0n, h1n, land, a.k);
         store(V_DENS, rho);
     }
+}
+
+__global__ void __launch_bounds__(DAY_THREADS)
+day_step_kernel(const __grid_constant__ DayArgs a) {
+    __shared__ double s_h[2][TY + 4][TX + 4];
+    __shared__ double s_ut[TY + 4][TX + 4];
+    __shared__ double s_vt[TY + 4][TX + 4];
+    __shared__ double s_raw[4][TY + 2][TX + 2];   // adv0, adv1, div0, div1 after the NaN->0 fill
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const bool interior = x0 >= 2 && y0 >= 2 && x0 + TX + 2 <= a.nx && y0 + TY + 2 <= a.ny;
+    if (interior) day_step_body<true>(a, s_h, s_ut, s_vt, s_raw);
+    else day_step_body<false>(a, s_h, s_ut, s_vt, s_raw);
 }
 
 // Slot 0 of every array: zeros (genEmptyArrays, NESOSIM.py:350-376) and the initial-condition split of main
