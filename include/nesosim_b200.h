@@ -170,6 +170,33 @@ int nesosim_final_products(const double *depths_dev, const double *density_dev, 
 int nesosim_set_path(nesosim_ctx *ctx, int path);
 int nesosim_last_path(const nesosim_ctx *ctx);
 
+/* ---- Row-strip domain decomposition over peer memory (grids too large for one GPU: the 5 km case; the reference
+ * has no counterpart -- its grid is one numpy array -- so the contract is that of calcBudget on the whole grid).
+ * A context created on rows [lo-2, hi+2) of the full grid (mask and forcing sliced the same way; 2 = radius of
+ * np.gradient followed by the 3x3 convolution, NESOSIM.py:204-213,184-185; no ghost rows at the global edges) is one
+ * STRIP.  After nesosim_strip_setup + nesosim_strip_connect*, nesosim_run_season on the general path advances the
+ * strip with ONE launch per day and nothing in between: the day kernel itself stores the new depths of its first /
+ * last two owned rows into the neighbouring strip's mailbox (peer memory over NVLink when the neighbour is another
+ * GPU) and raises that strip's flag; the next day's boundary CTAs wait for their own flag and take the ghost rows
+ * from the mailbox.  The owned rows of every output come out identical to a single-context run of the whole grid;
+ * the ghost rows of the outputs are scratch.  n_members must be 1.  All strips must run the same sequence of
+ * nesosim_run_season calls (whole seasons, or the same first_step/num_steps pieces), and every strip's previous
+ * season must have completed on its stream before any strip starts the next one (one barrier between seasons).
+ * A neighbour that never delivers does not hang the GPU: waits give up after a time-out (default 5 s) and
+ * nesosim_strip_status reports it. */
+#define NESOSIM_IPC_HANDLE_BYTES 64
+int nesosim_strip_setup(nesosim_ctx *ctx, int has_up_neighbour, int has_down_neighbour);
+/* the strip's exchange block: as a cudaIpcMemHandle_t (64 bytes, for a neighbour in another process) ... */
+int nesosim_strip_export(nesosim_ctx *ctx, void *handle64);
+/* ... or as a device pointer (for a neighbour in the same process; other device: peer access must be enabled) */
+int nesosim_strip_block(nesosim_ctx *ctx, void **block_dev, int64_t *bytes);
+/* attach the neighbours' blocks (NULL where there is no neighbour) */
+int nesosim_strip_connect(nesosim_ctx *ctx, const void *up_handle64, const void *down_handle64);
+int nesosim_strip_connect_local(nesosim_ctx *ctx, void *up_block_dev, void *down_block_dev);
+/* *timed_out = 1 if any wait for a neighbour gave up since nesosim_strip_setup (synchronous device read) */
+int nesosim_strip_status(nesosim_ctx *ctx, int *timed_out);
+int nesosim_strip_set_timeout(nesosim_ctx *ctx, double seconds);
+
 /* Diagnostics for the exact constant-division path used for /dx, /(2.*dx), /rho and /kernel.sum()
  * (cell_math.cuh div_const): whether the 3-operation path was proven exact for divisor c, and a host
  * replica of the device routine (same branches, std::fma) so CPU tests can compare it with x / c. */

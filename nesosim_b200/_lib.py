@@ -74,6 +74,13 @@ _SIGNATURES = {
     "nesosim_launch_count": (C.c_int64, [C.c_void_p]),
     "nesosim_rerun_count": (C.c_int64, [C.c_void_p]),
     "nesosim_season_kernel_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "nesosim_strip_setup": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "nesosim_strip_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nesosim_strip_block": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "nesosim_strip_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nesosim_strip_connect_local": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nesosim_strip_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "nesosim_strip_set_timeout": (C.c_int, [C.c_void_p, C.c_double]),
     "nesosim_set_path": (C.c_int, [C.c_void_p, C.c_int]),
     "nesosim_last_path": (C.c_int, [C.c_void_p]),
     "nesosim_const_div_is_fast": (C.c_int, [C.c_double]),

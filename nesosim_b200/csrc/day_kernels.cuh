@@ -44,12 +44,42 @@ constexpr int TX = 32;
 constexpr int TY = 16;
 constexpr int DAY_THREADS = 256;
 
+// Row-strip domain decomposition over peer memory (SURVEY.md §8e "Space"; host side: nesosim_strip_* in the ABI).
+// This context's grid is one strip of a larger grid, extended by STRIP_GHOST ghost rows towards each neighbouring
+// strip.  Only the two depth layers of the ghost rows are ever needed from a neighbour (fused stencil radius 2 of
+// calcDynamics + smooth_snow, NESOSIM.py:204-213,184-185), so every strip owns two "mailboxes" (one per side,
+// [parity][layer][STRIP_GHOST][nx] doubles, parity = time slot & 1) that its neighbours fill: the day kernel stores the
+// new depths of its first / last STRIP_GHOST OWNED rows straight into the neighbour's mailbox (peer memory: NVLink
+// between GPUs, plain global memory between strips of one GPU), and the last boundary CTA to finish publishes the
+// slot number in the neighbour's flag.  The next day's boundary CTAs wait for their own flag and read the ghost rows
+// from the mailbox instead of the (stale) ghost rows of their output array.  No other kernel, copy or collective runs
+// between two days; CTAs away from the strip boundary never look at any of this.
+constexpr int STRIP_GHOST = 2;
+
+struct StripLink {
+    int has_up, has_dn;                       // a neighbouring strip above (rows < 0) / below (rows >= ny)
+    int use_mail;                             // 0 on the first step of a season: ghost rows of slot 0 come from the IC
+    const double *mail_top, *mail_bot;        // this strip's mailboxes (written by the neighbours)
+    double *peer_up_mail, *peer_dn_mail;      // up neighbour's BOTTOM mailbox, down neighbour's TOP mailbox
+    const unsigned long long *flag_top, *flag_bot;   // latest slot the neighbour has delivered (epoch in the high word)
+    unsigned long long *peer_up_flag, *peer_dn_flag;
+    unsigned int *cnt_top, *cnt_bot;          // boundary CTAs done so far (this launch)
+    unsigned int expect_top, expect_bot;
+    int *timed_out;                           // set when a flag did not arrive within the time limit
+    unsigned long long base;                  // epoch << 32: flags only ever grow
+    unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ bool strip_top_cta(int y0) { return y0 - 2 < 2 * STRIP_GHOST; }
+__device__ __forceinline__ bool strip_bot_cta(int y0, int ny) { return y0 + TY + 2 > ny - 2 * STRIP_GHOST; }
+
 // INTERIOR: the tile with its two-cell halo lies inside the grid and none of its raw-dynamics cells is a grid-edge
 // cell, so there are no bounds tests, every difference is centred and the divisor is a launch constant (the
 // overwhelming majority of the CTAs on the 25 km and 5 km grids).
-template <bool INTERIOR>
+template <bool INTERIOR, bool STRIP = false>
 __device__ __forceinline__ void day_step_body(const DayArgs &a, double (&s_h)[2][TY + 4][TX + 4], double (&s_ut)[TY + 4][TX + 4],
-                                              double (&s_vt)[TY + 4][TX + 4], double (&s_raw)[4][TY + 2][TX + 2]) {
+                                              double (&s_vt)[TY + 4][TX + 4], double (&s_raw)[4][TY + 2][TX + 2],
+                                              const StripLink *sl = nullptr) {
     const int m = blockIdx.z;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
     const int tid = threadIdx.x;
@@ -93,8 +123,20 @@ __device__ __forceinline__ void day_step_body(const DayArgs &a, double (&s_h)[2]
             double h0 = 0.0, h1 = 0.0, ut = 0.0, vt = 0.0;
             if (INTERIOR || (gy >= 0 && gy < ny && gx >= 0 && gx < nx)) {
                 const long long o = (long long)gy * nx + gx;
-                h0 = h0p[o];
-                h1 = h1p[o];
+                const double *mail = nullptr;      // ghost row of a neighbouring strip: depths come from the mailbox
+                int mrow = 0;
+                if (STRIP && sl->use_mail) {
+                    if (sl->has_up && gy < STRIP_GHOST) { mail = sl->mail_top; mrow = gy; }
+                    else if (sl->has_dn && gy >= ny - STRIP_GHOST) { mail = sl->mail_bot; mrow = gy - (ny - STRIP_GHOST); }
+                }
+                if (STRIP && mail) {
+                    const long long mo = ((long long)(a.x & 1) * 2 * STRIP_GHOST + mrow) * nx + gx;
+                    h0 = __ldcg(mail + mo);
+                    h1 = __ldcg(mail + mo + (long long)STRIP_GHOST * nx);
+                } else {
+                    h0 = h0p[o];
+                    h1 = h1p[o];
+                }
                 ut = mul(__ldg(aU + o), a.k.deltaT);   // driftGday[0]*deltaT (NESOSIM.py:204,210)
                 vt = mul(__ldg(aV + o), a.k.deltaT);
             }
@@ -194,6 +236,19 @@ __device__ __forceinline__ void day_step_body(const DayArgs &a, double (&s_h)[2]
         h1n = mask_nan(h1n, land, true);
         store(V_H0, h0n);
         store(V_H1, h1n);
+        if (STRIP) {      // first / last owned rows -> the neighbour's mailbox for slot x+1
+            const long long par = (long long)((a.x + 1) & 1) * 2 * STRIP_GHOST;
+            if (sl->has_up && gy >= STRIP_GHOST && gy < 2 * STRIP_GHOST) {
+                const long long mo = (par + (gy - STRIP_GHOST)) * nx + gx;
+                sl->peer_up_mail[mo] = h0n;
+                sl->peer_up_mail[mo + (long long)STRIP_GHOST * nx] = h1n;
+            }
+            if (sl->has_dn && gy >= ny - 2 * STRIP_GHOST && gy < ny - STRIP_GHOST) {
+                const long long mo = (par + (gy - (ny - 2 * STRIP_GHOST))) * nx + gx;
+                sl->peer_dn_mail[mo] = h0n;
+                sl->peer_dn_mail[mo + (long long)STRIP_GHOST * nx] = h1n;
+            }
+        }
         const double rho = a.sw.clim ? density_clim(a.rho_new.c, h0n, h1n, C, land, a.k)
                                      : density_variable(h0n, h1n, land, a.k);
         store(V_DENS, rho);
@@ -210,6 +265,68 @@ day_step_kernel(const __grid_constant__ DayArgs a) {
     const bool interior = x0 >= 2 && y0 >= 2 && x0 + TX + 2 <= a.nx && y0 + TY + 2 <= a.ny;
     if (interior) day_step_body<true>(a, s_h, s_ut, s_vt, s_raw);
     else day_step_body<false>(a, s_h, s_ut, s_vt, s_raw);
+}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Wait until *flag >= want (system-scope acquire: the neighbour may be another GPU).  Bounded: a strip whose neighbour
+// never delivers raises `timed_out` and carries on with whatever the mailbox holds; the host reports the error.
+__device__ __forceinline__ void strip_wait(const unsigned long long *flag, unsigned long long want, const StripLink &s) {
+    if (*(volatile int *)s.timed_out) return;
+    const unsigned long long t0 = globaltimer_ns();
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+        if (v >= want) return;
+        if (globaltimer_ns() - t0 > s.timeout_ns) { atomicExch(s.timed_out, 1); return; }
+        __nanosleep(200);
+    }
+}
+
+__device__ __forceinline__ void strip_signal(unsigned int *cnt, unsigned int expect, unsigned long long *peer_flag,
+                                             unsigned long long value) {
+    if (atomicAdd(cnt, 1u) == expect - 1u) {     // every boundary CTA of this side has fenced its mailbox stores
+        atomicExch(cnt, 0u);
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flag), "l"(value) : "memory");
+    }
+}
+
+// The day step of one strip (M = 1, dynamics on).  CTAs whose tile (with its halo) stays clear of the ghost rows and
+// of the rows a neighbour needs run exactly the code of day_step_kernel.
+__global__ void __launch_bounds__(DAY_THREADS)
+day_step_strip_kernel(const __grid_constant__ DayArgs a, const __grid_constant__ StripLink s) {
+    __shared__ double s_h[2][TY + 4][TX + 4];
+    __shared__ double s_ut[TY + 4][TX + 4];
+    __shared__ double s_vt[TY + 4][TX + 4];
+    __shared__ double s_raw[4][TY + 2][TX + 2];
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const bool top = s.has_up && strip_top_cta(y0), bot = s.has_dn && strip_bot_cta(y0, a.ny);
+    if (!top && !bot) {
+        const bool interior = x0 >= 2 && y0 >= 2 && x0 + TX + 2 <= a.nx && y0 + TY + 2 <= a.ny;
+        if (interior) day_step_body<true>(a, s_h, s_ut, s_vt, s_raw);
+        else day_step_body<false>(a, s_h, s_ut, s_vt, s_raw);
+        return;
+    }
+    if (s.use_mail) {
+        if (threadIdx.x == 0) {
+            if (top) strip_wait(s.flag_top, s.base + (unsigned long long)a.x, s);
+            if (bot) strip_wait(s.flag_bot, s.base + (unsigned long long)a.x, s);
+        }
+        __syncthreads();
+    }
+    day_step_body<false, true>(a, s_h, s_ut, s_vt, s_raw, &s);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long v = s.base + (unsigned long long)a.x + 1ull;
+        if (top) strip_signal(s.cnt_top, s.expect_top, s.peer_up_flag, v);
+        if (bot) strip_signal(s.cnt_bot, s.expect_bot, s.peer_dn_flag, v);
+    }
 }
 
 // Slot 0 of every array: zeros (genEmptyArrays, NESOSIM.py:350-376) and the initial-condition split of main

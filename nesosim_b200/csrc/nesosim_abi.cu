@@ -165,6 +165,16 @@ struct nesosim_ctx {
     long long ens_reruns = 0;
     int path = 0;                   // 0 auto, 1 general per-day launches, 2 season-resident ensemble kernel
     int last_path = 0;              // which path the last run_season used (1 or 2)
+    // row-strip domain decomposition over peer memory (nesosim_strip_*; StripLink in day_kernels.cuh)
+    struct {
+        bool on = false;
+        int has_up = 0, has_dn = 0;
+        char *block = nullptr;      // [mail_top | mail_bot | flags[2] | cnt[2] | timed_out], one cudaMalloc (IPC-exportable)
+        char *peer_up = nullptr, *peer_dn = nullptr;   // the neighbours' blocks (same layout: every strip has this nx)
+        bool ipc_up = false, ipc_dn = false;           // opened with cudaIpcOpenMemHandle (to be closed)
+        unsigned long long epoch = 0;
+        double timeout_s = 5.0;
+    } strip;
 };
 
 namespace {
@@ -248,8 +258,56 @@ int check_outputs(const nesosim_ctx *ctx, const nesosim_outputs *o) {
     return NESOSIM_OK;
 }
 
+// Layout of a strip's exchange block (nesosim_strip_setup): two mailboxes of [parity 2][layer 2][STRIP_GHOST][nx]
+// doubles, then the two flags, the two CTA counters and the time-out mark.
+void strip_release(nesosim_ctx *ctx) {
+    if (ctx->strip.ipc_up && ctx->strip.peer_up) cudaIpcCloseMemHandle(ctx->strip.peer_up);
+    if (ctx->strip.ipc_dn && ctx->strip.peer_dn) cudaIpcCloseMemHandle(ctx->strip.peer_dn);
+    cudaFree(ctx->strip.block);
+    ctx->strip.block = ctx->strip.peer_up = ctx->strip.peer_dn = nullptr;
+    ctx->strip.ipc_up = ctx->strip.ipc_dn = false;
+    ctx->strip.on = false;
+}
+
+size_t strip_mail_bytes(int nx) { return (size_t)2 * 2 * STRIP_GHOST * nx * sizeof(double); }
+size_t strip_block_bytes(int nx) { return 2 * strip_mail_bytes(nx) + 2 * sizeof(unsigned long long) + 4 * sizeof(unsigned int); }
+
+void strip_link(const nesosim_ctx *ctx, int x, dim3 grid, StripLink *s) {
+    const int nx = ctx->cfg.nx, ny = ctx->cfg.ny;
+    const size_t mb = strip_mail_bytes(nx);
+    auto mail = [&](char *blk, int side) { return (double *)(blk + side * mb); };
+    auto flag = [&](char *blk, int side) { return (unsigned long long *)(blk + 2 * mb) + side; };
+    char *blk = ctx->strip.block;
+    unsigned int *cnt = (unsigned int *)(blk + 2 * mb + 2 * sizeof(unsigned long long));
+    s->has_up = ctx->strip.has_up;
+    s->has_dn = ctx->strip.has_dn;
+    s->use_mail = x > 0;
+    s->mail_top = mail(blk, 0);
+    s->mail_bot = mail(blk, 1);
+    s->flag_top = flag(blk, 0);
+    s->flag_bot = flag(blk, 1);
+    s->peer_up_mail = ctx->strip.peer_up ? mail(ctx->strip.peer_up, 1) : nullptr;
+    s->peer_up_flag = ctx->strip.peer_up ? flag(ctx->strip.peer_up, 1) : nullptr;
+    s->peer_dn_mail = ctx->strip.peer_dn ? mail(ctx->strip.peer_dn, 0) : nullptr;
+    s->peer_dn_flag = ctx->strip.peer_dn ? flag(ctx->strip.peer_dn, 0) : nullptr;
+    s->cnt_top = cnt;
+    s->cnt_bot = cnt + 1;
+    s->timed_out = (int *)(cnt + 2);
+    unsigned top_rows = 0, bot_rows = 0;         // tile rows in each boundary set: same predicates as the kernel
+    for (unsigned by = 0; by < grid.y; ++by) {
+        const int y0 = (int)by * TY;
+        if (y0 - 2 < 2 * STRIP_GHOST) ++top_rows;
+        if (y0 + TY + 2 > ny - 2 * STRIP_GHOST) ++bot_rows;
+    }
+    s->expect_top = top_rows * grid.x;
+    s->expect_bot = bot_rows * grid.x;
+    s->base = ctx->strip.epoch << 32;
+    s->timeout_ns = (unsigned long long)(ctx->strip.timeout_s * 1e9);
+}
+
 int launch_day(nesosim_ctx *ctx, int x, const double *P, const double *C, const double *W, const double *U,
-               const double *V, double rho_new, const nesosim_outputs *o, int m0, int mcount, cudaStream_t st) {
+               const double *V, double rho_new, const nesosim_outputs *o, int m0, int mcount, cudaStream_t st,
+               bool strip_step = false) {
     DayArgs a;
     a.ny = ctx->cfg.ny;
     a.nx = ctx->cfg.nx;
@@ -277,7 +335,13 @@ int launch_day(nesosim_ctx *ctx, int x, const double *P, const double *C, const 
     a.set_stride = (long long)ctx->cfg.num_days * ctx->plane;
     a.x = x;
     dim3 grid((a.nx + TX - 1) / TX, (a.ny + TY - 1) / TY, mcount);
-    day_step_kernel<<<grid, DAY_THREADS, 0, st>>>(a);
+    if (strip_step && ctx->strip.on && a.sw.dynamics && (ctx->strip.has_up || ctx->strip.has_dn)) {
+        StripLink s;
+        strip_link(ctx, x, grid, &s);
+        day_step_strip_kernel<<<grid, DAY_THREADS, 0, st>>>(a, s);
+    } else {
+        day_step_kernel<<<grid, DAY_THREADS, 0, st>>>(a);
+    }
     ctx->launches++;
     CU(cudaGetLastError());
     return NESOSIM_OK;
@@ -529,6 +593,7 @@ int build_strip_tables(nesosim_ctx *ctx) {
 // shared memory, 16-byte aligned planes for the bulk stores.
 bool ensemble_eligible(nesosim_ctx *ctx, int first_step, int num_steps, const nesosim_outputs *out, const char **why) {
     const nesosim_config &c = ctx->cfg;
+    if (ctx->strip.on) { *why = "strip of a decomposed grid"; return false; }
     if (c.nx > ENS_MAX_NX) { *why = "nx > 96"; return false; }
     if (c.nx < 3) { *why = "nx < 3"; return false; }
     if (c.ny < 2 * ENS_MIN_ROWS) { *why = "ny < 8"; return false; }
@@ -689,11 +754,16 @@ int run_members(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, const
     if (any_missing(out) && (rc = ensure_scratch(ctx))) return rc;
     if (first_step == 0 && (rc = launch_init(ctx, ic_dev, ic_per_member, ctx->C, out, m0, mcount, st))) return rc;
     const long long plane = ctx->plane;
+    if (ctx->strip.on) {
+        if ((ctx->strip.has_up && !ctx->strip.peer_up) || (ctx->strip.has_dn && !ctx->strip.peer_dn))
+            return fail(NESOSIM_ERR_STATE, "strip neighbours are not connected (nesosim_strip_connect*)");
+        if (first_step == 0) ctx->strip.epoch++;       // every strip counts its seasons the same way: flags only grow
+    }
     for (int x = first_step; x < first_step + num_steps; ++x) {
         const double rho = ctx->cfg.density_clim ? ctx->rho_clim_host[x] : ctx->cfg.snowDensityFresh;
         rc = launch_day(ctx, x, ctx->P + x * plane, ctx->C + x * plane, ctx->W + x * plane,
                         ctx->UV + (long long)x * 2 * plane, ctx->UV + ((long long)x * 2 + 1) * plane, rho, out,
-                        m0, mcount, st);
+                        m0, mcount, st, true);
         if (rc) return rc;
     }
     return NESOSIM_OK;
@@ -754,6 +824,7 @@ int nesosim_destroy(nesosim_ctx *ctx) {
     ensemble_release(ctx->ens);
     for (int i = 0; i < 2; ++i)
         if (ctx->ens_ev[i]) cudaEventDestroy(ctx->ens_ev[i]);
+    strip_release(ctx);
     cudaFree(ctx->mask_dev);
     cudaFree(ctx->coef_dev);
     cudaFree(ctx->scratch);
@@ -947,6 +1018,96 @@ int nesosim_season_kernel_time(const nesosim_ctx *ctx, double *total_ms, int64_t
     if (!ctx || !total_ms || !launches) return fail(NESOSIM_ERR_ARG, "NULL argument");
     *total_ms = ctx->ens_kernel_ms;
     *launches = ctx->ens_kernel_launches;
+    return NESOSIM_OK;
+}
+
+// ---- row-strip domain decomposition over peer memory
+
+int nesosim_strip_setup(nesosim_ctx *ctx, int has_up, int has_dn) {
+    if (!ctx) return fail(NESOSIM_ERR_ARG, "NULL context");
+    if (ctx->cfg.n_members != 1 || ctx->n_sets != 1)
+        return fail(NESOSIM_ERR_ARG, "strips are for a single member on a single forcing set");
+    const int ghosts = (has_up ? STRIP_GHOST : 0) + (has_dn ? STRIP_GHOST : 0);
+    if (ctx->cfg.ny < ghosts + STRIP_GHOST)
+        return fail(NESOSIM_ERR_ARG, "a strip must own at least two rows besides its ghost rows");
+    CU(cudaSetDevice(ctx->cfg.device));
+    strip_release(ctx);
+    const size_t bytes = strip_block_bytes(ctx->cfg.nx);
+    CU(cudaMalloc(&ctx->strip.block, bytes));
+    CU(cudaMemset(ctx->strip.block, 0, bytes));
+    CU(cudaDeviceSynchronize());
+    ctx->strip.has_up = has_up != 0;
+    ctx->strip.has_dn = has_dn != 0;
+    ctx->strip.epoch = 0;
+    ctx->strip.on = true;
+    return NESOSIM_OK;
+}
+
+int nesosim_strip_block(nesosim_ctx *ctx, void **block_dev, int64_t *bytes) {
+    if (!ctx || !ctx->strip.on) return fail(NESOSIM_ERR_STATE, "nesosim_strip_setup has not been called");
+    if (block_dev) *block_dev = ctx->strip.block;
+    if (bytes) *bytes = (int64_t)strip_block_bytes(ctx->cfg.nx);
+    return NESOSIM_OK;
+}
+
+int nesosim_strip_export(nesosim_ctx *ctx, void *handle64) {
+    if (!ctx || !handle64) return fail(NESOSIM_ERR_ARG, "NULL argument");
+    if (!ctx->strip.on) return fail(NESOSIM_ERR_STATE, "nesosim_strip_setup has not been called");
+    static_assert(sizeof(cudaIpcMemHandle_t) == NESOSIM_IPC_HANDLE_BYTES, "IPC handle size");
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ctx->strip.block));
+    std::memcpy(handle64, &h, sizeof(h));
+    return NESOSIM_OK;
+}
+
+int nesosim_strip_connect_local(nesosim_ctx *ctx, void *up_block_dev, void *dn_block_dev) {
+    if (!ctx || !ctx->strip.on) return fail(NESOSIM_ERR_STATE, "nesosim_strip_setup has not been called");
+    if ((ctx->strip.has_up && !up_block_dev) || (ctx->strip.has_dn && !dn_block_dev))
+        return fail(NESOSIM_ERR_ARG, "a neighbour declared in nesosim_strip_setup is missing");
+    ctx->strip.peer_up = ctx->strip.has_up ? (char *)up_block_dev : nullptr;
+    ctx->strip.peer_dn = ctx->strip.has_dn ? (char *)dn_block_dev : nullptr;
+    ctx->strip.ipc_up = ctx->strip.ipc_dn = false;
+    return NESOSIM_OK;
+}
+
+int nesosim_strip_connect(nesosim_ctx *ctx, const void *up_handle64, const void *dn_handle64) {
+    if (!ctx || !ctx->strip.on) return fail(NESOSIM_ERR_STATE, "nesosim_strip_setup has not been called");
+    if ((ctx->strip.has_up && !up_handle64) || (ctx->strip.has_dn && !dn_handle64))
+        return fail(NESOSIM_ERR_ARG, "a neighbour declared in nesosim_strip_setup is missing");
+    CU(cudaSetDevice(ctx->cfg.device));
+    auto open = [&](const void *h64, char **out) -> int {
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, h64, sizeof(h));
+        void *p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        *out = (char *)p;
+        return NESOSIM_OK;
+    };
+    int rc;
+    if (ctx->strip.has_up) {
+        if ((rc = open(up_handle64, &ctx->strip.peer_up))) return rc;
+        ctx->strip.ipc_up = true;
+    }
+    if (ctx->strip.has_dn) {
+        if ((rc = open(dn_handle64, &ctx->strip.peer_dn))) return rc;
+        ctx->strip.ipc_dn = true;
+    }
+    return NESOSIM_OK;
+}
+
+int nesosim_strip_status(nesosim_ctx *ctx, int *timed_out) {
+    if (!ctx || !timed_out) return fail(NESOSIM_ERR_ARG, "NULL argument");
+    if (!ctx->strip.on) return fail(NESOSIM_ERR_STATE, "nesosim_strip_setup has not been called");
+    CU(cudaSetDevice(ctx->cfg.device));
+    const size_t off = 2 * strip_mail_bytes(ctx->cfg.nx) + 2 * sizeof(unsigned long long) + 2 * sizeof(unsigned int);
+    CU(cudaMemcpy(timed_out, ctx->strip.block + off, sizeof(int), cudaMemcpyDeviceToHost));
+    return NESOSIM_OK;
+}
+
+int nesosim_strip_set_timeout(nesosim_ctx *ctx, double seconds) {
+    if (!ctx || !(seconds > 0)) return fail(NESOSIM_ERR_ARG, "bad argument");
+    ctx->strip.timeout_s = seconds;
     return NESOSIM_OK;
 }
 

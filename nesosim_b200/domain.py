@@ -11,9 +11,16 @@ single-domain run: inside the extended strip the stencils of the owned rows only
 one-sided differences / zero padding the kernels apply at the edges of the LOCAL grid only reach the ghost rows --
 except on the first and last strip, where the local edge IS the global edge.
 
-The exchange uses ``torch.distributed`` point-to-point operations (NCCL over NVLink between the GPUs of a box; gloo in
-the CPU tests).  The stepping itself is behind a small interface so the same driver runs the GPU engine in production
-and the numpy oracle in the CPU test of the exchange logic.
+Two drivers share the decomposition:
+
+* ``run_decomposed_season_peer`` (production): the exchange is FUSED INTO THE DAY KERNEL.  Every strip's boundary CTAs
+  store their new depths straight into the neighbour's mailbox in peer memory (NVLink between the GPUs of a box; CUDA
+  IPC between the one-process-per-GPU ranks) and raise a flag there; the next day's boundary CTAs wait on their own
+  flag.  One native call enqueues the whole season -- one launch per day, no collective, no host round trip.
+  ``torch.distributed`` only carries the 64-byte IPC handles once and the barriers around the season.
+* ``run_decomposed_season`` (baseline / CPU-testable): one engine call per day followed by a ``torch.distributed``
+  batched isend/irecv of the ghost rows (NCCL on GPUs; gloo in the CPU tests).  The stepping is behind a small
+  interface so the same driver runs the GPU engine and, in the CPU test of the exchange logic, the numpy oracle.
 """
 import numpy as np
 
@@ -38,7 +45,7 @@ class GpuStripStepper:
         self.eng.set_forcing(forcing_local["precip"], forcing_local["conc"], forcing_local["wind"], forcing_local["drift"],
                              forcing_local.get("rho_clim"))
         self.params = [list(params_row)]
-        self.ic = ic_local
+        self.ic = None if ic_local is None else self.eng._dev(ic_local)      # staged once, not once per day
         self.out = self.eng.alloc_outputs()
 
     def step(self, x):
@@ -91,7 +98,8 @@ def slice_rows(forcing, elo, ehi):
     return out
 
 
-def run_decomposed_season(mask, num_days, dx, forcing, params_row, ic, rank, world, make_stepper, group=None):
+def run_decomposed_season(mask, num_days, dx, forcing, params_row, ic, rank, world, make_stepper, group=None,
+                          on_ready=None, on_done=None):
     """This rank's part of one season: returns (lo, hi, {array: owned rows}).  ``forcing`` / ``ic`` / ``mask`` are the
     GLOBAL arrays (each rank slices its rows; only the slices go to the device).  ``make_stepper(local_mask, num_days,
     dx, forcing_local, params_row, ic_local)`` builds the strip stepper (``GpuStripStepper`` in production)."""
@@ -102,10 +110,14 @@ def run_decomposed_season(mask, num_days, dx, forcing, params_row, ic, rank, wor
     stepper = make_stepper(np.ascontiguousarray(mask[elo:ehi]), num_days, dx, slice_rows(forcing, elo, ehi), params_row,
                            None if ic is None else np.ascontiguousarray(ic[elo:ehi]))
     top, bottom = lo - elo, ehi - hi
+    if on_ready is not None:
+        on_ready()                         # the strip is staged (tools/domain_run.py starts its clock here)
     for x in range(num_days - 1):
         stepper.step(x)
         if world > 1:
             exchange_ghost_rows(stepper.depths(x + 1), rank, world, top, bottom, group=group)
+    if on_done is not None:
+        on_done()                          # ... and stops it here, before the strip is copied to the host
     return lo, hi, stepper.result(slice(top, top + (hi - lo)))
 
 
@@ -138,4 +150,93 @@ def run_decomposed_season_one_process(mask, num_days, dx, forcing, params_row, i
             out = {k: np.empty(v.shape[:-2] + (ny, v.shape[-1]), dtype=v.dtype) for k, v in part.items()}
         for k, v in part.items():
             out[k][..., lo:hi, :] = v
+    return out
+
+
+# ------------------------------------------------------------------------------ fused peer-memory exchange
+
+def make_strip_engine(mask, num_days, dx, forcing, rank, world, device=0, timeout_s=None, **flags):
+    """Engine on this rank's extended strip with its forcing staged and ``nesosim_strip_setup`` done.
+    Returns (engine, lo, hi, elo, ehi, ic_rows) -- ``ic_rows`` slices a global (ny, nx) array to the strip."""
+    from .engine import SnowBudgetEngine
+    ny = mask.shape[0]
+    lo, hi, elo, ehi = strip_rows(ny, rank, world)
+    if hi - lo < GHOST:
+        raise ValueError("strips must own at least %d rows (ny=%d over %d ranks)" % (GHOST, ny, world))
+    eng = SnowBudgetEngine(np.ascontiguousarray(mask[elo:ehi]), num_days, dx, n_members=1, device=device, **flags)
+    eng.set_path("general")
+    f = slice_rows(forcing, elo, ehi)
+    eng.set_forcing(f["precip"], f["conc"], f["wind"], f["drift"], f.get("rho_clim"))
+    eng.strip_setup(rank > 0, rank < world - 1, timeout_s=timeout_s)
+    return eng, lo, hi, elo, ehi
+
+
+def run_decomposed_season_peer(mask, num_days, dx, forcing, params_row, ic, rank, world, device=0, group=None,
+                               outputs=None, engine=None, timeout_s=None, **flags):
+    """This rank's strip of one season with the ghost-row exchange fused into the day kernel (peer memory).
+    ``torch.distributed`` must be initialised (any backend: it moves 64-byte handles and barriers only).
+    Returns (lo, hi, {array: device tensor of the OWNED rows}, engine); pass ``engine`` back in to run further seasons
+    on the same strip without re-staging."""
+    import torch
+    import torch.distributed as dist
+    if engine is None:
+        eng, lo, hi, elo, ehi = make_strip_engine(mask, num_days, dx, forcing, rank, world, device=device,
+                                                  timeout_s=timeout_s, **flags)
+        handles = [None] * world
+        dist.all_gather_object(handles, eng.strip_export(), group=group)
+        eng.strip_connect(handles[rank - 1] if rank > 0 else None, handles[rank + 1] if rank < world - 1 else None)
+        eng._strip_rows = (lo, hi, elo, ehi)
+    else:
+        eng = engine
+        lo, hi, elo, ehi = eng._strip_rows
+    ic_local = None if ic is None else np.ascontiguousarray(ic[elo:ehi])
+    torch.cuda.synchronize(device)
+    dist.barrier(group=group)              # every strip's previous season is complete and every mailbox attached
+    out = eng.run_season([list(params_row)], ic_local, outputs)
+    torch.cuda.synchronize(device)
+    if eng.strip_timed_out():
+        raise RuntimeError("rank %d: a neighbouring strip did not deliver its ghost rows in time" % rank)
+    dist.barrier(group=group)
+    own = slice(lo - elo, lo - elo + (hi - lo))
+    return lo, hi, {k: v[0][..., own, :] for k, v in out.items()}, eng
+
+
+def run_decomposed_season_peer_one_process(mask, num_days, dx, forcing, params_row, ic, n_strips, device=0,
+                                           whole_season_per_strip=False, **flags):
+    """All strips as separate contexts on ONE GPU, wired through device pointers instead of IPC handles: the same day
+    kernel, mailboxes and flags as the multi-GPU run.  Default: the strips take turns day by day on one stream (no wait
+    ever spins).  ``whole_season_per_strip``: each strip's whole season is enqueued on its own stream, so the strips
+    really run concurrently and synchronise through their flags, as they do across GPUs."""
+    import torch
+    ny = mask.shape[0]
+    strips = []
+    for r in range(n_strips):
+        eng, lo, hi, elo, ehi = make_strip_engine(mask, num_days, dx, forcing, r, n_strips, device=device, **flags)
+        strips.append([eng, lo, hi, elo, ehi, eng.alloc_outputs(), None if ic is None else np.ascontiguousarray(ic[elo:ehi])])
+    blocks = [s[0].strip_block() for s in strips]
+    for r, s in enumerate(strips):
+        s[0].strip_connect_local(blocks[r - 1] if r > 0 else None, blocks[r + 1] if r < n_strips - 1 else None)
+    p = [list(params_row)]
+    if whole_season_per_strip:
+        streams = [torch.cuda.Stream(device) for _ in strips]
+        torch.cuda.synchronize(device)
+        for st, s in zip(streams, strips):
+            with torch.cuda.stream(st):
+                s[0].run_season(p, s[6], s[5])
+    else:
+        for x in range(num_days - 1):
+            for s in strips:
+                s[0].run_season(p, s[6], s[5], first_step=x, num_steps=1)
+    torch.cuda.synchronize(device)
+    out = None
+    for eng, lo, hi, elo, ehi, o, _ in strips:
+        if eng.strip_timed_out():
+            raise RuntimeError("a strip timed out waiting for its neighbour")
+        for k, v in o.items():
+            part = v[0][..., lo - elo:lo - elo + (hi - lo), :].cpu().numpy()
+            if out is None:
+                out = {}
+            if k not in out:
+                out[k] = np.empty(part.shape[:-2] + (ny, part.shape[-1]), dtype=part.dtype)
+            out[k][..., lo:hi, :] = part
     return out

@@ -201,6 +201,36 @@ class SnowBudgetEngine:
         _lib.check(self.lib.nesosim_season_kernel_time(self.handle, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    # ------------------------------------------------------------- strips of a decomposed grid (peer memory)
+    def strip_setup(self, has_up, has_down, timeout_s=None):
+        """Declare this context a row strip with neighbours above / below (see nesosim_strip_setup)."""
+        _lib.check(self.lib.nesosim_strip_setup(self.handle, int(bool(has_up)), int(bool(has_down))))
+        if timeout_s is not None:
+            _lib.check(self.lib.nesosim_strip_set_timeout(self.handle, float(timeout_s)))
+
+    def strip_export(self):
+        """The exchange block as a 64-byte CUDA IPC handle (for a neighbour in another process)."""
+        buf = C.create_string_buffer(64)
+        _lib.check(self.lib.nesosim_strip_export(self.handle, buf))
+        return buf.raw
+
+    def strip_block(self):
+        """The exchange block as a device address (for a neighbour in this process)."""
+        ptr, n = C.c_void_p(), C.c_int64(0)
+        _lib.check(self.lib.nesosim_strip_block(self.handle, C.byref(ptr), C.byref(n)))
+        return ptr.value
+
+    def strip_connect(self, up_handle=None, down_handle=None):
+        _lib.check(self.lib.nesosim_strip_connect(self.handle, up_handle, down_handle))
+
+    def strip_connect_local(self, up_block=None, down_block=None):
+        _lib.check(self.lib.nesosim_strip_connect_local(self.handle, up_block, down_block))
+
+    def strip_timed_out(self):
+        v = C.c_int(0)
+        _lib.check(self.lib.nesosim_strip_status(self.handle, C.byref(v)))
+        return bool(v.value)
+
     PATHS = {"auto": 0, "general": 1, "ensemble": 2}
 
     def set_path(self, path):

@@ -118,3 +118,125 @@ def test_gpu_strips_reproduce_the_single_domain_run(cuda):
     got = domain.run_decomposed_season_one_process(mask, T, 100000, forcing, PARAMS, ic, 4, make)
     for k in NAMES:
         assert np.array_equal(got[k], ref[k], equal_nan=True), k
+
+
+# ------------------------------------------------------------------ exchange fused into the day kernel (peer memory)
+
+def _gpu_reference(mask, T, dx, forcing, ic, **flags):
+    from nesosim_b200.engine import SnowBudgetEngine
+    eng = SnowBudgetEngine(mask, T, dx, n_members=1, **flags)
+    eng.set_path("general")
+    eng.set_forcing(forcing["precip"], forcing["conc"], forcing["wind"], forcing["drift"])
+    return {k: v[0].cpu().numpy() for k, v in eng.run_season([PARAMS], ic).items()}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_strips", [2, 3, 5])
+def test_peer_strips_on_a_small_grid_match_the_oracle(cuda, n_strips):
+    """Strips of 4-12 rows: one tile row is the top AND the bottom boundary set of its strip."""
+    mask, forcing, ic, ref = setup()
+    got = domain.run_decomposed_season_peer_one_process(mask, 7, 50000, forcing, PARAMS, ic, n_strips, atmlossInc=1)
+    for k in NAMES:
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ny,nx,n_strips,concurrent", [(90, 90, 4, False), (357, 357, 3, False), (357, 357, 3, True),
+                                                        (131, 70, 2, True), (200, 45, 7, True)])
+def test_peer_strips_match_the_single_domain_run(cuda, ny, nx, n_strips, concurrent):
+    """Same day kernel, mailboxes and flags as across GPUs, all strips on one device; `concurrent` = every strip's whole
+    season on its own stream, synchronised only through the flags."""
+    mask = S.region_mask(dx=100000) if (ny, nx) == (90, 90) else S.region_mask(shape=(ny, nx), kind="disc")
+    T = 9
+    forcing = S.make_season(mask, T, seed=23)
+    ic = S.make_ic(mask, seed=23)
+    ref = _gpu_reference(mask, T, 25000, forcing, ic, atmlossInc=1)
+    got = domain.run_decomposed_season_peer_one_process(mask, T, 25000, forcing, PARAMS, ic, n_strips,
+                                                        whole_season_per_strip=concurrent, atmlossInc=1)
+    for k in NAMES:
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+
+
+@pytest.mark.gpu
+def test_peer_strips_run_two_seasons_and_without_dynamics(cuda):
+    """The flag epoch: a second season on the same contexts; and dynamicsInc=0, where nothing is exchanged."""
+    import torch
+    mask = S.region_mask(shape=(64, 40), kind="disc")
+    T = 6
+    forcing = S.make_season(mask, T, seed=3)
+    ic = S.make_ic(mask, seed=3)
+    for flags in (dict(atmlossInc=1), dict(dynamicsInc=0)):
+        ref = _gpu_reference(mask, T, 50000, forcing, ic, **flags)
+        strips = [domain.make_strip_engine(mask, T, 50000, forcing, r, 3, **flags) for r in range(3)]
+        blocks = [s[0].strip_block() for s in strips]
+        for r, s in enumerate(strips):
+            s[0].strip_connect_local(blocks[r - 1] if r > 0 else None, blocks[r + 1] if r < 2 else None)
+        for season in range(2):
+            outs = []
+            streams = [torch.cuda.Stream() for _ in strips]
+            torch.cuda.synchronize()
+            for st, (eng, lo, hi, elo, ehi) in zip(streams, strips):
+                with torch.cuda.stream(st):
+                    outs.append(eng.run_season([PARAMS], np.ascontiguousarray(ic[elo:ehi])))
+            torch.cuda.synchronize()
+            for (eng, lo, hi, elo, ehi), o in zip(strips, outs):
+                assert not eng.strip_timed_out()
+                for k in NAMES:
+                    assert np.array_equal(o[k][0][..., lo - elo:hi - elo, :].cpu().numpy(), ref[k][..., lo:hi, :],
+                                          equal_nan=True), (k, season, flags)
+
+
+@pytest.mark.gpu
+def test_a_strip_without_its_neighbour_times_out_instead_of_hanging(cuda):
+    mask = S.region_mask(shape=(40, 40), kind="disc")
+    T = 4
+    forcing = S.make_season(mask, T, seed=3)
+    a = domain.make_strip_engine(mask, T, 50000, forcing, 0, 2, timeout_s=0.2)[0]
+    b = domain.make_strip_engine(mask, T, 50000, forcing, 1, 2, timeout_s=0.2)[0]
+    a.strip_connect_local(None, b.strip_block())
+    a.run_season([PARAMS], None)          # b never runs: a's second day waits for ghost rows that never come
+    cuda.cuda.synchronize()
+    assert a.strip_timed_out()
+
+
+def _peer_rank(rank, world, port, q, n_dev):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dev = rank % n_dev
+    torch.cuda.set_device(dev)
+    mask = S.region_mask(shape=(120, 80), kind="disc")
+    T = 6
+    forcing = S.make_season(mask, T, seed=9)
+    ic = S.make_ic(mask, seed=9)
+    lo, hi, part, eng = domain.run_decomposed_season_peer(mask, T, 25000, forcing, PARAMS, ic, rank, world, device=dev,
+                                                          atmlossInc=1, timeout_s=30.0)
+    q.put((rank, lo, hi, {k: v.cpu().numpy() for k, v in part.items()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_peer_strips_across_processes_over_cuda_ipc(cuda):
+    """One process per strip, mailboxes attached through CUDA IPC handles: on a multi-GPU box one GPU per rank (peer
+    stores over NVLink), on a one-GPU box both ranks share the device (time-sliced contexts)."""
+    if cuda.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs: two processes time-slicing one GPU cannot wait on each other's kernels")
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_rank, args=(r, world, port, q, cuda.cuda.device_count())) for r in range(world)]
+    for p in procs:
+        p.start()
+    parts = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    mask = S.region_mask(shape=(120, 80), kind="disc")
+    forcing = S.make_season(mask, 6, seed=9)
+    ref = _gpu_reference(mask, 6, 25000, forcing, S.make_ic(mask, seed=9), atmlossInc=1)
+    for rank, lo, hi, part in parts:
+        for k in NAMES:
+            assert np.array_equal(part[k], ref[k][..., lo:hi, :], equal_nan=True), (k, rank)
