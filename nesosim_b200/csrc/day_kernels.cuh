@@ -38,11 +38,13 @@ struct DayArgs {
     const int *member_set, *set_steps;
     long long set_stride;
     int x;
+    // per-tile flag "every in-grid cell of this TX x TY tile is land/lake" (NULL: shortcut off for this launch; it is
+    // only handed over when slot x was written by this library's own previous step, see day_step_land_tile)
+    const uint8_t *tile_land;
 };
 
 constexpr int TX = 32;
 constexpr int TY = 16;
-constexpr int DAY_THREADS = 256;
 
 // Row-strip domain decomposition over peer memory (SURVEY.md §8e "Space"; host side: nesosim_strip_* in the ABI).
 // This context's grid is one strip of a larger grid, extended by STRIP_GHOST ghost rows towards each neighbouring
@@ -76,7 +78,7 @@ __device__ __forceinline__ bool strip_bot_cta(int y0, int ny) { return y0 + TY +
 // INTERIOR: the tile with its two-cell halo lies inside the grid and none of its raw-dynamics cells is a grid-edge
 // cell, so there are no bounds tests, every difference is centred and the divisor is a launch constant (the
 // overwhelming majority of the CTAs on the 25 km and 5 km grids).
-template <bool INTERIOR, bool STRIP = false>
+template <bool INTERIOR, bool STRIP = false, int DAY_THREADS = 256>
 __device__ __forceinline__ void day_step_body(const DayArgs &a, double (&s_h)[2][TY + 4][TX + 4], double (&s_ut)[TY + 4][TX + 4],
                                               double (&s_vt)[TY + 4][TX + 4], double (&s_raw)[4][TY + 2][TX + 2],
                                               const StripLink *sl = nullptr) {
@@ -255,16 +257,81 @@ __device__ __forceinline__ void day_step_body(const DayArgs &a, double (&s_h)[2]
     }
 }
 
-__global__ void __launch_bounds__(DAY_THREADS)
-day_step_kernel(const __grid_constant__ DayArgs a) {
-    __shared__ double s_h[2][TY + 4][TX + 4];
-    __shared__ double s_ut[TY + 4][TX + 4];
-    __shared__ double s_vt[TY + 4][TX + 4];
-    __shared__ double s_raw[4][TY + 2][TX + 2];   // adv0, adv1, div0, div1 after the NaN->0 fill
+// A tile without a single ocean cell (more than half of the polar grid is land, and it comes in large blocks).  From
+// the second step on every depth on land is NaN (fill_nan_no_negative, NESOSIM.py:158-162,332-333), so every term that
+// multiplies h0 or passes the land mask is NaN whatever its other operands are -- 0*NaN included, which the reference
+// relies on too -- and only snowAcc / snowOcean (NESOSIM.py:263-270, never masked) still need their inputs: 32 B read
+// per cell instead of 129, no tiles, no stencils.  Terms whose switch is off add their literal zeros as calcBudget does.
+// Only used for a slot this library wrote itself in the same call (x > first_step): a caller-provided slot may hold
+// finite depths on land (the IC does), and then the general code below is the reference's arithmetic.
+template <int DAY_THREADS>
+__device__ __forceinline__ void day_step_land_tile(const DayArgs &a) {
+    const int m = blockIdx.z;
+    const int fset = a.member_set ? a.member_set[m] : 0;
+    if (a.set_steps && a.x >= a.set_steps[fset]) return;
+    const long long fo = (long long)fset * a.set_stride;
+    const int gx = blockIdx.x * TX + (threadIdx.x & (TX - 1));
+    if (gx >= a.nx) return;
+    const double nan = qnan();
+#pragma unroll
+    for (int rr = 0; rr < TY / (DAY_THREADS / TX); ++rr) {
+        const int gy = blockIdx.y * TY + (threadIdx.x / TX) + rr * (DAY_THREADS / TX);
+        if (gy >= a.ny) break;
+        const long long o = (long long)gy * a.nx + gx;
+        auto prev = [&](int v) { return a.prev[v][(long long)m * a.prev_stride[v] + o]; };
+        auto store = [&](int v, double val) {
+            if (a.next[v]) a.next[v][(long long)m * a.next_stride[v] + o] = val;
+        };
+        const double P = __ldg(a.P + fo + o), C = __ldg(a.C + fo + o);
+        const double pacc = prev(V_ACC), poc = prev(V_OCEAN);
+        const double pd = div_const(P, a.rho_new);
+        store(V_ACC, add(pacc, mul(pd, C)));
+        store(V_OCEAN, add(poc, -mul(pd, sub(1.0, C))));
+        store(V_ADV, a.sw.dynamics ? nan : add(add(prev(V_ADV), 0.0), 0.0));
+        store(V_DIV, a.sw.dynamics ? nan : add(add(prev(V_DIV), 0.0), 0.0));
+        store(V_LEAD, a.sw.leadloss ? nan : add(prev(V_LEAD), 0.0));
+        store(V_ATM, a.sw.atmloss ? nan : add(prev(V_ATM), 0.0));
+        store(V_WPL, a.sw.windpack ? nan : add(prev(V_WPL), 0.0));
+        store(V_WPG, a.sw.windpack ? nan : add(prev(V_WPG), 0.0));
+        store(V_WP, a.sw.windpack ? nan : add(prev(V_WP), 0.0));
+        store(V_H0, nan);
+        store(V_H1, nan);
+        store(V_DENS, nan);
+    }
+}
+
+struct TileSmem {
+    double h[2][TY + 4][TX + 4];
+    double ut[TY + 4][TX + 4];
+    double vt[TY + 4][TX + 4];
+    double raw[4][TY + 2][TX + 2];   // adv0, adv1, div0, div1 after the NaN->0 fill
+};
+
+template <int DAY_THREADS>
+__device__ __forceinline__ void day_step_tile(const DayArgs &a, TileSmem &sm) {
+    if (a.tile_land && a.tile_land[blockIdx.y * gridDim.x + blockIdx.x]) {
+        day_step_land_tile<DAY_THREADS>(a);
+        return;
+    }
+    auto &s_h = sm.h;
+    auto &s_ut = sm.ut;
+    auto &s_vt = sm.vt;
+    auto &s_raw = sm.raw;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
     const bool interior = x0 >= 2 && y0 >= 2 && x0 + TX + 2 <= a.nx && y0 + TY + 2 <= a.ny;
-    if (interior) day_step_body<true>(a, s_h, s_ut, s_vt, s_raw);
-    else day_step_body<false>(a, s_h, s_ut, s_vt, s_raw);
+    if (interior) day_step_body<true, false, DAY_THREADS>(a, s_h, s_ut, s_vt, s_raw);
+    else day_step_body<false, false, DAY_THREADS>(a, s_h, s_ut, s_vt, s_raw);
+}
+
+// Two builds of the same tile code: 256 threads x 2 cells (large grids: fewer, fatter threads) and 512 threads x 1
+// cell (small grids, where a day is one wave of CTAs and its length is the dependent chain inside a CTA).
+__global__ void __launch_bounds__(256) day_step_kernel(const __grid_constant__ DayArgs a) {
+    __shared__ TileSmem sm;
+    day_step_tile<256>(a, sm);
+}
+__global__ void __launch_bounds__(512, 2) day_step_kernel_512(const __grid_constant__ DayArgs a) {
+    __shared__ TileSmem sm;
+    day_step_tile<512>(a, sm);
 }
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -298,18 +365,13 @@ __device__ __forceinline__ void strip_signal(unsigned int *cnt, unsigned int exp
 
 // The day step of one strip (M = 1, dynamics on).  CTAs whose tile (with its halo) stays clear of the ghost rows and
 // of the rows a neighbour needs run exactly the code of day_step_kernel.
-__global__ void __launch_bounds__(DAY_THREADS)
-day_step_strip_kernel(const __grid_constant__ DayArgs a, const __grid_constant__ StripLink s) {
-    __shared__ double s_h[2][TY + 4][TX + 4];
-    __shared__ double s_ut[TY + 4][TX + 4];
-    __shared__ double s_vt[TY + 4][TX + 4];
-    __shared__ double s_raw[4][TY + 2][TX + 2];
-    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+template <int DAY_THREADS>
+__device__ __forceinline__ void day_step_strip(const DayArgs &a, const StripLink &s) {
+    const int y0 = blockIdx.y * TY;
     const bool top = s.has_up && strip_top_cta(y0), bot = s.has_dn && strip_bot_cta(y0, a.ny);
+    __shared__ TileSmem sm;
     if (!top && !bot) {
-        const bool interior = x0 >= 2 && y0 >= 2 && x0 + TX + 2 <= a.nx && y0 + TY + 2 <= a.ny;
-        if (interior) day_step_body<true>(a, s_h, s_ut, s_vt, s_raw);
-        else day_step_body<false>(a, s_h, s_ut, s_vt, s_raw);
+        day_step_tile<DAY_THREADS>(a, sm);
         return;
     }
     if (s.use_mail) {
@@ -319,7 +381,7 @@ day_step_strip_kernel(const __grid_constant__ DayArgs a, const __grid_constant__
         }
         __syncthreads();
     }
-    day_step_body<false, true>(a, s_h, s_ut, s_vt, s_raw, &s);
+    day_step_body<false, true, DAY_THREADS>(a, sm.h, sm.ut, sm.vt, sm.raw, &s);
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -328,6 +390,11 @@ day_step_strip_kernel(const __grid_constant__ DayArgs a, const __grid_constant__
         if (bot) strip_signal(s.cnt_bot, s.expect_bot, s.peer_dn_flag, v);
     }
 }
+
+__global__ void __launch_bounds__(256)
+day_step_strip_kernel(const __grid_constant__ DayArgs a, const __grid_constant__ StripLink s) { day_step_strip<256>(a, s); }
+__global__ void __launch_bounds__(512, 2)
+day_step_strip_kernel_512(const __grid_constant__ DayArgs a, const __grid_constant__ StripLink s) { day_step_strip<512>(a, s); }
 
 // Slot 0 of every array: zeros (genEmptyArrays, NESOSIM.py:350-376) and the initial-condition split of main
 // (NESOSIM.py:604-609): IC[conc<minConc]=0; h[0,0]=h[0,1]=IC*0.5.

@@ -163,6 +163,9 @@ struct nesosim_ctx {
     int *member_set_dev = nullptr, *set_steps_dev = nullptr;
     int ens_status = 0;             // flag read back from the last season-resident launch (1 = rerun needed)
     long long ens_reruns = 0;
+    uint8_t *tile_land_dev = nullptr;   // per day-kernel tile: no ocean cell inside (day_step_land_tile)
+    bool land_shortcut = true;
+    int day_variant = 256;          // threads per CTA of the day kernel (256 x 2 cells or 512 x 1 cell)
     int path = 0;                   // 0 auto, 1 general per-day launches, 2 season-resident ensemble kernel
     int last_path = 0;              // which path the last run_season used (1 or 2)
     // row-strip domain decomposition over peer memory (nesosim_strip_*; StripLink in day_kernels.cuh)
@@ -307,8 +310,9 @@ void strip_link(const nesosim_ctx *ctx, int x, dim3 grid, StripLink *s) {
 
 int launch_day(nesosim_ctx *ctx, int x, const double *P, const double *C, const double *W, const double *U,
                const double *V, double rho_new, const nesosim_outputs *o, int m0, int mcount, cudaStream_t st,
-               bool strip_step = false) {
+               bool strip_step = false, bool land_ok = false) {
     DayArgs a;
+    a.tile_land = (land_ok && ctx->land_shortcut) ? ctx->tile_land_dev : nullptr;
     a.ny = ctx->cfg.ny;
     a.nx = ctx->cfg.nx;
     a.P = P; a.C = C; a.W = W; a.U = U; a.V = V;
@@ -338,9 +342,12 @@ int launch_day(nesosim_ctx *ctx, int x, const double *P, const double *C, const 
     if (strip_step && ctx->strip.on && a.sw.dynamics && (ctx->strip.has_up || ctx->strip.has_dn)) {
         StripLink s;
         strip_link(ctx, x, grid, &s);
-        day_step_strip_kernel<<<grid, DAY_THREADS, 0, st>>>(a, s);
+        if (ctx->day_variant == 512) day_step_strip_kernel_512<<<grid, 512, 0, st>>>(a, s);
+        else day_step_strip_kernel<<<grid, 256, 0, st>>>(a, s);
+    } else if (ctx->day_variant == 512) {
+        day_step_kernel_512<<<grid, 512, 0, st>>>(a);
     } else {
-        day_step_kernel<<<grid, DAY_THREADS, 0, st>>>(a);
+        day_step_kernel<<<grid, 256, 0, st>>>(a);
     }
     ctx->launches++;
     CU(cudaGetLastError());
@@ -763,7 +770,7 @@ int run_members(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, const
         const double rho = ctx->cfg.density_clim ? ctx->rho_clim_host[x] : ctx->cfg.snowDensityFresh;
         rc = launch_day(ctx, x, ctx->P + x * plane, ctx->C + x * plane, ctx->W + x * plane,
                         ctx->UV + (long long)x * 2 * plane, ctx->UV + ((long long)x * 2 + 1) * plane, rho, out,
-                        m0, mcount, st, true);
+                        m0, mcount, st, true, x > first_step);
         if (rc) return rc;
     }
     return NESOSIM_OK;
@@ -810,10 +817,35 @@ int nesosim_create(const nesosim_config *cfg, const uint8_t *region_mask_host, n
     if (e == cudaSuccess) e = cudaMemcpy(ctx->mask_dev, region_mask_host, ctx->plane, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->coef_dev, sizeof(MemberCoef) * cfg->n_members);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->flags_dev, sizeof(int));
+    // day-kernel tiles without an ocean cell (land: code > 10, lakes: code < 1; fill_nan_no_negative, NESOSIM.py:158-162)
+    const int tgx = (cfg->nx + TX - 1) / TX, tgy = (cfg->ny + TY - 1) / TY;
+    std::vector<uint8_t> tl((size_t)tgx * tgy, 1);
+    for (int y = 0; y < cfg->ny; ++y)
+        for (int x = 0; x < cfg->nx; ++x) {
+            const uint8_t c = region_mask_host[(size_t)y * cfg->nx + x];
+            if (!(c > 10 || c < 1)) tl[(size_t)(y / TY) * tgx + x / TX] = 0;
+        }
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->tile_land_dev, tl.size());
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->tile_land_dev, tl.data(), tl.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         nesosim_destroy(ctx);
         return cuda_fail(e, "nesosim_create allocation");
     }
+    // CTA shape and land shortcut by the number of CTAs per day (measured on a B200, tools/general_timing.py): a day of
+    // one wave or less is as long as the dependent chain inside one CTA -- 512 threads x 1 cell shorten it when an SM
+    // holds a single CTA (100 km: 12.1 -> 10.6 us/day), and the land-tile lookup only adds a load to that chain
+    // (25 km: 13.5 -> 15.2 us/day); with many waves throughput counts (5 km: 266 -> 194 us/day with both).
+    {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+        const long long ctas = (long long)tgx * tgy * cfg->n_members;
+        if (ctas <= sms) { ctx->day_variant = 512; ctx->land_shortcut = false; }
+        else if (ctas >= 8LL * sms) { ctx->day_variant = 512; ctx->land_shortcut = true; }
+        else { ctx->day_variant = 256; ctx->land_shortcut = false; }
+    }
+    // development switches for A/B timing (both settings of each produce identical values)
+    if (const char *v = std::getenv("NESOSIM_DAY_THREADS")) ctx->day_variant = std::atoi(v) == 512 ? 512 : 256;
+    if (const char *v = std::getenv("NESOSIM_LAND_SHORTCUT")) ctx->land_shortcut = std::atoi(v) != 0;
     *out = ctx;
     return NESOSIM_OK;
 }
@@ -825,6 +857,7 @@ int nesosim_destroy(nesosim_ctx *ctx) {
     for (int i = 0; i < 2; ++i)
         if (ctx->ens_ev[i]) cudaEventDestroy(ctx->ens_ev[i]);
     strip_release(ctx);
+    cudaFree(ctx->tile_land_dev);
     cudaFree(ctx->mask_dev);
     cudaFree(ctx->coef_dev);
     cudaFree(ctx->scratch);

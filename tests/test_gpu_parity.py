@@ -212,6 +212,74 @@ def test_prenormalised_kernel_variant(cuda, path):
     compare_all(got, refs)
 
 
+def _blocky_mask(ny=100, nx=150):
+    """Large land blocks (whole 32x16 tiles), a lake-only tile, a coast running through tiles, ocean elsewhere."""
+    mask = np.full((ny, nx), 8, dtype=np.uint8)
+    mask[:40, :70] = 11          # land: tiles (0..1, 0..1) entirely, and partly the ones around them
+    mask[64:80, 96:128] = 0      # one tile of lake cells exactly
+    mask[50:, 130:] = 12         # coast code, ragged last tile column
+    mask[90:, :] = 11
+    return mask
+
+
+@pytest.mark.parametrize("threads", ["256", "512"])
+@pytest.mark.parametrize("flags", [dict(atmlossInc=1), dict(dynamicsInc=0), dict(leadlossInc=0, windpackInc=0),
+                                   dict(dynamicsInc=0, leadlossInc=0, windpackInc=0, atmlossInc=0),
+                                   dict(densityType="clim")])
+def test_land_tile_shortcut_and_thread_variants(cuda, flags, threads, monkeypatch):
+    """Tiles without an ocean cell take the closed-form land path from the second step on (day_step_land_tile); the
+    IC deliberately puts snow on land, so step 0 must still be the general arithmetic.  Both CTA shapes."""
+    monkeypatch.setenv("NESOSIM_DAY_THREADS", threads)
+    mask = _blocky_mask()
+    T = 7
+    rho = 1000 * (0.29 + 0.0003 * np.arange(T)) if flags.get("densityType") == "clim" else None
+    from nesosim_b200.engine import SnowBudgetEngine
+    forcing = S.make_season(mask, T, seed=21)
+    ic = np.full(mask.shape, 0.08)               # finite depth everywhere at slot 0, land included
+    eng = SnowBudgetEngine(mask, T, 50000, n_members=2, **flags)
+    eng.set_path("general")
+    eng.set_forcing(forcing["precip"], forcing["conc"], forcing["wind"], forcing["drift"], rho)
+    got = {k: v.cpu().numpy() for k, v in eng.run_season([MULTISEASON, ONESEASON], ic).items()}
+    fl = O.Flags(dynamicsInc=flags.get("dynamicsInc", 1), leadlossInc=flags.get("leadlossInc", 1),
+                 windpackInc=flags.get("windpackInc", 1), atmlossInc=flags.get("atmlossInc", 0),
+                 densityType=flags.get("densityType", "variable"))
+    refs = [O.run_season(forcing, ic, mask, 50000, oracle_params(row), fl, rho_clim=rho) for row in (MULTISEASON, ONESEASON)]
+    compare_all(got, refs)
+    # resumed in pieces: the first step of every piece reads a caller-provided slot and must not take the shortcut
+    out = eng.alloc_outputs(zero=True)
+    for a, b in ((0, 1), (1, 3), (4, 2)):
+        eng.run_season([MULTISEASON, ONESEASON], ic, out, first_step=a, num_steps=b)
+    for k in got:
+        assert np.array_equal(out[k].cpu().numpy(), got[k], equal_nan=True), k
+    eng.close()
+
+
+def test_land_shortcut_is_not_taken_on_a_caller_provided_slot(cuda):
+    """nesosim_run_season(first_step=k) on a state the caller made up: finite depths on land at slot k are data."""
+    from nesosim_b200.engine import SnowBudgetEngine
+    mask = _blocky_mask()
+    T = 4
+    forcing = S.make_season(mask, T, seed=22)
+    eng = SnowBudgetEngine(mask, T, 50000, n_members=1, atmlossInc=1)
+    eng.set_path("general")
+    eng.set_forcing(forcing["precip"], forcing["conc"], forcing["wind"], forcing["drift"])
+    out = eng.alloc_outputs(zero=True)
+    rng = np.random.default_rng(5)
+    state = O.gen_empty_arrays(T, *mask.shape)
+    for k in out:
+        made_up = rng.random(state[k][1].shape) * 0.2
+        state[k][1] = made_up
+        out[k][0, 1] = cuda.from_numpy(made_up).cuda()
+    eng.run_season([MULTISEASON], None, out, first_step=1, num_steps=2)
+    p = oracle_params(MULTISEASON)
+    for x in (1, 2):
+        O.calc_budget(state, forcing["conc"][x], forcing["precip"][x], forcing["drift"][x], forcing["wind"][x],
+                      np.full(mask.shape, np.nan), mask, 50000, x, p, O.Flags(atmlossInc=1))
+    for k in out:
+        assert np.array_equal(out[k][0, 2:].cpu().numpy(), state[k][2:], equal_nan=True), k
+    eng.close()
+
+
 def test_25km_short_season(cuda):
     mask = S.region_mask(dx=25000)
     got, refs = run_both(mask, 6, 25000, [MULTISEASON], dict(atmlossInc=1), seed=18, expect_path="general")

@@ -1,27 +1,47 @@
-"""Throughput of the general per-day path (day_step_kernel) on the larger grids: single season, M members.
-usage: python tools/general_timing.py n days [members]"""
-import os, sys
+"""Throughput of the general per-day path (day_step_kernel) on the larger grids: single season, M members, for every
+build variant of the day kernel (NESOSIM_DAY_THREADS x NESOSIM_LAND_SHORTCUT), checking that all variants agree.
+usage: python tools/general_timing.py n days [members] [generated_days]"""
+import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
 import torch
 from nesosim_b200 import synthetic as S
 from nesosim_b200.engine import SnowBudgetEngine
 n = int(sys.argv[1]); T = int(sys.argv[2]); M = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+G = int(sys.argv[4]) if len(sys.argv) > 4 else min(T, 8)
 dx = {90: 100000, 357: 25000, 1785: 5000}[n]
 mask = S.region_mask(dx=dx) if n in (90, 357) else S.region_mask(shape=(n, n), kind="disc")
-F = S.make_season(mask, T, seed=1)
+gen = S.make_season(mask, G, seed=1)
+idx = np.arange(T) % G
+F = {k: (v if v is None else torch.from_numpy(v[idx]).cuda()) for k, v in gen.items()}
 ic = S.make_ic(mask, seed=1)
 params = S.ensemble_params(M, seed=1)
-eng = SnowBudgetEngine(mask, T, dx, n_members=M, atmlossInc=1)
-eng.set_path("general")
-eng.set_forcing(F["precip"], F["conc"], F["wind"], F["drift"])
-out = eng.alloc_outputs()
-ts = []
-for rep in range(4):
-    torch.cuda.synchronize()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record(); eng.run_season(params, ic, out); e1.record(); torch.cuda.synchronize()
-    ts.append(e0.elapsed_time(e1))
-ms = min(ts[1:])
 cells = M * n * n * (T - 1)
-print("general path %dx%d, %d days, M=%d: %.3f ms/season, %.1f us/day, %.3e cell-days/s, %.0f GB/s algorithmic (%.1f%% of 6551)"
-      % (n, n, T, M, ms, 1e3 * ms / (T - 1), cells / ms * 1e3, cells * (96 + 41.0 / M) / ms / 1e6, cells * (96 + 41.0 / M) / ms / 1e6 / 65.51))
+land = float(np.mean((mask > 10) | (mask < 1)))
+first = None
+variants = [v.split(":") for v in os.environ.get("VARIANTS", "256:0,256:1,512:0,512:1").split(",")]
+for threads, shortcut in variants:
+    os.environ["NESOSIM_DAY_THREADS"] = threads
+    os.environ["NESOSIM_LAND_SHORTCUT"] = shortcut
+    eng = SnowBudgetEngine(mask, T, dx, n_members=M, atmlossInc=1)
+    eng.set_path("general")
+    eng.set_forcing(F["precip"], F["conc"], F["wind"], F["drift"])
+    out = eng.alloc_outputs()
+    ts = []
+    for rep in range(5):
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); eng.run_season(params, ic, out); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = min(ts[1:])
+    digest = {k: (float(torch.nansum(v).item()), int(torch.isnan(v).sum().item())) for k, v in out.items()}
+    if first is None:
+        first = digest
+    print(json.dumps({"grid": [n, n], "days": T, "members": M, "land_fraction": round(land, 3), "threads": int(threads),
+                      "land_shortcut": int(shortcut), "ms_per_season": ms, "us_per_day": 1e3 * ms / (T - 1),
+                      "cell_days_per_s": cells / ms * 1e3, "algorithmic_GBs": cells * (96 + 41.0 / M) / ms / 1e6,
+                      "frac_of_6551": cells * (96 + 41.0 / M) / ms / 1e6 / 6551, "same_digest_as_first": digest == first}),
+          flush=True)
+    del out
+    eng.close()
+    torch.cuda.empty_cache()
