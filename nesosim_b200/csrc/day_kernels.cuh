@@ -81,9 +81,9 @@ __device__ __forceinline__ bool strip_bot_cta(int y0, int ny) { return y0 + TY +
 template <bool INTERIOR, bool STRIP = false, int DAY_THREADS = 256>
 __device__ __forceinline__ void day_step_body(const DayArgs &a, double (&s_h)[2][TY + 4][TX + 4], double (&s_ut)[TY + 4][TX + 4],
                                               double (&s_vt)[TY + 4][TX + 4], double (&s_raw)[4][TY + 2][TX + 2],
-                                              const StripLink *sl = nullptr) {
+                                              const int by, const StripLink *sl = nullptr) {
     const int m = blockIdx.z;
-    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int x0 = blockIdx.x * TX, y0 = by * TY;     // `by`: tile row (blockIdx.y, permuted by the strip kernel)
     const int tid = threadIdx.x;
     const int ny = a.ny, nx = a.nx;
     const int fset = a.member_set ? a.member_set[m] : 0;
@@ -265,7 +265,7 @@ __device__ __forceinline__ void day_step_body(const DayArgs &a, double (&s_h)[2]
 // Only used for a slot this library wrote itself in the same call (x > first_step): a caller-provided slot may hold
 // finite depths on land (the IC does), and then the general code below is the reference's arithmetic.
 template <int DAY_THREADS>
-__device__ __forceinline__ void day_step_land_tile(const DayArgs &a) {
+__device__ __forceinline__ void day_step_land_tile(const DayArgs &a, const int by) {
     const int m = blockIdx.z;
     const int fset = a.member_set ? a.member_set[m] : 0;
     if (a.set_steps && a.x >= a.set_steps[fset]) return;
@@ -275,7 +275,7 @@ __device__ __forceinline__ void day_step_land_tile(const DayArgs &a) {
     const double nan = qnan();
 #pragma unroll
     for (int rr = 0; rr < TY / (DAY_THREADS / TX); ++rr) {
-        const int gy = blockIdx.y * TY + (threadIdx.x / TX) + rr * (DAY_THREADS / TX);
+        const int gy = by * TY + (threadIdx.x / TX) + rr * (DAY_THREADS / TX);
         if (gy >= a.ny) break;
         const long long o = (long long)gy * a.nx + gx;
         auto prev = [&](int v) { return a.prev[v][(long long)m * a.prev_stride[v] + o]; };
@@ -308,30 +308,30 @@ struct TileSmem {
 };
 
 template <int DAY_THREADS>
-__device__ __forceinline__ void day_step_tile(const DayArgs &a, TileSmem &sm) {
-    if (a.tile_land && a.tile_land[blockIdx.y * gridDim.x + blockIdx.x]) {
-        day_step_land_tile<DAY_THREADS>(a);
+__device__ __forceinline__ void day_step_tile(const DayArgs &a, TileSmem &sm, const int by) {
+    if (a.tile_land && a.tile_land[by * gridDim.x + blockIdx.x]) {
+        day_step_land_tile<DAY_THREADS>(a, by);
         return;
     }
     auto &s_h = sm.h;
     auto &s_ut = sm.ut;
     auto &s_vt = sm.vt;
     auto &s_raw = sm.raw;
-    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int x0 = blockIdx.x * TX, y0 = by * TY;
     const bool interior = x0 >= 2 && y0 >= 2 && x0 + TX + 2 <= a.nx && y0 + TY + 2 <= a.ny;
-    if (interior) day_step_body<true, false, DAY_THREADS>(a, s_h, s_ut, s_vt, s_raw);
-    else day_step_body<false, false, DAY_THREADS>(a, s_h, s_ut, s_vt, s_raw);
+    if (interior) day_step_body<true, false, DAY_THREADS>(a, s_h, s_ut, s_vt, s_raw, by);
+    else day_step_body<false, false, DAY_THREADS>(a, s_h, s_ut, s_vt, s_raw, by);
 }
 
 // Two builds of the same tile code: 256 threads x 2 cells (large grids: fewer, fatter threads) and 512 threads x 1
 // cell (small grids, where a day is one wave of CTAs and its length is the dependent chain inside a CTA).
 __global__ void __launch_bounds__(256) day_step_kernel(const __grid_constant__ DayArgs a) {
     __shared__ TileSmem sm;
-    day_step_tile<256>(a, sm);
+    day_step_tile<256>(a, sm, blockIdx.y);
 }
 __global__ void __launch_bounds__(512, 2) day_step_kernel_512(const __grid_constant__ DayArgs a) {
     __shared__ TileSmem sm;
-    day_step_tile<512>(a, sm);
+    day_step_tile<512>(a, sm, blockIdx.y);
 }
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -367,11 +367,15 @@ __device__ __forceinline__ void strip_signal(unsigned int *cnt, unsigned int exp
 // of the rows a neighbour needs run exactly the code of day_step_kernel.
 template <int DAY_THREADS>
 __device__ __forceinline__ void day_step_strip(const DayArgs &a, const StripLink &s) {
-    const int y0 = blockIdx.y * TY;
+    // CTAs start roughly in blockIdx order, so the tile rows are dealt boundary first -- top, bottom, second, second to
+    // last, ... -- and the rows a neighbour waits for leave in the first wave of the launch instead of its last
+    const int ty = blockIdx.y, nty = gridDim.y;
+    const int by = (ty & 1) ? nty - 1 - (ty >> 1) : (ty >> 1);
+    const int y0 = by * TY;
     const bool top = s.has_up && strip_top_cta(y0), bot = s.has_dn && strip_bot_cta(y0, a.ny);
     __shared__ TileSmem sm;
     if (!top && !bot) {
-        day_step_tile<DAY_THREADS>(a, sm);
+        day_step_tile<DAY_THREADS>(a, sm, by);
         return;
     }
     if (s.use_mail) {
@@ -381,7 +385,7 @@ __device__ __forceinline__ void day_step_strip(const DayArgs &a, const StripLink
         }
         __syncthreads();
     }
-    day_step_body<false, true, DAY_THREADS>(a, sm.h, sm.ut, sm.vt, sm.raw, &s);
+    day_step_body<false, true, DAY_THREADS>(a, sm.h, sm.ut, sm.vt, sm.raw, by, &s);
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
