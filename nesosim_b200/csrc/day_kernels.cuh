@@ -75,6 +75,22 @@ struct StripLink {
 __device__ __forceinline__ bool strip_top_cta(int y0) { return y0 - 2 < 2 * STRIP_GHOST; }
 __device__ __forceinline__ bool strip_bot_cta(int y0, int ny) { return y0 + TY + 2 > ny - 2 * STRIP_GHOST; }
 
+// Programmatic dependent launch: the day kernels of a season are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so day x+1's CTAs may become resident while day x is still
+// draining.  Everything that does not depend on day x -- parameters, the forcing and mask of the CTA's cells, the drift
+// tile -- is requested before pdl_wait(); yesterday's arrays are only touched after it (it returns once day x has
+// completed and its writes are visible).  Without the launch attribute both instructions do nothing.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// 8-byte asynchronous global -> shared copy (no register staging); `valid` false writes 0.0 instead (src-size 0)
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gmem_src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int n = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gmem_src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // INTERIOR: the tile with its two-cell halo lies inside the grid and none of its raw-dynamics cells is a grid-edge
 // cell, so there are no bounds tests, every difference is centred and the divisor is a launch constant (the
 // overwhelming majority of the CTAs on the 25 km and 5 km grids).
@@ -95,7 +111,7 @@ __device__ __forceinline__ void day_step_body(const DayArgs &a, double (&s_h)[2]
 
     // The point-wise inputs of this thread's cells (forcing, mask, yesterday's nine accumulators) are requested
     // before anything else: they land while the tiles are staged and the raw dynamics computed, instead of each
-    // load waiting in front of its one consumer behind the previous store.
+    // load waiting in front of its one consumer behind the previous store.  Forcing first (independent of day x) ...
     constexpr int CPT = TY / (DAY_THREADS / TX);   // cells per thread
     const int ptx = tid & (TX - 1), pgx = x0 + ptx;
     double pf_P[CPT], pf_C[CPT], pf_W[CPT], pf_prev[CPT][9];
@@ -105,14 +121,37 @@ __device__ __forceinline__ void day_step_body(const DayArgs &a, double (&s_h)[2]
         const int gy = y0 + (tid / TX) + rr * (DAY_THREADS / TX);
         pf_P[rr] = pf_C[rr] = pf_W[rr] = 0.0;
         pf_land[rr] = true;
-#pragma unroll
-        for (int v = 0; v < 9; ++v) pf_prev[rr][v] = 0.0;
         if (INTERIOR || (pgx < nx && gy < ny)) {
             const long long o = (long long)gy * nx + pgx;
             pf_P[rr] = __ldg(aP + o);
             pf_C[rr] = __ldg(aC + o);
             pf_W[rr] = __ldg(aW + o);
             pf_land[rr] = is_land(__ldg(a.mask + o));
+        }
+    }
+    // ... and the raw drift tile straight into shared memory (the *deltaT of NESOSIM.py:204,210 is applied where the
+    // raw dynamics read it; cells outside the grid are written as 0.0)
+    if (a.sw.dynamics) {
+        for (int i = tid; i < (TY + 4) * (TX + 4); i += DAY_THREADS) {
+            const int r = i / (TX + 4), c = i - r * (TX + 4);
+            const int gy = y0 + r - 2, gx = x0 + c - 2;
+            const bool in = INTERIOR || (gy >= 0 && gy < ny && gx >= 0 && gx < nx);
+            const long long o = in ? (long long)gy * nx + gx : 0;
+            cp_async8(&s_ut[r][c], aU + o, in);
+            cp_async8(&s_vt[r][c], aV + o, in);
+        }
+    }
+    const MemberCoef mc = a.coef[m];
+
+    pdl_wait();      // ---- from here on yesterday's slot may be read
+
+#pragma unroll
+    for (int rr = 0; rr < CPT; ++rr) {
+        const int gy = y0 + (tid / TX) + rr * (DAY_THREADS / TX);
+#pragma unroll
+        for (int v = 0; v < 9; ++v) pf_prev[rr][v] = 0.0;
+        if (INTERIOR || (pgx < nx && gy < ny)) {
+            const long long o = (long long)gy * nx + pgx;
 #pragma unroll
             for (int v = 0; v < 9; ++v) pf_prev[rr][v] = a.prev[V_ACC + v][(long long)m * a.prev_stride[V_ACC + v] + o];
         }
@@ -122,45 +161,39 @@ __device__ __forceinline__ void day_step_body(const DayArgs &a, double (&s_h)[2]
         for (int i = tid; i < (TY + 4) * (TX + 4); i += DAY_THREADS) {
             const int r = i / (TX + 4), c = i - r * (TX + 4);
             const int gy = y0 + r - 2, gx = x0 + c - 2;
-            double h0 = 0.0, h1 = 0.0, ut = 0.0, vt = 0.0;
-            if (INTERIOR || (gy >= 0 && gy < ny && gx >= 0 && gx < nx)) {
-                const long long o = (long long)gy * nx + gx;
-                const double *mail = nullptr;      // ghost row of a neighbouring strip: depths come from the mailbox
-                int mrow = 0;
-                if (STRIP && sl->use_mail) {
-                    if (sl->has_up && gy < STRIP_GHOST) { mail = sl->mail_top; mrow = gy; }
-                    else if (sl->has_dn && gy >= ny - STRIP_GHOST) { mail = sl->mail_bot; mrow = gy - (ny - STRIP_GHOST); }
-                }
-                if (STRIP && mail) {
-                    const long long mo = ((long long)(a.x & 1) * 2 * STRIP_GHOST + mrow) * nx + gx;
-                    h0 = __ldcg(mail + mo);
-                    h1 = __ldcg(mail + mo + (long long)STRIP_GHOST * nx);
-                } else {
-                    h0 = h0p[o];
-                    h1 = h1p[o];
-                }
-                ut = mul(__ldg(aU + o), a.k.deltaT);   // driftGday[0]*deltaT (NESOSIM.py:204,210)
-                vt = mul(__ldg(aV + o), a.k.deltaT);
+            const bool in = INTERIOR || (gy >= 0 && gy < ny && gx >= 0 && gx < nx);
+            const long long o = in ? (long long)gy * nx + gx : 0;
+            const double *mail = nullptr;      // ghost row of a neighbouring strip: depths come from the mailbox
+            int mrow = 0;
+            if (STRIP && in && sl->use_mail) {
+                if (sl->has_up && gy < STRIP_GHOST) { mail = sl->mail_top; mrow = gy; }
+                else if (sl->has_dn && gy >= ny - STRIP_GHOST) { mail = sl->mail_bot; mrow = gy - (ny - STRIP_GHOST); }
             }
-            s_h[0][r][c] = h0;
-            s_h[1][r][c] = h1;
-            s_ut[r][c] = ut;
-            s_vt[r][c] = vt;
+            if (STRIP && mail) {
+                const long long mo = ((long long)(a.x & 1) * 2 * STRIP_GHOST + mrow) * nx + gx;
+                s_h[0][r][c] = __ldcg(mail + mo);
+                s_h[1][r][c] = __ldcg(mail + mo + (long long)STRIP_GHOST * nx);
+            } else {
+                cp_async8(&s_h[0][r][c], h0p + o, in);
+                cp_async8(&s_h[1][r][c], h1p + o, in);
+            }
         }
+        cp_async_wait_all();
         __syncthreads();
+        const double dT = a.k.deltaT;
         for (int i = tid; i < (TY + 2) * (TX + 2); i += DAY_THREADS) {
             const int r = i / (TX + 2), c = i - r * (TX + 2);
             const int gy = y0 + r - 1, gx = x0 + c - 1;
             double adv0 = 0.0, adv1 = 0.0, div0 = 0.0, div1 = 0.0;   // zero padding of convolve(boundary='fill')
             if (INTERIOR || (gy >= 0 && gy < ny && gx >= 0 && gx < nx)) {
                 const int sr = r + 1, sc = c + 1;
-                const double ut = s_ut[sr][sc], vt = s_vt[sr][sc];
+                const double ut = mul(s_ut[sr][sc], dT), vt = mul(s_vt[sr][sc], dT);   // driftGday*deltaT
                 // centred difference with the constant divisor 2.*dx where no cell of the tile is a grid-edge cell
                 auto grad = [&](double fm, double fc, double fp, int idx, int n) {
                     return INTERIOR ? div_const(sub(fp, fm), a.g.two_dx) : gradient1d(fm, fc, fp, idx, n, a.g);
                 };
-                const double gxu = grad(s_ut[sr][sc - 1], ut, s_ut[sr][sc + 1], gx, nx);
-                const double gyv = grad(s_vt[sr - 1][sc], vt, s_vt[sr + 1][sc], gy, ny);
+                const double gxu = grad(mul(s_ut[sr][sc - 1], dT), ut, mul(s_ut[sr][sc + 1], dT), gx, nx);
+                const double gyv = grad(mul(s_vt[sr - 1][sc], dT), vt, mul(s_vt[sr + 1][sc], dT), gy, ny);
 #pragma unroll
                 for (int l = 0; l < 2; ++l) {
                     const double h = s_h[l][sr][sc];
@@ -179,7 +212,6 @@ __device__ __forceinline__ void day_step_body(const DayArgs &a, double (&s_h)[2]
         __syncthreads();
     }
 
-    const MemberCoef mc = a.coef[m];
     const int tx = tid & (TX - 1);
     const int gx = x0 + tx;
     if (!INTERIOR && gx >= nx) return;
@@ -273,8 +305,21 @@ __device__ __forceinline__ void day_step_land_tile(const DayArgs &a, const int b
     const int gx = blockIdx.x * TX + (threadIdx.x & (TX - 1));
     if (gx >= a.nx) return;
     const double nan = qnan();
+    constexpr int CPT = TY / (DAY_THREADS / TX);
+    double P[CPT], C[CPT];
 #pragma unroll
-    for (int rr = 0; rr < TY / (DAY_THREADS / TX); ++rr) {
+    for (int rr = 0; rr < CPT; ++rr) {
+        const int gy = by * TY + (threadIdx.x / TX) + rr * (DAY_THREADS / TX);
+        P[rr] = C[rr] = 0.0;
+        if (gy < a.ny) {
+            const long long o = (long long)gy * a.nx + gx;
+            P[rr] = __ldg(a.P + fo + o);
+            C[rr] = __ldg(a.C + fo + o);
+        }
+    }
+    pdl_wait();
+#pragma unroll
+    for (int rr = 0; rr < CPT; ++rr) {
         const int gy = by * TY + (threadIdx.x / TX) + rr * (DAY_THREADS / TX);
         if (gy >= a.ny) break;
         const long long o = (long long)gy * a.nx + gx;
@@ -282,11 +327,10 @@ __device__ __forceinline__ void day_step_land_tile(const DayArgs &a, const int b
         auto store = [&](int v, double val) {
             if (a.next[v]) a.next[v][(long long)m * a.next_stride[v] + o] = val;
         };
-        const double P = __ldg(a.P + fo + o), C = __ldg(a.C + fo + o);
         const double pacc = prev(V_ACC), poc = prev(V_OCEAN);
-        const double pd = div_const(P, a.rho_new);
-        store(V_ACC, add(pacc, mul(pd, C)));
-        store(V_OCEAN, add(poc, -mul(pd, sub(1.0, C))));
+        const double pd = div_const(P[rr], a.rho_new);
+        store(V_ACC, add(pacc, mul(pd, C[rr])));
+        store(V_OCEAN, add(poc, -mul(pd, sub(1.0, C[rr]))));
         store(V_ADV, a.sw.dynamics ? nan : add(add(prev(V_ADV), 0.0), 0.0));
         store(V_DIV, a.sw.dynamics ? nan : add(add(prev(V_DIV), 0.0), 0.0));
         store(V_LEAD, a.sw.leadloss ? nan : add(prev(V_LEAD), 0.0));
@@ -302,13 +346,14 @@ __device__ __forceinline__ void day_step_land_tile(const DayArgs &a, const int b
 
 struct TileSmem {
     double h[2][TY + 4][TX + 4];
-    double ut[TY + 4][TX + 4];
+    double ut[TY + 4][TX + 4];       // raw drift components (multiplied by deltaT where they are read)
     double vt[TY + 4][TX + 4];
     double raw[4][TY + 2][TX + 2];   // adv0, adv1, div0, div1 after the NaN->0 fill
 };
 
 template <int DAY_THREADS>
 __device__ __forceinline__ void day_step_tile(const DayArgs &a, TileSmem &sm, const int by) {
+    pdl_launch_dependents();
     if (a.tile_land && a.tile_land[by * gridDim.x + blockIdx.x]) {
         day_step_land_tile<DAY_THREADS>(a, by);
         return;
@@ -385,6 +430,10 @@ __device__ __forceinline__ void day_step_strip(const DayArgs &a, const StripLink
         }
         __syncthreads();
     }
+    // Only now may the next day's CTAs take SM slots: every CTA of this launch that depends on another strip has what it
+    // needs, so this launch finishes on its own and nothing resident is waiting on a kernel that cannot be scheduled
+    // (several strips sharing one GPU would otherwise deadlock on slots held by early-launched, waiting grids).
+    pdl_launch_dependents();
     day_step_body<false, true, DAY_THREADS>(a, sm.h, sm.ut, sm.vt, sm.raw, by, &s);
     __threadfence_system();
     __syncthreads();

@@ -165,6 +165,7 @@ struct nesosim_ctx {
     long long ens_reruns = 0;
     uint8_t *tile_land_dev = nullptr;   // per day-kernel tile: no ocean cell inside (day_step_land_tile)
     bool land_shortcut = true;
+    bool pdl = true;                // programmatic dependent launch of the day kernels (NESOSIM_PDL=0 turns it off)
     int day_variant = 256;          // threads per CTA of the day kernel (256 x 2 cells or 512 x 1 cell)
     int path = 0;                   // 0 auto, 1 general per-day launches, 2 season-resident ensemble kernel
     int last_path = 0;              // which path the last run_season used (1 or 2)
@@ -263,6 +264,23 @@ int check_outputs(const nesosim_ctx *ctx, const nesosim_outputs *o) {
 
 // Layout of a strip's exchange block (nesosim_strip_setup): two mailboxes of [parity 2][layer 2][STRIP_GHOST][nx]
 // doubles, then the two flags, the two CTA counters and the time-out mark.
+// Day kernels are launched with programmatic stream serialization (see pdl_wait in day_kernels.cuh): the next day's
+// CTAs may start their day-independent prologue while this day's last CTAs finish.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_day_kernel(void (*kern)(KArgs...), dim3 grid, int threads, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 void strip_release(nesosim_ctx *ctx) {
     if (ctx->strip.ipc_up && ctx->strip.peer_up) cudaIpcCloseMemHandle(ctx->strip.peer_up);
     if (ctx->strip.ipc_dn && ctx->strip.peer_dn) cudaIpcCloseMemHandle(ctx->strip.peer_dn);
@@ -342,12 +360,12 @@ int launch_day(nesosim_ctx *ctx, int x, const double *P, const double *C, const 
     if (strip_step && ctx->strip.on && a.sw.dynamics && (ctx->strip.has_up || ctx->strip.has_dn)) {
         StripLink s;
         strip_link(ctx, x, grid, &s);
-        if (ctx->day_variant == 512) day_step_strip_kernel_512<<<grid, 512, 0, st>>>(a, s);
-        else day_step_strip_kernel<<<grid, 256, 0, st>>>(a, s);
+        if (ctx->day_variant == 512) CU(launch_day_kernel(day_step_strip_kernel_512, grid, 512, st, ctx->pdl, a, s));
+        else CU(launch_day_kernel(day_step_strip_kernel, grid, 256, st, ctx->pdl, a, s));
     } else if (ctx->day_variant == 512) {
-        day_step_kernel_512<<<grid, 512, 0, st>>>(a);
+        CU(launch_day_kernel(day_step_kernel_512, grid, 512, st, ctx->pdl, a));
     } else {
-        day_step_kernel<<<grid, 256, 0, st>>>(a);
+        CU(launch_day_kernel(day_step_kernel, grid, 256, st, ctx->pdl, a));
     }
     ctx->launches++;
     CU(cudaGetLastError());
@@ -846,6 +864,7 @@ int nesosim_create(const nesosim_config *cfg, const uint8_t *region_mask_host, n
     // development switches for A/B timing (both settings of each produce identical values)
     if (const char *v = std::getenv("NESOSIM_DAY_THREADS")) ctx->day_variant = std::atoi(v) == 512 ? 512 : 256;
     if (const char *v = std::getenv("NESOSIM_LAND_SHORTCUT")) ctx->land_shortcut = std::atoi(v) != 0;
+    if (const char *v = std::getenv("NESOSIM_PDL")) ctx->pdl = std::atoi(v) != 0;
     *out = ctx;
     return NESOSIM_OK;
 }

@@ -101,6 +101,10 @@ eng.close(); eng = None
 torch.cuda.empty_cache()
 dist.barrier()
 
+if "nccl" not in os.environ.get("ARMS", "one-gpu,peer,nccl"):
+    dist.destroy_process_group()
+    sys.exit(0)
+
 # ---- NCCL strips (host-driven exchange every day)
 def make(local_mask, num_days, dx_, forcing_local, params_row, ic_local):
     return domain.GpuStripStepper(local_mask, num_days, dx_, forcing_local, params_row, ic_local, device=local, atmlossInc=1)

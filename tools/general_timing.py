@@ -1,5 +1,5 @@
 """Throughput of the general per-day path (day_step_kernel) on the larger grids: single season, M members, for every
-build variant of the day kernel (NESOSIM_DAY_THREADS x NESOSIM_LAND_SHORTCUT), checking that all variants agree.
+build variant of the day kernel (NESOSIM_DAY_THREADS x NESOSIM_LAND_SHORTCUT x NESOSIM_PDL; VARIANTS=threads:shortcut:pdl,...), checking that all variants agree.
 usage: python tools/general_timing.py n days [members] [generated_days]"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -19,10 +19,11 @@ params = S.ensemble_params(M, seed=1)
 cells = M * n * n * (T - 1)
 land = float(np.mean((mask > 10) | (mask < 1)))
 first = None
-variants = [v.split(":") for v in os.environ.get("VARIANTS", "256:0,256:1,512:0,512:1").split(",")]
-for threads, shortcut in variants:
+variants = [(v.split(":") + ["1"])[:3] for v in os.environ.get("VARIANTS", "256:0,256:1,512:0,512:1").split(",")]
+for threads, shortcut, pdl in variants:
     os.environ["NESOSIM_DAY_THREADS"] = threads
     os.environ["NESOSIM_LAND_SHORTCUT"] = shortcut
+    os.environ["NESOSIM_PDL"] = pdl
     eng = SnowBudgetEngine(mask, T, dx, n_members=M, atmlossInc=1)
     eng.set_path("general")
     eng.set_forcing(F["precip"], F["conc"], F["wind"], F["drift"])
@@ -38,7 +39,7 @@ for threads, shortcut in variants:
     if first is None:
         first = digest
     print(json.dumps({"grid": [n, n], "days": T, "members": M, "land_fraction": round(land, 3), "threads": int(threads),
-                      "land_shortcut": int(shortcut), "ms_per_season": ms, "us_per_day": 1e3 * ms / (T - 1),
+                      "land_shortcut": int(shortcut), "pdl": int(pdl), "ms_per_season": ms, "us_per_day": 1e3 * ms / (T - 1),
                       "cell_days_per_s": cells / ms * 1e3, "algorithmic_GBs": cells * (96 + 41.0 / M) / ms / 1e6,
                       "frac_of_6551": cells * (96 + 41.0 / M) / ms / 1e6 / 6551, "same_digest_as_first": digest == first}),
           flush=True)
