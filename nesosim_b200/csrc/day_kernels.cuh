@@ -91,6 +91,134 @@ __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gmem_s
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// Raw advection / divergence of both layers (calcDynamics, NESOSIM.py:189-222, then fillMaskAndNaNWithZero) on the tile
+// grown by one cell, from the staged depth and raw-drift tiles; zero outside the grid (convolve's boundary='fill').
+template <bool INTERIOR, int DAY_THREADS>
+__device__ __forceinline__ void tile_raw_phase(const DayArgs &a, const int x0, const int y0, double (&s_h)[2][TY + 4][TX + 4],
+                                               double (&s_ut)[TY + 4][TX + 4], double (&s_vt)[TY + 4][TX + 4],
+                                               double (&s_raw)[4][TY + 2][TX + 2]) {
+    const int tid = threadIdx.x;
+    const int ny = a.ny, nx = a.nx;
+    const double dT = a.k.deltaT;
+    for (int i = tid; i < (TY + 2) * (TX + 2); i += DAY_THREADS) {
+        const int r = i / (TX + 2), c = i - r * (TX + 2);
+        const int gy = y0 + r - 1, gx = x0 + c - 1;
+        double adv0 = 0.0, adv1 = 0.0, div0 = 0.0, div1 = 0.0;   // zero padding of convolve(boundary='fill')
+        if (INTERIOR || (gy >= 0 && gy < ny && gx >= 0 && gx < nx)) {
+            const int sr = r + 1, sc = c + 1;
+            const double ut = mul(s_ut[sr][sc], dT), vt = mul(s_vt[sr][sc], dT);   // driftGday*deltaT
+            // centred difference with the constant divisor 2.*dx where no cell of the tile is a grid-edge cell
+            auto grad = [&](double fm, double fc, double fp, int idx, int n) {
+                return INTERIOR ? div_const(sub(fp, fm), a.g.two_dx) : gradient1d(fm, fc, fp, idx, n, a.g);
+            };
+            const double gxu = grad(mul(s_ut[sr][sc - 1], dT), ut, mul(s_ut[sr][sc + 1], dT), gx, nx);
+            const double gyv = grad(mul(s_vt[sr - 1][sc], dT), vt, mul(s_vt[sr + 1][sc], dT), gy, ny);
+#pragma unroll
+            for (int l = 0; l < 2; ++l) {
+                const double h = s_h[l][sr][sc];
+                const double gxh = grad(s_h[l][sr][sc - 1], h, s_h[l][sr][sc + 1], gx, nx);
+                const double gyh = grad(s_h[l][sr - 1][sc], h, s_h[l][sr + 1][sc], gy, ny);
+                const double dv = zero_if_nonfinite(div_term(h, gxu, gyv));
+                const double ad = zero_if_nonfinite(adv_term(ut, vt, gxh, gyh));
+                if (l == 0) { adv0 = ad; div0 = dv; } else { adv1 = ad; div1 = dv; }
+            }
+        }
+        s_raw[0][r][c] = adv0;
+        s_raw[1][r][c] = adv1;
+        s_raw[2][r][c] = div0;
+        s_raw[3][r][c] = div1;
+    }
+}
+
+// 3x3 smoothing of the four raw planes, the point-wise budget terms and the twelve stores of this thread's cells.
+template <bool INTERIOR, bool STRIP, int DAY_THREADS>
+__device__ __forceinline__ void tile_point_phase(const DayArgs &a, const int x0, const int y0, const int m,
+                                                 double (&s_h)[2][TY + 4][TX + 4], double (&s_raw)[4][TY + 2][TX + 2],
+                                                 const double *h0p, const double *h1p, const MemberCoef &mc,
+                                                 const double (&pf_P)[TY / (DAY_THREADS / TX)],
+                                                 const double (&pf_C)[TY / (DAY_THREADS / TX)],
+                                                 const double (&pf_W)[TY / (DAY_THREADS / TX)],
+                                                 const double (&pf_prev)[TY / (DAY_THREADS / TX)][9],
+                                                 const bool (&pf_land)[TY / (DAY_THREADS / TX)], const StripLink *sl) {
+    const int tid = threadIdx.x;
+    const int ny = a.ny, nx = a.nx;
+    const int tx = tid & (TX - 1);
+    const int gx = x0 + tx;
+    if (!INTERIOR && gx >= nx) return;
+#pragma unroll
+    for (int rr = 0; rr < TY / (DAY_THREADS / TX); ++rr) {
+        const int ty = (tid / TX) + rr * (DAY_THREADS / TX);
+        const int gy = y0 + ty;
+        if (!INTERIOR && gy >= ny) break;
+        const long long o = (long long)gy * nx + gx;
+        const bool land = pf_land[rr];
+
+        double adv0 = 0.0, adv1 = 0.0, div0 = 0.0, div1 = 0.0, h0, h1;
+        if (a.sw.dynamics) {
+            double sm[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const double top = conv3x3(a.w, [&](int ii, int jj) { return s_raw[p][ty + ii][tx + jj]; });
+                sm[p] = mask_nan(div_const(top, a.conv_div), land, false);   // NESOSIM.py:276-284
+            }
+            adv0 = sm[0]; adv1 = sm[1]; div0 = sm[2]; div1 = sm[3];
+            h0 = s_h[0][ty + 2][tx + 2];
+            h1 = s_h[1][ty + 2][tx + 2];
+        } else {
+            h0 = h0p[o];
+            h1 = h1p[o];
+        }
+
+        const double P = pf_P[rr], C = pf_C[rr], W = pf_W[rr];
+        const double pd = div_const(P, a.rho_new);           // precipDayT/snowDensityNew (NESOSIM.py:260)
+        const double acc = mul(pd, C);                       // NESOSIM.py:263
+        const double oc = -mul(pd, sub(1.0, C));             // NESOSIM.py:267
+        const double wt = wind_flag(W, mc.wpt);
+        const double lead = a.sw.leadloss ? lead_loss(wt, h0, W, C, mc, a.k) : 0.0;
+        const double atm = a.sw.atmloss ? atm_loss(wt, h0, W, mc, a.k) : 0.0;
+        double wpl = 0.0, wpg = 0.0, wpn = 0.0;
+        if (a.sw.windpack) wind_packing(wt, h0, mc, a.k, wpl, wpg, wpn);
+
+        auto prev = [&](int v) { return pf_prev[rr][v - V_ACC]; };
+        auto store = [&](int v, double val) {
+            if (a.next[v]) a.next[v][(long long)m * a.next_stride[v] + o] = val;
+        };
+        store(V_ACC, add(prev(V_ACC), acc));
+        store(V_OCEAN, add(prev(V_OCEAN), oc));
+        store(V_ADV, add(add(prev(V_ADV), adv0), adv1));     // NESOSIM.py:290
+        store(V_DIV, add(add(prev(V_DIV), div0), div1));     // NESOSIM.py:291
+        store(V_LEAD, add(prev(V_LEAD), lead));
+        store(V_ATM, add(prev(V_ATM), atm));
+        store(V_WPL, add(prev(V_WPL), wpl));
+        store(V_WPG, add(prev(V_WPG), wpg));
+        store(V_WP, add(prev(V_WP), wpn));
+
+        // NESOSIM.py:327,329 (left to right), then fill_nan_no_negative (332-333)
+        double h0n = add(add(add(add(add(add(h0, acc), wpl), lead), atm), adv0), div0);
+        double h1n = add(add(add(h1, wpg), adv1), div1);
+        h0n = mask_nan(h0n, land, true);
+        h1n = mask_nan(h1n, land, true);
+        store(V_H0, h0n);
+        store(V_H1, h1n);
+        if (STRIP) {      // first / last owned rows -> the neighbour's mailbox for slot x+1
+            const long long par = (long long)((a.x + 1) & 1) * 2 * STRIP_GHOST;
+            if (sl->has_up && gy >= STRIP_GHOST && gy < 2 * STRIP_GHOST) {
+                const long long mo = (par + (gy - STRIP_GHOST)) * nx + gx;
+                sl->peer_up_mail[mo] = h0n;
+                sl->peer_up_mail[mo + (long long)STRIP_GHOST * nx] = h1n;
+            }
+            if (sl->has_dn && gy >= ny - 2 * STRIP_GHOST && gy < ny - STRIP_GHOST) {
+                const long long mo = (par + (gy - (ny - 2 * STRIP_GHOST))) * nx + gx;
+                sl->peer_dn_mail[mo] = h0n;
+                sl->peer_dn_mail[mo + (long long)STRIP_GHOST * nx] = h1n;
+            }
+        }
+        const double rho = a.sw.clim ? density_clim(a.rho_new.c, h0n, h1n, C, land, a.k)
+                                     : density_variable(h0n, h1n, land, a.k);
+        store(V_DENS, rho);
+    }
+}
+
 // INTERIOR: the tile with its two-cell halo lies inside the grid and none of its raw-dynamics cells is a grid-edge
 // cell, so there are no bounds tests, every difference is centred and the divisor is a launch constant (the
 // overwhelming majority of the CTAs on the 25 km and 5 km grids).
@@ -180,113 +308,11 @@ __device__ __forceinline__ void day_step_body(const DayArgs &a, double (&s_h)[2]
         }
         cp_async_wait_all();
         __syncthreads();
-        const double dT = a.k.deltaT;
-        for (int i = tid; i < (TY + 2) * (TX + 2); i += DAY_THREADS) {
-            const int r = i / (TX + 2), c = i - r * (TX + 2);
-            const int gy = y0 + r - 1, gx = x0 + c - 1;
-            double adv0 = 0.0, adv1 = 0.0, div0 = 0.0, div1 = 0.0;   // zero padding of convolve(boundary='fill')
-            if (INTERIOR || (gy >= 0 && gy < ny && gx >= 0 && gx < nx)) {
-                const int sr = r + 1, sc = c + 1;
-                const double ut = mul(s_ut[sr][sc], dT), vt = mul(s_vt[sr][sc], dT);   // driftGday*deltaT
-                // centred difference with the constant divisor 2.*dx where no cell of the tile is a grid-edge cell
-                auto grad = [&](double fm, double fc, double fp, int idx, int n) {
-                    return INTERIOR ? div_const(sub(fp, fm), a.g.two_dx) : gradient1d(fm, fc, fp, idx, n, a.g);
-                };
-                const double gxu = grad(mul(s_ut[sr][sc - 1], dT), ut, mul(s_ut[sr][sc + 1], dT), gx, nx);
-                const double gyv = grad(mul(s_vt[sr - 1][sc], dT), vt, mul(s_vt[sr + 1][sc], dT), gy, ny);
-#pragma unroll
-                for (int l = 0; l < 2; ++l) {
-                    const double h = s_h[l][sr][sc];
-                    const double gxh = grad(s_h[l][sr][sc - 1], h, s_h[l][sr][sc + 1], gx, nx);
-                    const double gyh = grad(s_h[l][sr - 1][sc], h, s_h[l][sr + 1][sc], gy, ny);
-                    const double dv = zero_if_nonfinite(div_term(h, gxu, gyv));
-                    const double ad = zero_if_nonfinite(adv_term(ut, vt, gxh, gyh));
-                    if (l == 0) { adv0 = ad; div0 = dv; } else { adv1 = ad; div1 = dv; }
-                }
-            }
-            s_raw[0][r][c] = adv0;
-            s_raw[1][r][c] = adv1;
-            s_raw[2][r][c] = div0;
-            s_raw[3][r][c] = div1;
-        }
+        tile_raw_phase<INTERIOR, DAY_THREADS>(a, x0, y0, s_h, s_ut, s_vt, s_raw);
         __syncthreads();
     }
 
-    const int tx = tid & (TX - 1);
-    const int gx = x0 + tx;
-    if (!INTERIOR && gx >= nx) return;
-#pragma unroll
-    for (int rr = 0; rr < TY / (DAY_THREADS / TX); ++rr) {
-        const int ty = (tid / TX) + rr * (DAY_THREADS / TX);
-        const int gy = y0 + ty;
-        if (!INTERIOR && gy >= ny) break;
-        const long long o = (long long)gy * nx + gx;
-        const bool land = pf_land[rr];
-
-        double adv0 = 0.0, adv1 = 0.0, div0 = 0.0, div1 = 0.0, h0, h1;
-        if (a.sw.dynamics) {
-            double sm[4];
-#pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                const double top = conv3x3(a.w, [&](int ii, int jj) { return s_raw[p][ty + ii][tx + jj]; });
-                sm[p] = mask_nan(div_const(top, a.conv_div), land, false);   // NESOSIM.py:276-284
-            }
-            adv0 = sm[0]; adv1 = sm[1]; div0 = sm[2]; div1 = sm[3];
-            h0 = s_h[0][ty + 2][tx + 2];
-            h1 = s_h[1][ty + 2][tx + 2];
-        } else {
-            h0 = h0p[o];
-            h1 = h1p[o];
-        }
-
-        const double P = pf_P[rr], C = pf_C[rr], W = pf_W[rr];
-        const double pd = div_const(P, a.rho_new);           // precipDayT/snowDensityNew (NESOSIM.py:260)
-        const double acc = mul(pd, C);                       // NESOSIM.py:263
-        const double oc = -mul(pd, sub(1.0, C));             // NESOSIM.py:267
-        const double wt = wind_flag(W, mc.wpt);
-        const double lead = a.sw.leadloss ? lead_loss(wt, h0, W, C, mc, a.k) : 0.0;
-        const double atm = a.sw.atmloss ? atm_loss(wt, h0, W, mc, a.k) : 0.0;
-        double wpl = 0.0, wpg = 0.0, wpn = 0.0;
-        if (a.sw.windpack) wind_packing(wt, h0, mc, a.k, wpl, wpg, wpn);
-
-        auto prev = [&](int v) { return pf_prev[rr][v - V_ACC]; };
-        auto store = [&](int v, double val) {
-            if (a.next[v]) a.next[v][(long long)m * a.next_stride[v] + o] = val;
-        };
-        store(V_ACC, add(prev(V_ACC), acc));
-        store(V_OCEAN, add(prev(V_OCEAN), oc));
-        store(V_ADV, add(add(prev(V_ADV), adv0), adv1));     // NESOSIM.py:290
-        store(V_DIV, add(add(prev(V_DIV), div0), div1));     // NESOSIM.py:291
-        store(V_LEAD, add(prev(V_LEAD), lead));
-        store(V_ATM, add(prev(V_ATM), atm));
-        store(V_WPL, add(prev(V_WPL), wpl));
-        store(V_WPG, add(prev(V_WPG), wpg));
-        store(V_WP, add(prev(V_WP), wpn));
-
-        // NESOSIM.py:327,329 (left to right), then fill_nan_no_negative (332-333)
-        double h0n = add(add(add(add(add(add(h0, acc), wpl), lead), atm), adv0), div0);
-        double h1n = add(add(add(h1, wpg), adv1), div1);
-        h0n = mask_nan(h0n, land, true);
-        h1n = mask_nan(h1n, land, true);
-        store(V_H0, h0n);
-        store(V_H1, h1n);
-        if (STRIP) {      // first / last owned rows -> the neighbour's mailbox for slot x+1
-            const long long par = (long long)((a.x + 1) & 1) * 2 * STRIP_GHOST;
-            if (sl->has_up && gy >= STRIP_GHOST && gy < 2 * STRIP_GHOST) {
-                const long long mo = (par + (gy - STRIP_GHOST)) * nx + gx;
-                sl->peer_up_mail[mo] = h0n;
-                sl->peer_up_mail[mo + (long long)STRIP_GHOST * nx] = h1n;
-            }
-            if (sl->has_dn && gy >= ny - 2 * STRIP_GHOST && gy < ny - STRIP_GHOST) {
-                const long long mo = (par + (gy - (ny - 2 * STRIP_GHOST))) * nx + gx;
-                sl->peer_dn_mail[mo] = h0n;
-                sl->peer_dn_mail[mo + (long long)STRIP_GHOST * nx] = h1n;
-            }
-        }
-        const double rho = a.sw.clim ? density_clim(a.rho_new.c, h0n, h1n, C, land, a.k)
-                                     : density_variable(h0n, h1n, land, a.k);
-        store(V_DENS, rho);
-    }
+    tile_point_phase<INTERIOR, STRIP, DAY_THREADS>(a, x0, y0, m, s_h, s_raw, h0p, h1p, mc, pf_P, pf_C, pf_W, pf_prev, pf_land, sl);
 }
 
 // A tile without a single ocean cell (more than half of the polar grid is land, and it comes in large blocks).  From
@@ -297,12 +323,12 @@ __device__ __forceinline__ void day_step_body(const DayArgs &a, double (&s_h)[2]
 // Only used for a slot this library wrote itself in the same call (x > first_step): a caller-provided slot may hold
 // finite depths on land (the IC does), and then the general code below is the reference's arithmetic.
 template <int DAY_THREADS>
-__device__ __forceinline__ void day_step_land_tile(const DayArgs &a, const int by) {
+__device__ __forceinline__ void day_step_land_tile(const DayArgs &a, const int bx, const int by) {
     const int m = blockIdx.z;
     const int fset = a.member_set ? a.member_set[m] : 0;
     if (a.set_steps && a.x >= a.set_steps[fset]) return;
     const long long fo = (long long)fset * a.set_stride;
-    const int gx = blockIdx.x * TX + (threadIdx.x & (TX - 1));
+    const int gx = bx * TX + (threadIdx.x & (TX - 1));
     if (gx >= a.nx) return;
     const double nan = qnan();
     constexpr int CPT = TY / (DAY_THREADS / TX);
@@ -355,7 +381,7 @@ template <int DAY_THREADS>
 __device__ __forceinline__ void day_step_tile(const DayArgs &a, TileSmem &sm, const int by) {
     pdl_launch_dependents();
     if (a.tile_land && a.tile_land[by * gridDim.x + blockIdx.x]) {
-        day_step_land_tile<DAY_THREADS>(a, by);
+        day_step_land_tile<DAY_THREADS>(a, blockIdx.x, by);
         return;
     }
     auto &s_h = sm.h;

@@ -849,17 +849,19 @@ int nesosim_create(const nesosim_config *cfg, const uint8_t *region_mask_host, n
         nesosim_destroy(ctx);
         return cuda_fail(e, "nesosim_create allocation");
     }
-    // CTA shape and land shortcut by the number of CTAs per day (measured on a B200, tools/general_timing.py): a day of
-    // one wave or less is as long as the dependent chain inside one CTA -- 512 threads x 1 cell shorten it when an SM
-    // holds a single CTA (100 km: 12.1 -> 10.6 us/day), and the land-tile lookup only adds a load to that chain
-    // (25 km: 13.5 -> 15.2 us/day); with many waves throughput counts (5 km: 266 -> 194 us/day with both).
+    // CTA shape and land shortcut by the number of CTAs per day (measured on a B200, tools/general_timing.py,
+    // profiles/r01_general_path_variants*.jsonl): a day of one wave or less is as long as the dependent chain inside one
+    // CTA -- 512 threads x 1 cell shorten it when an SM holds a single CTA (100 km: 8.2 -> 7.7 us/day); with about two
+    // CTAs per SM 256 threads x 2 cells are faster (25 km: 9.5 vs 12.4 us/day); with many waves throughput counts and
+    // the two shapes tie (5 km: 171 us/day).  The land-tile shortcut is looked up before the programmatic-launch wait,
+    // so it costs nothing on the chain and is on whenever there is more than one CTA per SM.
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
         const long long ctas = (long long)tgx * tgy * cfg->n_members;
         if (ctas <= sms) { ctx->day_variant = 512; ctx->land_shortcut = false; }
         else if (ctas >= 8LL * sms) { ctx->day_variant = 512; ctx->land_shortcut = true; }
-        else { ctx->day_variant = 256; ctx->land_shortcut = false; }
+        else { ctx->day_variant = 256; ctx->land_shortcut = true; }
     }
     // development switches for A/B timing (both settings of each produce identical values)
     if (const char *v = std::getenv("NESOSIM_DAY_THREADS")) ctx->day_variant = std::atoi(v) == 512 ? 512 : 256;

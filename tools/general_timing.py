@@ -9,9 +9,13 @@ from nesosim_b200 import synthetic as S
 from nesosim_b200.engine import SnowBudgetEngine
 n = int(sys.argv[1]); T = int(sys.argv[2]); M = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 G = int(sys.argv[4]) if len(sys.argv) > 4 else min(T, 8)
-dx = {90: 100000, 357: 25000, 1785: 5000}[n]
+dx = {90: 100000, 357: 25000, 1785: 5000}.get(n, 5000)
 mask = S.region_mask(dx=dx) if n in (90, 357) else S.region_mask(shape=(n, n), kind="disc")
 gen = S.make_season(mask, G, seed=1)
+if os.environ.get("MASK") == "land":      # decomposition experiments: a grid of land tiles only / of ocean tiles only
+    mask = np.full_like(mask, 11)
+elif os.environ.get("MASK") == "ocean":
+    mask = np.full_like(mask, 8)
 idx = np.arange(T) % G
 F = {k: (v if v is None else torch.from_numpy(v[idx]).cuda()) for k, v in gen.items()}
 ic = S.make_ic(mask, seed=1)
