@@ -225,9 +225,9 @@ __device__ __forceinline__ void tile_point_phase(const DayArgs &a, const int x0,
 template <bool INTERIOR, bool STRIP = false, int DAY_THREADS = 256>
 __device__ __forceinline__ void day_step_body(const DayArgs &a, double (&s_h)[2][TY + 4][TX + 4], double (&s_ut)[TY + 4][TX + 4],
                                               double (&s_vt)[TY + 4][TX + 4], double (&s_raw)[4][TY + 2][TX + 2],
-                                              const int by, const StripLink *sl = nullptr) {
+                                              const int bx, const int by, const StripLink *sl = nullptr) {
     const int m = blockIdx.z;
-    const int x0 = blockIdx.x * TX, y0 = by * TY;     // `by`: tile row (blockIdx.y, permuted by the strip kernel)
+    const int x0 = bx * TX, y0 = by * TY;     // (bx, by): the tile (blockIdx, or what a strip / season CTA picked)
     const int tid = threadIdx.x;
     const int ny = a.ny, nx = a.nx;
     const int fset = a.member_set ? a.member_set[m] : 0;
@@ -378,31 +378,31 @@ struct TileSmem {
 };
 
 template <int DAY_THREADS>
-__device__ __forceinline__ void day_step_tile(const DayArgs &a, TileSmem &sm, const int by) {
+__device__ __forceinline__ void day_step_tile(const DayArgs &a, TileSmem &sm, const int bx, const int by) {
     pdl_launch_dependents();
-    if (a.tile_land && a.tile_land[by * gridDim.x + blockIdx.x]) {
-        day_step_land_tile<DAY_THREADS>(a, blockIdx.x, by);
+    if (a.tile_land && a.tile_land[by * ((a.nx + TX - 1) / TX) + bx]) {
+        day_step_land_tile<DAY_THREADS>(a, bx, by);
         return;
     }
     auto &s_h = sm.h;
     auto &s_ut = sm.ut;
     auto &s_vt = sm.vt;
     auto &s_raw = sm.raw;
-    const int x0 = blockIdx.x * TX, y0 = by * TY;
+    const int x0 = bx * TX, y0 = by * TY;
     const bool interior = x0 >= 2 && y0 >= 2 && x0 + TX + 2 <= a.nx && y0 + TY + 2 <= a.ny;
-    if (interior) day_step_body<true, false, DAY_THREADS>(a, s_h, s_ut, s_vt, s_raw, by);
-    else day_step_body<false, false, DAY_THREADS>(a, s_h, s_ut, s_vt, s_raw, by);
+    if (interior) day_step_body<true, false, DAY_THREADS>(a, s_h, s_ut, s_vt, s_raw, bx, by);
+    else day_step_body<false, false, DAY_THREADS>(a, s_h, s_ut, s_vt, s_raw, bx, by);
 }
 
 // Two builds of the same tile code: 256 threads x 2 cells (large grids: fewer, fatter threads) and 512 threads x 1
 // cell (small grids, where a day is one wave of CTAs and its length is the dependent chain inside a CTA).
 __global__ void __launch_bounds__(256) day_step_kernel(const __grid_constant__ DayArgs a) {
     __shared__ TileSmem sm;
-    day_step_tile<256>(a, sm, blockIdx.y);
+    day_step_tile<256>(a, sm, blockIdx.x, blockIdx.y);
 }
 __global__ void __launch_bounds__(512, 2) day_step_kernel_512(const __grid_constant__ DayArgs a) {
     __shared__ TileSmem sm;
-    day_step_tile<512>(a, sm, blockIdx.y);
+    day_step_tile<512>(a, sm, blockIdx.x, blockIdx.y);
 }
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -446,7 +446,7 @@ __device__ __forceinline__ void day_step_strip(const DayArgs &a, const StripLink
     const bool top = s.has_up && strip_top_cta(y0), bot = s.has_dn && strip_bot_cta(y0, a.ny);
     __shared__ TileSmem sm;
     if (!top && !bot) {
-        day_step_tile<DAY_THREADS>(a, sm, by);
+        day_step_tile<DAY_THREADS>(a, sm, blockIdx.x, by);
         return;
     }
     if (s.use_mail) {
@@ -460,7 +460,7 @@ __device__ __forceinline__ void day_step_strip(const DayArgs &a, const StripLink
     // needs, so this launch finishes on its own and nothing resident is waiting on a kernel that cannot be scheduled
     // (several strips sharing one GPU would otherwise deadlock on slots held by early-launched, waiting grids).
     pdl_launch_dependents();
-    day_step_body<false, true, DAY_THREADS>(a, sm.h, sm.ut, sm.vt, sm.raw, by, &s);
+    day_step_body<false, true, DAY_THREADS>(a, sm.h, sm.ut, sm.vt, sm.raw, blockIdx.x, by, &s);
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {

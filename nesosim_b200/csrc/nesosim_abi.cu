@@ -326,10 +326,8 @@ void strip_link(const nesosim_ctx *ctx, int x, dim3 grid, StripLink *s) {
     s->timeout_ns = (unsigned long long)(ctx->strip.timeout_s * 1e9);
 }
 
-int launch_day(nesosim_ctx *ctx, int x, const double *P, const double *C, const double *W, const double *U,
-               const double *V, double rho_new, const nesosim_outputs *o, int m0, int mcount, cudaStream_t st,
-               bool strip_step = false, bool land_ok = false) {
-    DayArgs a;
+void fill_day_args(nesosim_ctx *ctx, int x, const double *P, const double *C, const double *W, const double *U,
+                   const double *V, double rho_new, const nesosim_outputs *o, int m0, bool land_ok, DayArgs &a) {
     a.tile_land = (land_ok && ctx->land_shortcut) ? ctx->tile_land_dev : nullptr;
     a.ny = ctx->cfg.ny;
     a.nx = ctx->cfg.nx;
@@ -356,6 +354,13 @@ int launch_day(nesosim_ctx *ctx, int x, const double *P, const double *C, const 
     a.set_steps = ctx->set_steps_dev;
     a.set_stride = (long long)ctx->cfg.num_days * ctx->plane;
     a.x = x;
+}
+
+int launch_day(nesosim_ctx *ctx, int x, const double *P, const double *C, const double *W, const double *U,
+               const double *V, double rho_new, const nesosim_outputs *o, int m0, int mcount, cudaStream_t st,
+               bool strip_step = false, bool land_ok = false) {
+    DayArgs a;
+    fill_day_args(ctx, x, P, C, W, U, V, rho_new, o, m0, land_ok, a);
     dim3 grid((a.nx + TX - 1) / TX, (a.ny + TY - 1) / TY, mcount);
     if (strip_step && ctx->strip.on && a.sw.dynamics && (ctx->strip.has_up || ctx->strip.has_dn)) {
         StripLink s;
