@@ -346,12 +346,21 @@ def run_ours(args):
         v, cores, sample, _ = cpu_baseline(1)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
+    other = None
+    if rank == 0 and world == 1 and not args.no_e2e and not args.no_other:
+        try:
+            del out
+            torch.cuda.empty_cache()
+            other = run_other_grids(peak)
+        except Exception as ex:
+            other = {"error": str(ex)[:200]}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(M, world, {"kernel_path": eng.last_path(), "variant": args.variant or "default"}), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-                "roofline": roofline, "cpu_baseline": cpu, "e2e_final_products": e2e_final}
+                "roofline": roofline, "cpu_baseline": cpu, "e2e_final_products": e2e_final, "other_grids": other}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
@@ -439,6 +448,46 @@ def run_e2e_final(args, eng, forcing, params, ic, dev_out, world, cells_per_step
                        "precipitation, wind), masked and rounded on the device"}
 
 
+def run_other_grids(peak):
+    """The other single-GPU configurations of BASELINE.json on the general per-day path (one member, full 12-array
+    output, forcing resident): the 25 km season and a short stretch of the 5 km grid.  Reported as an extra key next to
+    the headline workload, not as bench lines of their own; algorithmic bytes = 96 + 41 per cell-day (M = 1)."""
+    import torch
+    from nesosim_b200 import synthetic as S
+    from nesosim_b200.engine import SnowBudgetEngine
+    rows = []
+    for name, n, dx, T, gen_days in (("25 km Arctic grid, single season (general day kernel)", 357, 25000, NUM_DAYS, 8),
+                                     ("5 km pan-Arctic grid, 40 steps (general day kernel)", 1785, 5000, 41, 4)):
+        mask = S.region_mask(dx=dx) if n == 357 else S.region_mask(shape=(n, n), kind="disc")
+        gen = S.make_season(mask, gen_days, seed=7)
+        idx = np.arange(T) % gen_days
+        f = {k: torch.from_numpy(v[idx]).cuda() for k, v in gen.items() if v is not None}
+        ic = S.make_ic(mask, seed=7)
+        eng = SnowBudgetEngine(mask, T, dx, n_members=1, atmlossInc=1)
+        eng.set_path("general")
+        eng.set_forcing(f["precip"], f["conc"], f["wind"], f["drift"])
+        out = eng.alloc_outputs()
+        best = None
+        for rep in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            eng.run_season([[5.8e-7, 5., 1.45e-7, 2.2e-8]], ic, out)
+            e1.record()
+            torch.cuda.synchronize()
+            if rep:
+                best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
+        cells = n * n * (T - 1)
+        gbs = cells * 137.0 / (best * 1e-3) / 1e9
+        rows.append({"workload": name, "grid": [n, n], "num_days": T, "value": cells / (best * 1e-3), "unit": UNIT,
+                     "us_per_day": 1e3 * best / (T - 1), "kernel": "day_step_kernel", "launches": T - 1,
+                     "roofline_frac_algorithmic": gbs / peak, "data": "synthetic (%d generated days repeated)" % gen_days})
+        del out, f
+        eng.close()
+        torch.cuda.empty_cache()
+    return rows
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -452,6 +501,7 @@ def main():
     ap.add_argument("--variant", default="", help="season-resident kernel build variant (NESOSIM_ENS_VARIANT)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--no-other", action="store_true", help="skip the 25 km / 5 km general-path figures")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
