@@ -25,7 +25,9 @@ struct DayArgs {
     const uint8_t *mask;
     const double *prev[NVAR];              // slot x   (prev[V_DENS] unused)
     double *next[NVAR];                    // slot x+1 (NULL: not stored)
-    long long prev_stride[NVAR], next_stride[NVAR];   // elements between members
+    // elements between members: one stride for the two depth layers, one for the ten [T][ny][nx] arrays (the host
+    // launches member by member in the rare case where the arrays of one kind do not share a stride)
+    long long depth_mstride, plane_mstride;
     const MemberCoef *coef;                // device [M]
     ModelConsts k;
     GradConsts g;
@@ -180,8 +182,9 @@ __device__ __forceinline__ void tile_point_phase(const DayArgs &a, const int x0,
         if (a.sw.windpack) wind_packing(wt, h0, mc, a.k, wpl, wpg, wpn);
 
         auto prev = [&](int v) { return pf_prev[rr][v - V_ACC]; };
-        auto store = [&](int v, double val) {
-            if (a.next[v]) a.next[v][(long long)m * a.next_stride[v] + o] = val;
+        const long long ip = (long long)m * a.plane_mstride + o, id = (long long)m * a.depth_mstride + o;
+        auto store = [&](int v, double val) {       // only the density output is optional
+            if (v != V_DENS || a.next[v]) a.next[v][(v == V_H0 || v == V_H1) ? id : ip] = val;
         };
         store(V_ACC, add(prev(V_ACC), acc));
         store(V_OCEAN, add(prev(V_OCEAN), oc));
@@ -234,8 +237,8 @@ __device__ __forceinline__ void day_step_body(const DayArgs &a, double (&s_h)[2]
     if (a.set_steps && a.x >= a.set_steps[fset]) return;      // this member's season is over (whole CTA)
     const long long fo = (long long)fset * a.set_stride;
     const double *aP = a.P + fo, *aC = a.C + fo, *aW = a.W + fo, *aU = a.U + 2 * fo, *aV = a.V + 2 * fo;
-    const double *h0p = a.prev[V_H0] + (long long)m * a.prev_stride[V_H0];
-    const double *h1p = a.prev[V_H1] + (long long)m * a.prev_stride[V_H1];
+    const double *h0p = a.prev[V_H0] + (long long)m * a.depth_mstride;
+    const double *h1p = a.prev[V_H1] + (long long)m * a.depth_mstride;
 
     // The point-wise inputs of this thread's cells (forcing, mask, yesterday's nine accumulators) are requested
     // before anything else: they land while the tiles are staged and the raw dynamics computed, instead of each
@@ -279,9 +282,9 @@ __device__ __forceinline__ void day_step_body(const DayArgs &a, double (&s_h)[2]
 #pragma unroll
         for (int v = 0; v < 9; ++v) pf_prev[rr][v] = 0.0;
         if (INTERIOR || (pgx < nx && gy < ny)) {
-            const long long o = (long long)gy * nx + pgx;
+            const long long ip = (long long)m * a.plane_mstride + (long long)gy * nx + pgx;
 #pragma unroll
-            for (int v = 0; v < 9; ++v) pf_prev[rr][v] = a.prev[V_ACC + v][(long long)m * a.prev_stride[V_ACC + v] + o];
+            for (int v = 0; v < 9; ++v) pf_prev[rr][v] = a.prev[V_ACC + v][ip];
         }
     }
 
@@ -349,9 +352,10 @@ __device__ __forceinline__ void day_step_land_tile(const DayArgs &a, const int b
         const int gy = by * TY + (threadIdx.x / TX) + rr * (DAY_THREADS / TX);
         if (gy >= a.ny) break;
         const long long o = (long long)gy * a.nx + gx;
-        auto prev = [&](int v) { return a.prev[v][(long long)m * a.prev_stride[v] + o]; };
+        const long long ip = (long long)m * a.plane_mstride + o, id = (long long)m * a.depth_mstride + o;
+        auto prev = [&](int v) { return a.prev[v][ip]; };
         auto store = [&](int v, double val) {
-            if (a.next[v]) a.next[v][(long long)m * a.next_stride[v] + o] = val;
+            if (v != V_DENS || a.next[v]) a.next[v][(v == V_H0 || v == V_H1) ? id : ip] = val;
         };
         const double pacc = prev(V_ACC), poc = prev(V_OCEAN);
         const double pd = div_const(P[rr], a.rho_new);

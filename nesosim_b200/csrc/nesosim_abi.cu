@@ -326,8 +326,12 @@ void strip_link(const nesosim_ctx *ctx, int x, dim3 grid, StripLink *s) {
     s->timeout_ns = (unsigned long long)(ctx->strip.timeout_s * 1e9);
 }
 
-void fill_day_args(nesosim_ctx *ctx, int x, const double *P, const double *C, const double *W, const double *U,
+// Returns false when the arrays of one kind (depth layers / plane arrays) do not share one member stride (some outputs
+// given by the caller, others in the internal scratch): such a step is launched member by member.
+bool fill_day_args(nesosim_ctx *ctx, int x, const double *P, const double *C, const double *W, const double *U,
                    const double *V, double rho_new, const nesosim_outputs *o, int m0, bool land_ok, DayArgs &a) {
+    bool uniform = true;
+    a.depth_mstride = a.plane_mstride = -1;
     a.tile_land = (land_ok && ctx->land_shortcut) ? ctx->tile_land_dev : nullptr;
     a.ny = ctx->cfg.ny;
     a.nx = ctx->cfg.nx;
@@ -338,8 +342,12 @@ void fill_day_args(nesosim_ctx *ctx, int x, const double *P, const double *C, co
         long long ps, ns;
         slot_ptr(ctx, o, v, x, m0, &pp, &ps);
         slot_ptr(ctx, o, v, x + 1, m0, &np_, &ns);
-        a.prev[v] = pp; a.prev_stride[v] = ps;
-        a.next[v] = np_; a.next_stride[v] = ns;
+        a.prev[v] = pp;
+        a.next[v] = np_;
+        if (v == V_DENS && !o->density) continue;        // never read, not stored
+        long long &want = (v == V_H0 || v == V_H1) ? a.depth_mstride : a.plane_mstride;
+        if (want < 0) want = ns;
+        else if (want != ns) uniform = false;
     }
     if (!o->density) a.next[V_DENS] = nullptr;
     a.coef = ctx->coef_dev + m0;
@@ -354,13 +362,25 @@ void fill_day_args(nesosim_ctx *ctx, int x, const double *P, const double *C, co
     a.set_steps = ctx->set_steps_dev;
     a.set_stride = (long long)ctx->cfg.num_days * ctx->plane;
     a.x = x;
+    return uniform;
 }
 
 int launch_day(nesosim_ctx *ctx, int x, const double *P, const double *C, const double *W, const double *U,
                const double *V, double rho_new, const nesosim_outputs *o, int m0, int mcount, cudaStream_t st,
                bool strip_step = false, bool land_ok = false) {
     DayArgs a;
-    fill_day_args(ctx, x, P, C, W, U, V, rho_new, o, m0, land_ok, a);
+    if (!fill_day_args(ctx, x, P, C, W, U, V, rho_new, o, m0, land_ok, a) && mcount > 1) {
+        for (int mm = 0; mm < mcount; ++mm) {            // mixed strides: one member per launch, pointers pre-offset
+            nesosim_outputs om = *o;
+            double **ptrs[] = {&om.snowDepths, &om.density, &om.snowAcc, &om.snowOcean, &om.snowAdv, &om.snowDiv, &om.snowLead,
+                               &om.snowAtm, &om.snowWindPackLoss, &om.snowWindPackGain, &om.snowWindPack};
+            for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); ++i)
+                if (*ptrs[i]) *ptrs[i] += (long long)mm * (i == 0 ? o->depth_member_stride : o->plane_member_stride);
+            int rc = launch_day(ctx, x, P, C, W, U, V, rho_new, &om, m0 + mm, 1, st, strip_step, land_ok);
+            if (rc) return rc;
+        }
+        return NESOSIM_OK;
+    }
     dim3 grid((a.nx + TX - 1) / TX, (a.ny + TY - 1) / TY, mcount);
     if (strip_step && ctx->strip.on && a.sw.dynamics && (ctx->strip.has_up || ctx->strip.has_dn)) {
         StripLink s;
