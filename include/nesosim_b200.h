@@ -121,7 +121,9 @@ int nesosim_step_day(nesosim_ctx *ctx, int x, const double *conc_dev, const doub
  * to the device, runs the season, copies every non-NULL output back, synchronises.  This is the call
  * bench.py times for the end-to-end figure.  `out_host` strides are in elements like nesosim_outputs.
  * Members are processed in batches so that device and pinned staging memory stay bounded; bytes moved are
- * reported through h2d_bytes / d2h_bytes when non-NULL. */
+ * reported through h2d_bytes / d2h_bytes when non-NULL.  snowAcc and snowOcean do not depend on the member (forcing
+ * only, NESOSIM.py:263-270): with one shared forcing a single copy crosses the link and host threads replicate it into
+ * every member's slot of the caller's arrays. */
 int nesosim_run_season_host(nesosim_ctx *ctx, const double *precip, const double *conc, const double *wind,
                             const double *drift, const double *rho_clim,
                             const nesosim_member_params *params, const double *ic, int ic_per_member,

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/nesosim_b200.h"
@@ -134,6 +135,7 @@ struct HostPath {
     int batch = 0;
     cudaStream_t compute = nullptr, copy = nullptr;
     cudaEvent_t done[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr};
+    cudaEvent_t shared_ready = nullptr;   // member 0's snowAcc / snowOcean have reached the host
     size_t ic_elems = 0;
 };
 
@@ -917,6 +919,7 @@ int nesosim_destroy(nesosim_ctx *ctx) {
         if (ctx->hp.done[i]) cudaEventDestroy(ctx->hp.done[i]);
         if (ctx->hp.drained[i]) cudaEventDestroy(ctx->hp.drained[i]);
     }
+    if (ctx->hp.shared_ready) cudaEventDestroy(ctx->hp.shared_ready);
     if (ctx->hp.compute) cudaStreamDestroy(ctx->hp.compute);
     if (ctx->hp.copy) cudaStreamDestroy(ctx->hp.copy);
     delete ctx;
