@@ -469,6 +469,27 @@ def test_outputs_subset_uses_internal_state(cuda):
         assert cuda.equal(full[n].nan_to_num(nan=-7.0), part[n].nan_to_num(nan=-7.0)), n
 
 
+def test_outputs_subset_on_the_general_path_with_mixed_member_strides(cuda):
+    """Some plane arrays from the caller (member stride T*ny*nx), the rest in the internal scratch (stride ny*nx): the
+    day kernel carries one stride per array kind, so such a step is launched member by member."""
+    from nesosim_b200.engine import SnowBudgetEngine
+    mask = S.region_mask(shape=(40, 70), kind="disc")
+    T = 6
+    forcing = S.make_season(mask, T, seed=31)
+    ic = S.make_ic(mask, seed=31)
+    eng = SnowBudgetEngine(mask, T, 50000, n_members=3, atmlossInc=1)
+    eng.set_path("general")
+    eng.set_forcing(forcing["precip"], forcing["conc"], forcing["wind"], forcing["drift"])
+    params = S.ensemble_params(3, seed=4)
+    full = eng.run_season(params, ic)
+    for names in (("snowDepths", "density"), ("snowLead", "snowAcc", "density"), ("snowDepths", "snowAdv")):
+        part = eng.alloc_outputs(names=names)
+        eng.run_season(params, ic, part)
+        for n in part:
+            assert cuda.equal(full[n].nan_to_num(nan=-7.0), part[n].nan_to_num(nan=-7.0)), (n, names)
+    eng.close()
+
+
 def test_host_path_end_to_end(cuda):
     from nesosim_b200.engine import SnowBudgetEngine
     mask = S.region_mask(dx=100000)
