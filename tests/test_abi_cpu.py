@@ -71,6 +71,14 @@ def test_argument_validation_and_no_cpu_fallback(lib):
             SnowBudgetEngine(mask, 3, 100000)
     assert lib.nesosim_destroy(None) == 0
     assert lib.nesosim_smooth(None, None, 3, 3, None, 1.0, None) == _lib.ERR_ARG
+    # strips of a decomposed grid: nothing to set up, export or query without a context
+    assert lib.nesosim_strip_setup(None, 1, 0) == _lib.ERR_ARG
+    assert lib.nesosim_strip_export(None, C.create_string_buffer(64)) == _lib.ERR_ARG
+    assert lib.nesosim_strip_status(None, C.byref(C.c_int(0))) == _lib.ERR_ARG
+    assert lib.nesosim_strip_set_timeout(None, 1.0) == _lib.ERR_ARG
+    assert lib.nesosim_strip_block(None, None, None) == _lib.ERR_STATE
+    assert lib.nesosim_strip_connect(None, None, None) == _lib.ERR_STATE
+    assert lib.nesosim_strip_connect_local(None, None, None) == _lib.ERR_STATE
 
 
 def test_missing_library_is_an_import_error(monkeypatch):
