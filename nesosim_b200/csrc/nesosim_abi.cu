@@ -1147,6 +1147,8 @@ int nesosim_strip_connect_local(nesosim_ctx *ctx, void *up_block_dev, void *dn_b
     if (!ctx || !ctx->strip.on) return fail(NESOSIM_ERR_STATE, "nesosim_strip_setup has not been called");
     if ((ctx->strip.has_up && !up_block_dev) || (ctx->strip.has_dn && !dn_block_dev))
         return fail(NESOSIM_ERR_ARG, "a neighbour declared in nesosim_strip_setup is missing");
+    if (ctx->strip.ipc_up && ctx->strip.peer_up) cudaIpcCloseMemHandle(ctx->strip.peer_up);      // reconnecting
+    if (ctx->strip.ipc_dn && ctx->strip.peer_dn) cudaIpcCloseMemHandle(ctx->strip.peer_dn);
     ctx->strip.peer_up = ctx->strip.has_up ? (char *)up_block_dev : nullptr;
     ctx->strip.peer_dn = ctx->strip.has_dn ? (char *)dn_block_dev : nullptr;
     ctx->strip.ipc_up = ctx->strip.ipc_dn = false;
@@ -1158,6 +1160,10 @@ int nesosim_strip_connect(nesosim_ctx *ctx, const void *up_handle64, const void 
     if ((ctx->strip.has_up && !up_handle64) || (ctx->strip.has_dn && !dn_handle64))
         return fail(NESOSIM_ERR_ARG, "a neighbour declared in nesosim_strip_setup is missing");
     CU(cudaSetDevice(ctx->cfg.device));
+    if (ctx->strip.ipc_up && ctx->strip.peer_up) cudaIpcCloseMemHandle(ctx->strip.peer_up);      // reconnecting
+    if (ctx->strip.ipc_dn && ctx->strip.peer_dn) cudaIpcCloseMemHandle(ctx->strip.peer_dn);
+    ctx->strip.peer_up = ctx->strip.peer_dn = nullptr;
+    ctx->strip.ipc_up = ctx->strip.ipc_dn = false;
     auto open = [&](const void *h64, char **out) -> int {
         cudaIpcMemHandle_t h;
         std::memcpy(&h, h64, sizeof(h));
