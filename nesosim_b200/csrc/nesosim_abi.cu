@@ -370,6 +370,11 @@ bool fill_day_args(nesosim_ctx *ctx, int x, const double *P, const double *C, co
 int launch_day(nesosim_ctx *ctx, int x, const double *P, const double *C, const double *W, const double *U,
                const double *V, double rho_new, const nesosim_outputs *o, int m0, int mcount, cudaStream_t st,
                bool strip_step = false, bool land_ok = false) {
+    // Programmatic launch only behind one of this library's own day kernels of the same call (x > first_step, which is
+    // what land_ok says too): the part of a day kernel that runs before griddepcontrol.wait reads forcing, mask and
+    // coefficients, and whatever the caller enqueued before the first step (a kernel producing those) must be complete
+    // and visible -- an ordinary launch guarantees that.
+    const bool pdl = ctx->pdl && land_ok;
     DayArgs a;
     if (!fill_day_args(ctx, x, P, C, W, U, V, rho_new, o, m0, land_ok, a) && mcount > 1) {
         for (int mm = 0; mm < mcount; ++mm) {            // mixed strides: one member per launch, pointers pre-offset
@@ -387,12 +392,12 @@ int launch_day(nesosim_ctx *ctx, int x, const double *P, const double *C, const 
     if (strip_step && ctx->strip.on && a.sw.dynamics && (ctx->strip.has_up || ctx->strip.has_dn)) {
         StripLink s;
         strip_link(ctx, x, grid, &s);
-        if (ctx->day_variant == 512) CU(launch_day_kernel(day_step_strip_kernel_512, grid, 512, st, ctx->pdl, a, s));
-        else CU(launch_day_kernel(day_step_strip_kernel, grid, 256, st, ctx->pdl, a, s));
+        if (ctx->day_variant == 512) CU(launch_day_kernel(day_step_strip_kernel_512, grid, 512, st, pdl, a, s));
+        else CU(launch_day_kernel(day_step_strip_kernel, grid, 256, st, pdl, a, s));
     } else if (ctx->day_variant == 512) {
-        CU(launch_day_kernel(day_step_kernel_512, grid, 512, st, ctx->pdl, a));
+        CU(launch_day_kernel(day_step_kernel_512, grid, 512, st, pdl, a));
     } else {
-        CU(launch_day_kernel(day_step_kernel, grid, 256, st, ctx->pdl, a));
+        CU(launch_day_kernel(day_step_kernel, grid, 256, st, pdl, a));
     }
     ctx->launches++;
     CU(cudaGetLastError());
