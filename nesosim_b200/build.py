@@ -6,7 +6,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnesosim_b200.so")
+# The CUDA runtime is linked as a shared library: inside a PyTorch process the library then binds to the runtime torch
+# has already loaded (one runtime per process); standalone, the rpath finds the toolkit's own copy.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
+              "--cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64",
               "-shared", "-Xcompiler", "-fPIC,-pthread", "-Xptxas", "-v"]
 
 

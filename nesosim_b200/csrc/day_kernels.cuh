@@ -234,7 +234,10 @@ __device__ __forceinline__ void day_step_body(const DayArgs &a, double (&s_h)[2]
     const int tid = threadIdx.x;
     const int ny = a.ny, nx = a.nx;
     const int fset = a.member_set ? a.member_set[m] : 0;
-    if (a.set_steps && a.x >= a.set_steps[fset]) return;      // this member's season is over (whole CTA)
+    if (a.set_steps && a.x >= a.set_steps[fset]) {            // this member's season is over (whole CTA)
+        pdl_wait();      // a grid whose CTAs all leave early must still order its successor behind its predecessor
+        return;
+    }
     const long long fo = (long long)fset * a.set_stride;
     const double *aP = a.P + fo, *aC = a.C + fo, *aW = a.W + fo, *aU = a.U + 2 * fo, *aV = a.V + 2 * fo;
     const double *h0p = a.prev[V_H0] + (long long)m * a.depth_mstride;
@@ -329,7 +332,10 @@ template <int DAY_THREADS>
 __device__ __forceinline__ void day_step_land_tile(const DayArgs &a, const int bx, const int by) {
     const int m = blockIdx.z;
     const int fset = a.member_set ? a.member_set[m] : 0;
-    if (a.set_steps && a.x >= a.set_steps[fset]) return;
+    if (a.set_steps && a.x >= a.set_steps[fset]) {
+        pdl_wait();
+        return;
+    }
     const long long fo = (long long)fset * a.set_stride;
     const int gx = bx * TX + (threadIdx.x & (TX - 1));
     if (gx >= a.nx) return;

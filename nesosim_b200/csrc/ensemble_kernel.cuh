@@ -138,7 +138,8 @@ enum { BAR_A = 1, BAR_DRAIN = 2, BAR_STORE = 3 };   // named CTA barriers (0 is 
 //   planes 2..9 [PE] each (own cells only)
 //   staging  [2][PE]    snowAcc / snowOcean rows on their way global -> shared -> global (TMA only)
 //   raw adv  [(rows+2)*SXR + 1] double2,  raw div likewise (the +1 is the slot idle list entries write to)
-//   member coefficients [10], land codes (uint16), three mbarriers (staging loads, halo pushes, neighbours done reading)
+//   member coefficients [10], land codes (uint16), five mbarriers (staging loads, halo pushes, planes drained, and one
+//   "done reading" barrier per neighbour)
 struct EnsLayout {
     int PE, PEX;                       // doubles
     unsigned off_stage, off_adv, tile_bytes, off_coef, off_codes, off_mbar, total;   // bytes
@@ -157,7 +158,9 @@ __host__ __device__ inline EnsLayout ens_layout(int rows, int nx, int land_alloc
     L.off_coef = L.off_adv + 2 * L.tile_bytes;
     L.off_codes = L.off_coef + 10 * 8;
     L.off_mbar = (L.off_codes + (unsigned)land_alloc * 2u + 15u) / 16u * 16u;
-    L.total = L.off_mbar + 32;   // [0] staging loads, [8] halo pushes, [16] neighbours done reading, [24] planes drained
+    // [0] staging loads, [8] halo pushes, [16] the strip ABOVE has finished reading its halo, [24] planes drained,
+    // [32] the strip BELOW has finished reading its halo
+    L.total = L.off_mbar + 48;
     return L;
 }
 
@@ -305,7 +308,8 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
     const unsigned HOWN = 2u * ROWB;                   // own cell (lr,c) of h0: HOWN + (lr*nx+c)*8
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
     unsigned short *s_land_code = reinterpret_cast<unsigned short *>(smem + L.off_codes);
-    const unsigned mbar_stage = sbase + L.off_mbar, mbar_halo = mbar_stage + 8u, mbar_done = mbar_stage + 16u, mbar_drain = mbar_stage + 24u;
+    const unsigned mbar_stage = sbase + L.off_mbar, mbar_halo = mbar_stage + 8u, mbar_done_up = mbar_stage + 16u, mbar_drain = mbar_stage + 24u,
+                   mbar_done_dn = mbar_stage + 32u;
 
     auto LD = [&](unsigned off) -> double { return *reinterpret_cast<const double *>(smem + off); };
     auto LD2 = [&](unsigned off) -> double2 { return *reinterpret_cast<const double2 *>(smem + off); };
@@ -333,7 +337,12 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
         mbar_init(mbar_stage, 1);
         mbar_init(mbar_halo, 1);
         mbar_init(mbar_drain, 1);
-        mbar_init(mbar_done, (k > 0 ? 1u : 0u) + (k < CL - 1 ? 1u : 0u) + (CL == 1 ? 1u : 0u));
+        // One "done reading" barrier PER NEIGHBOUR (count 1 each).  A single barrier counting both neighbours would
+        // complete a phase on two arrivals of the SAME neighbour -- which happens when that neighbour needs no bytes
+        // from this strip (this strip's two rows facing it hold no ocean cell) and so runs a day ahead -- and this CTA
+        // would then push into the other neighbour's halo while it is still being read.
+        mbar_init(mbar_done_up, 1);
+        mbar_init(mbar_done_dn, 1);
     }
 
     // neighbour's halo cell (shared::cluster address, layer 0) that mirrors my local row lr, column c; 0 = none.
@@ -348,8 +357,9 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
     };
     const unsigned rmbar_up = k > 0 ? map_to_rank(mbar_halo, (unsigned)(k - 1)) : 0u;
     const unsigned rmbar_dn = k < CL - 1 ? map_to_rank(mbar_halo, (unsigned)(k + 1)) : 0u;
-    const unsigned rdone_up = k > 0 ? map_to_rank(mbar_done, (unsigned)(k - 1)) : 0u;
-    const unsigned rdone_dn = k < CL - 1 ? map_to_rank(mbar_done, (unsigned)(k + 1)) : 0u;
+    // I am the strip BELOW my upper neighbour and the strip ABOVE my lower one
+    const unsigned rdone_up = k > 0 ? map_to_rank(mbar_done_dn, (unsigned)(k - 1)) : 0u;
+    const unsigned rdone_dn = k < CL - 1 ? map_to_rank(mbar_done_up, (unsigned)(k + 1)) : 0u;
 
     // Work split: list entry i belongs to thread i % NTC, so every warp carries floor or ceil of the average and
     // the four schedulers of the SM see the same load.  nqA / nqB = entries of this WARP (warp-uniform: the phase
@@ -421,14 +431,15 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
         tlast = now_;                                    \
     }
 
-    // every CTA of the cluster is running (and has zeroed its tiles) before anyone writes into a neighbour
-    cluster_arrive_release();
-    cluster_wait_acquire();
-
     unsigned stage_parity = 0, halo_parity = 0, done_parity = 0, drain_parity = 0;
     const bool want_cum = a.out[V_ACC] != nullptr || a.out[V_OCEAN] != nullptr;
 
     for (int m = cid; m < a.M; m += ncl) {
+        // Every CTA of the cluster is running and has zeroed its tiles (first member) / has finished the previous member's
+        // last day, i.e. has stopped reading its halo rows (later members), before anyone writes slot 0 into a neighbour's
+        // halo: a strip whose rows facing a neighbour hold no ocean cell never waits for that neighbour inside the day loop.
+        cluster_arrive_release();
+        cluster_wait_acquire();
         // this member's forcing set and season length
         const int fset = SETS ? a.member_set[m] : 0;
         const int steps = SETS ? a.set_steps[fset] : max_steps;
@@ -722,7 +733,7 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
             ENS_TICK(4)   // drain
 
             // ---------------- publish: planes of day x+1 and the neighbours' halo rows
-            bool waited_done = false;
+            bool waited_up = false, waited_dn = false;
             {
 #pragma unroll
                 for (int j = 0; j < KO; ++j) {
@@ -739,11 +750,17 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
                     ST(L.plane_off(PL_WPG) + ci, r_wpg[j]);
                     ST(L.plane_off(PL_WP) + ci, r_wp[j]);
                     if (b_rem[j]) {
-                        if (!waited_done) {   // (1): my neighbours have finished reading their halo rows of day x
-                            mbar_wait(mbar_done, done_parity);
-                            waited_done = true;
+                        const bool down = ((flags >> (20 + j)) & 1u) != 0u;
+                        // (1): the neighbour this cell is pushed to has finished reading its halo rows of day x
+                        if (down && !waited_dn) {
+                            mbar_wait(mbar_done_dn, done_parity);
+                            waited_dn = true;
                         }
-                        const unsigned rmb = ((flags >> (20 + j)) & 1u) ? rmbar_dn : rmbar_up;
+                        if (!down && !waited_up) {
+                            mbar_wait(mbar_done_up, done_parity);
+                            waited_up = true;
+                        }
+                        const unsigned rmb = down ? rmbar_dn : rmbar_up;
                         st_async(b_rem[j], r_h0[j], rmb);
                         st_async(b_rem[j] + PEXB, r_h1[j], rmb);
                     }

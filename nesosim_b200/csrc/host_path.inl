@@ -89,15 +89,28 @@ extern "C" int nesosim_run_season_host(nesosim_ctx *ctx, const double *precip, c
     size_t cap = (size_t)(cap_gb * (1ull << 30));
     if (!hp->outbuf[0] && cap * 2 > free_b / 10 * 8) cap = free_b / 10 * 4;
     int batch = (int)std::max<long long>(1, std::min<long long>(M, (long long)(cap / (per_member * 8))));
-    if (hp->batch < batch || !hp->outbuf[0]) {
+    // The buffers are cached by their size in BYTES: the bytes a member needs depend on which outputs were asked for,
+    // so a later call with more outputs (same batch count) must regrow them.
+    const size_t need_bytes = (size_t)batch * per_member * 8;
+    if (hp->outbuf_bytes < need_bytes || !hp->outbuf[0] || !hp->outbuf[1]) {
         for (int i = 0; i < 2; ++i) {
             cudaFree(hp->outbuf[i]);
             hp->outbuf[i] = nullptr;
         }
-        for (int i = 0; i < 2; ++i) CU(cudaMalloc(&hp->outbuf[i], (size_t)batch * per_member * 8));
-        hp->batch = batch;
+        hp->outbuf_bytes = 0;
+        for (int i = 0; i < 2; ++i) {
+            cudaError_t e_ = cudaMalloc(&hp->outbuf[i], need_bytes);
+            if (e_ != cudaSuccess) {               // leave no half-allocated pair behind
+                for (int j = 0; j < 2; ++j) {
+                    cudaFree(hp->outbuf[j]);
+                    hp->outbuf[j] = nullptr;
+                }
+                return cuda_fail(e_, "cudaMalloc(output staging)");
+            }
+        }
+        hp->outbuf_bytes = need_bytes;
     }
-    batch = std::min(batch, hp->batch);
+    batch = (int)std::max<long long>(1, std::min<long long>(batch, (long long)(hp->outbuf_bytes / ((size_t)per_member * 8))));
 
     // member-independent arrays (v = 2 snowAcc, v = 3 snowOcean): one device->host copy, replicated on the host
     const bool share = M > 1 && ctx->n_sets == 1 && !getenv("NESOSIM_HOST_NO_SHARE");

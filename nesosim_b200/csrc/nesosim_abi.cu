@@ -132,7 +132,7 @@ struct HostPath {
     double *forcing = nullptr;      // [P|C|W][T][plane] + drift [T][2][plane] + rho_clim [T]
     double *ic = nullptr;
     double *outbuf[2] = {nullptr, nullptr};
-    int batch = 0;
+    size_t outbuf_bytes = 0;        // bytes of each of the two output staging buffers
     cudaStream_t compute = nullptr, copy = nullptr;
     cudaEvent_t done[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr};
     cudaEvent_t shared_ready = nullptr;   // member 0's snowAcc / snowOcean have reached the host
@@ -516,6 +516,26 @@ bool try_strip_tables(nesosim_ctx *ctx, int cl, int cap_raw, int cap_ocean, int 
     t.cluster = cl;
     for (int k = cl, r = ny; k >= 1; --k) { t.row0[k] = r; r = from[k][r]; }
     t.row0[0] = 0;
+    // NESOSIM_ENS_ROWS="r1,r2,...": put the cl-1 interior strip boundaries at these rows (tests of the halo protocol on
+    // masks with all-land rows at a boundary); ignored unless it names a valid cut for this cluster size
+    if (const char *env = getenv("NESOSIM_ENS_ROWS")) {
+        std::vector<int> rows;
+        for (const char *q = env; *q;) {
+            char *end;
+            const long v = strtol(q, &end, 10);
+            if (end == q) break;
+            rows.push_back((int)v);
+            q = (*end == ',') ? end + 1 : end;
+        }
+        if ((int)rows.size() == cl - 1) {
+            rows.insert(rows.begin(), 0);
+            rows.push_back(ny);
+            bool ok = true;
+            for (int k = 0; k < cl && ok; ++k) ok = rows[k] < rows[k + 1] && strip_cost(rows[k], rows[k + 1]) >= 0;
+            if (!ok) return false;
+            for (int k = 0; k <= cl; ++k) t.row0[k] = rows[k];
+        }
+    }
     codes.clear();
     int max_ocean = 0, max_raw = 0, max_rows = 0, max_land = 0, max_edge = 0;
     for (int k = 0; k < cl; ++k) {
@@ -654,6 +674,7 @@ bool ensemble_eligible(nesosim_ctx *ctx, int first_step, int num_steps, const ne
     if (c.nx > ENS_MAX_NX) { *why = "nx > 96"; return false; }
     if (c.nx < 3) { *why = "nx < 3"; return false; }
     if (c.ny < 2 * ENS_MIN_ROWS) { *why = "ny < 8"; return false; }
+    if (c.ny > 511) { *why = "ny > 511 (cell codes are row*128+col in 16 bits)"; return false; }
     if (((long long)c.ny * c.nx) % 2) { *why = "odd number of cells (bulk stores need 16-byte aligned planes)"; return false; }
     if (c.density_clim) { *why = "densityType='clim'"; return false; }
     if (first_step != 0 || num_steps != c.num_days - 1) { *why = "partial season"; return false; }

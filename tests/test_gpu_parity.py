@@ -512,6 +512,77 @@ def test_host_path_end_to_end(cuda):
             assert_parity(out[name][m], ref[name], name)
 
 
+def test_host_path_regrows_its_staging_when_more_outputs_are_asked_for(cuda):
+    """One engine, first a season with only snowDepths requested, then with all eleven arrays and the same member
+    batch: the cached device staging is sized in bytes, so the second call must regrow it (it used to be cached by
+    the batch count and the second season wrote up to 6x past the allocation)."""
+    from nesosim_b200.engine import SnowBudgetEngine
+    mask = S.region_mask(dx=100000)
+    T, M = 9, 3
+    forcing = S.make_season(mask, T, seed=31)
+    ic = S.make_ic(mask, seed=31)
+    params = S.ensemble_params(M, seed=31)
+    eng = SnowBudgetEngine(mask, T, 100000, n_members=M, atmlossInc=1)
+    few, _, down_few = eng.run_season_host(forcing, params, ic, names=("snowDepths",))
+    full, _, down_full = eng.run_season_host(forcing, params, ic)
+    again, _, _ = eng.run_season_host(forcing, params, ic, names=("snowDepths", "density"))
+    assert down_few == 2 * M * T * mask.size * 8 and down_full > 5 * down_few
+    for m in range(M):
+        ref = O.run_season(forcing, ic, mask, 100000, oracle_params(params[m]), O.Flags(atmlossInc=1))
+        assert_parity(few["snowDepths"][m], ref["snowDepths"], "snowDepths (first call)")
+        for name in full:
+            assert_parity(full[name][m], ref[name], name + " (second call)")
+        for name in again:
+            assert_parity(again[name][m], ref[name], name + " (third call)")
+    eng.close()
+
+
+@pytest.mark.parametrize("cluster,rows,land_cols", [("5", "18,36,54,72", 3), ("6", "16,30,44,60,76", 55),
+                                                    ("6", "14,30,46,62,78", 55)])
+def test_ensemble_kernel_all_land_rows_at_a_strip_boundary(cuda, cluster, rows, land_cols, monkeypatch):
+    """A strip whose two rows facing a neighbour hold no ocean cell never pushes to that neighbour, and the neighbour,
+    expecting no bytes from it, may run a day ahead.  The "done reading" handshake is therefore kept PER NEIGHBOUR (a
+    shared barrier completed on two arrivals of the fast neighbour and let this strip overwrite the other neighbour's
+    halo while it was being read), and the next member's slot-0 pushes wait for a cluster barrier.  Masks with all-land
+    row bands straddling forced strip boundaries, several members per cluster, per-member ICs with snow on land."""
+    from nesosim_b200.engine import SnowBudgetEngine
+    monkeypatch.setenv("NESOSIM_ENS_CLUSTERS", "2")
+    monkeypatch.setenv("NESOSIM_ENS_CLUSTER", cluster)
+    monkeypatch.setenv("NESOSIM_ENS_ROWS", rows)
+    ny, nx = 90, 90
+    mask = np.full((ny, nx), 8, dtype=np.uint8)
+    cuts = [int(r) for r in rows.split(",")]
+    mask[cuts[0] - 2:cuts[0] + 2] = 11            # land on both sides of the first boundary
+    mask[cuts[1]:cuts[1] + 2] = 11                # only the lower strip's top rows are land
+    mask[cuts[2] - 2:cuts[2]] = 11                # only the upper strip's bottom rows are land
+    mask[:, :land_cols] = 11                      # (55 land columns: the strips' lists fit the default build variant)
+    mask[40:43, 60:70] = 0
+    T, M = 12, 7
+    forcing = S.make_season(mask, T, seed=37)
+    rng = np.random.default_rng(37)
+    ic = (0.05 + S.make_ic(mask, seed=37))[None] * rng.uniform(0.5, 3.0, (M, 1, 1))      # snow on land in slot 0 too
+    params = S.ensemble_params(M, seed=37)
+    eng = SnowBudgetEngine(mask, T, 100000, n_members=M, atmlossInc=1)
+    eng.set_path("ensemble")
+    eng.set_forcing(forcing["precip"], forcing["conc"], forcing["wind"], forcing["drift"])
+    for rep in range(3):                          # a race does not show on every run
+        out = {k: v.cpu().numpy() for k, v in eng.run_season(params, ic).items()}
+        for m in range(M):
+            ref = O.run_season(forcing, ic[m], mask, 100000, oracle_params(params[m]), O.Flags(atmlossInc=1))
+            for name in out:
+                assert_parity(out[name][m], ref[name], "%s[%d] rep %d" % (name, m, rep))
+    assert eng.rerun_count() == 0
+    eng.close()
+
+
+def test_tall_narrow_grid_is_not_taken_by_the_season_kernel(cuda):
+    """ny > 511 does not fit the 16-bit row*128+col cell codes of the season-resident kernel: general path."""
+    mask = np.full((520, 4), 8, dtype=np.uint8)
+    mask[::7, 0] = 11
+    got, refs = run_both(mask, 4, 100000, [MULTISEASON], dict(atmlossInc=1), seed=41, path="auto", expect_path="general")
+    compare_all(got, refs)
+
+
 # ------------------------------------------------------------------------------------ per-function KATs
 
 def test_smooth_plain_and_nan_branch(cuda):
