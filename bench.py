@@ -147,8 +147,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(MEMBERS_PER_GPU, args.gpus,
-                                                           {"reference_step": "bounded sample: " + sample}),
+            "data": "synthetic", "config": workload_config(MEMBERS_PER_GPU, args.gpus),
+            "reference_step": "bounded sample: " + sample,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -341,6 +341,59 @@ def run_ours(args):
     except Exception as ex:
         e2e_final = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
 
+    if isinstance(e2e, dict) and e2e.get("value") and not args.no_e2e:
+        try:
+            link = d2h_ceiling(world)
+            e2e["link_d2h_gbs_per_gpu"] = link
+            e2e["link_note"] = ("plain pinned device->host copy, one cudaMemcpyAsync stream per rank, all %d ranks at once; "
+                                "fraction = this call's D2H bytes / its time / that ceiling" % world)
+            e2e["d2h_fraction_of_link"] = e2e["d2h_bytes_per_step"] / (e2e["ms_per_step"] * 1e-3) / 1e9 / link
+        except Exception as ex:
+            e2e["link_error"] = str(ex)[:200]
+
+    kernel_path = eng.last_path()
+    del out
+    eng.close()
+    torch.cuda.empty_cache()
+    failures = []
+
+    # BASELINE configs[3]: the 1980-2021 multi-season batch, seasons dealt over the ranks
+    multi = None
+    if not args.no_extra:
+        try:
+            multi = run_multiseason_41(rank, world, local, barrier, peak)
+            if multi.get("identical_to_single_season_run") is False:
+                failures.append("multiseason_41: batch result differs from the single-season run")
+        except Exception as ex:
+            multi = {"error": str(ex)[:300]}
+            failures.append("multiseason_41: " + str(ex)[:200])
+
+    # BASELINE configs[4]: the 5 km grid as row strips over the ranks, ghost rows exchanged inside the day kernel
+    dom = None
+    if world > 1 and not args.no_extra:
+        try:
+            dom = run_domain_5km(rank, world, local, peak)
+            if rank == 0 and dom.get("identical_to_one_gpu") is not True:
+                failures.append("domain_5km: strips differ from the one-GPU run")
+        except Exception as ex:
+            dom = {"error": str(ex)[:300]}
+            failures.append("domain_5km: " + str(ex)[:200])
+    if world > 1:     # every rank learns whether any rank failed (rank 0 prints; all exit non-zero)
+        flags = [None] * world
+        dist.all_gather_object(flags, failures)
+        failures = sorted({f for fl in flags for f in fl})
+
+    # BASELINE configs[0]: the drop-in main() over a season of forcing files, next to the CPU loop over the same files
+    dropin = None
+    if rank == 0 and world == 1 and not args.no_cpu and not args.no_extra:
+        try:
+            dropin = run_main_dropin()
+            if dropin.get("identical_to_cpu_loop") is False:
+                failures.append("main_dropin: main() differs from the CPU loop on the same files")
+        except Exception as ex:
+            dropin = {"error": str(ex)[:300]}
+            failures.append("main_dropin: " + str(ex)[:200])
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, cores, sample, _ = cpu_baseline(1)
@@ -349,8 +402,6 @@ def run_ours(args):
     other = None
     if rank == 0 and world == 1 and not args.no_e2e and not args.no_other:
         try:
-            del out
-            torch.cuda.empty_cache()
             other = run_other_grids(peak)
         except Exception as ex:
             other = {"error": str(ex)[:200]}
@@ -359,12 +410,18 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(M, world, {"kernel_path": eng.last_path(), "variant": args.variant or "default"}), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-                "roofline": roofline, "cpu_baseline": cpu, "e2e_final_products": e2e_final, "other_grids": other}
+                "config": workload_config(M, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "kernel": {"path": kernel_path, "variant": args.variant or "default"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e_final_products": e2e_final, "other_grids": other,
+                "multiseason_41": multi, "domain_5km": dom, "main_dropin": dropin}
+        if failures:
+            line["failed"] = failures
         print(json.dumps(line), flush=True)
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
+    if failures:
+        sys.stderr.write("bench.py: FAILED checks: %s\n" % "; ".join(failures))
+        sys.exit(3)
 
 
 def run_e2e(args, eng, forcing, params, ic, rank, world, cells_per_step, barrier):
@@ -448,6 +505,347 @@ def run_e2e_final(args, eng, forcing, params, ic, dev_out, world, cells_per_step
                        "precipitation, wind), masked and rounded on the device"}
 
 
+def d2h_ceiling(world, gib=1.0, reps=3):
+    """GB/s of a plain pinned device->host cudaMemcpyAsync on this rank while every other rank does the same
+    (max time over ranks): the ceiling any end-to-end figure of this box can reach per GPU."""
+    import torch
+    n = int(gib * (1 << 30)) // 8
+    d = torch.empty(n, dtype=torch.float64, device="cuda")
+    h = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    h.copy_(d, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        h.copy_(d, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return reps * n * 8 / float(t.item()) / 1e9
+
+
+MULTI_YEARS = list(range(1980, 2021))      # 41 start years, Sep 1 - Apr 30 (run_multiseason.py:30-50)
+
+
+def season_days(year):
+    """numDays of the Sep 1 (year) - Apr 30 (year+1) season: 242, or 243 when February of year+1 has 29 days."""
+    import datetime
+    return (datetime.date(year + 1, 4, 30) - datetime.date(year, 9, 1)).days + 1
+
+
+def run_multiseason_41(rank, world, local, barrier, peak):
+    """The loop of run_multiseason.py as ONE native call per rank: the 41 seasons are dealt round-robin over the ranks
+    (sharding.season_assignment), each rank stacks its seasons' forcing with nesosim_set_forcing_sets (one member per
+    season, the script's parameters, seasons of 242 or 243 days) and runs them together.  Strong scaling: the job is
+    the 41 seasons = 9891 steps whatever N is.  Device time (CUDA events), max over ranks."""
+    import torch
+    from nesosim_b200 import sharding, synthetic as S
+    from nesosim_b200.engine import SnowBudgetEngine
+    mine = sharding.season_assignment(MULTI_YEARS, rank, world)
+    mask = S.region_mask(dx=DX)
+    ny, nx = mask.shape
+    days = [season_days(y) for y in mine]
+    T = max(season_days(y) for y in MULTI_YEARS)
+    total_steps = sum(season_days(y) - 1 for y in MULTI_YEARS)
+    Sn = len(mine)
+    stack = {k: np.zeros((Sn, T) + ((2,) if k == "drift" else ()) + (ny, nx)) for k in ("precip", "conc", "wind", "drift")}
+    ics = np.zeros((Sn, ny, nx))
+    for i, y in enumerate(mine):
+        f = S.make_season(mask, days[i], seed=y)
+        for k in stack:
+            stack[k][i, :days[i]] = f[k]
+        ics[i] = S.make_ic(mask, seed=y)
+    params = [[5.8e-7, 5., 1.45e-7, 2.2e-8]] * Sn           # run_multiseason.py:42-50
+    eng = SnowBudgetEngine(mask, T, DX, n_members=Sn, atmlossInc=1, device=local)
+    eng.set_forcing_sets(stack["precip"], stack["conc"], stack["wind"], stack["drift"], np.arange(Sn), days)
+    out = eng.alloc_outputs(zero=True)
+    ic_dev = eng._dev(ics)
+    l0 = eng.launch_count()
+    best = None
+    for rep in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        eng.run_season(params, ic_dev, out)
+        e1.record()
+        torch.cuda.synchronize()
+        if rep:
+            best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
+    launches = (eng.launch_count() - l0) // 4
+    path = eng.last_path()
+    t = torch.tensor([best], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    # the batch against the same season run alone (plain single-season context): rank 0, its first season
+    same = None
+    if rank == 0:
+        y, d = mine[0], days[0]
+        one = SnowBudgetEngine(mask, d, DX, n_members=1, atmlossInc=1, device=local)
+        one.set_forcing(stack["precip"][0, :d], stack["conc"][0, :d], stack["wind"][0, :d], stack["drift"][0, :d])
+        ref = one.run_season(params[:1], ics[0])
+        same = all(bool(torch.equal(torch.nan_to_num(out[k][0, :d], nan=-7.0), torch.nan_to_num(ref[k][0], nan=-7.0)))
+                   for k in out)
+        one.close()
+    eng.close()
+    del out
+    torch.cuda.empty_cache()
+    cells = total_steps * ny * nx
+    b_alg = 96.0 + 41.0            # every season has its own forcing: nothing is shared between members
+    return {"workload": "multi-season 1980-2021 batch: 41 seasons (Sep 1 - Apr 30, 242/243 days), 100 km grid, one native call "
+                        "per rank over its seasons (nesosim_set_forcing_sets)",
+            "seasons_total": len(MULTI_YEARS), "seasons_this_rank": Sn, "steps_total": total_steps, "n_gpus": world,
+            "ms": ms, "steps_per_s": total_steps / (ms * 1e-3), "value": cells / (ms * 1e-3), "unit": UNIT,
+            "scaling": "strong", "kernel_path": path, "launches_per_rank": launches,
+            "roofline_frac_algorithmic_per_gpu": cells * b_alg / world / (ms * 1e-3) / 1e9 / peak,
+            "identical_to_single_season_run": same, "data": "synthetic, one seed per start year"}
+
+
+def run_domain_5km(rank, world, local, peak, steps=40, gen_days=4, reps=3):
+    """5 km pan-Arctic grid (1785 x 1785, real coastline) as `world` row strips, one per GPU, the ghost-row exchange
+    fused into the day kernel over peer memory (nesosim_strip_*; domain.run_decomposed_season_peer).  Also runs the
+    same season on ONE GPU of the same box (rank 0) and compares EVERY owned row of all eleven arrays with it."""
+    import torch
+    import torch.distributed as dist
+    from nesosim_b200 import domain, synthetic as S
+    from nesosim_b200.engine import SnowBudgetEngine
+    dx, T = 5000, steps + 1
+    mask = S.region_mask(dx=dx)
+    n = mask.shape[0]
+    gen = S.make_season(mask, gen_days, seed=7)
+    gen = {k: v for k, v in gen.items() if k != "temp"}
+    idx = np.arange(T) % gen_days
+    ic = S.make_ic(mask, seed=7)
+    params = [5.8e-7, 5., 1.45e-7, 2.2e-8]
+    cells = n * n * steps
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- one GPU, the whole grid (rank 0; the others wait)
+    ref, one_ms = None, 0.0
+    if rank == 0:
+        eng1 = SnowBudgetEngine(mask, T, dx, n_members=1, device=local, atmlossInc=1)
+        eng1.set_path("general")
+        it = torch.as_tensor(idx, device="cuda", dtype=torch.long)
+        f = {k: eng1._dev(v)[it].contiguous() for k, v in gen.items()}
+        eng1.set_forcing(f["precip"], f["conc"], f["wind"], f["drift"])
+        ref = eng1.alloc_outputs()
+        best = None
+        for r in range(reps + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            eng1.run_season([params], ic, ref)
+            e1.record()
+            torch.cuda.synchronize()
+            if r:
+                best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
+        one_ms = best
+        eng1.close()
+        del f
+        torch.cuda.empty_cache()
+    dist.barrier()
+
+    # ---- the strips
+    lo, hi, part, eng = domain.run_decomposed_season_peer(mask, T, dx, gen, params, ic, rank, world, device=local,
+                                                          day_index=idx, atmlossInc=1, timeout_s=20.0)
+    outs = eng._keep[1]
+    lo_, hi_, elo, ehi = eng._strip_rows
+    ic_dev = eng._dev(np.ascontiguousarray(ic[elo:ehi]))
+    best = None
+    for r in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        eng.run_season([params], ic_dev, outs)
+        e1.record()
+        torch.cuda.synchronize()
+        domain.check_strips(eng, rank, world)            # raises on every rank if any strip timed out
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        best = ms if best is None else min(best, ms)
+
+    # ---- every owned row of every array against the one-GPU run (gathered to rank 0 over NCCL, compared on the device)
+    own = slice(lo - elo, lo - elo + (hi - lo))
+    names = sorted(outs)
+    ok = True
+    bounds = [None] * world
+    dist.all_gather_object(bounds, (lo, hi))
+    for k in names:
+        mine = outs[k][0][..., own, :].contiguous()
+        if rank == 0:
+            ok = ok and bool(torch.equal(torch.nan_to_num(mine, nan=-7.0), torch.nan_to_num(ref[k][0][..., lo:hi, :], nan=-7.0)))
+            for r in range(1, world):
+                rl, rh = bounds[r]
+                shape = list(ref[k][0].shape)
+                shape[-2] = rh - rl
+                buf = torch.empty(shape, dtype=torch.float64, device="cuda")
+                dist.recv(buf, src=r)
+                ok = ok and bool(torch.equal(torch.nan_to_num(buf, nan=-7.0), torch.nan_to_num(ref[k][0][..., rl:rh, :], nan=-7.0)))
+                del buf
+        else:
+            dist.send(mine, dst=0)
+    eng.close()
+    del outs, ref
+    torch.cuda.empty_cache()
+    dist.barrier()
+    if rank != 0:
+        return {}
+    gbs = cells * 137.0 / (best * 1e-3) / 1e9
+    return {"workload": "5 km pan-Arctic grid (1785x1785, real coastline), %d steps, %d row strips (one per GPU), ghost rows "
+                        "stored into the neighbour GPU's memory by the day kernel (peer memory, flags); no collective" % (steps, world),
+            "grid": [n, n], "steps": steps, "n_gpus": world, "ms": best, "us_per_day": 1e3 * best / steps,
+            "value": cells / (best * 1e-3), "unit": UNIT, "scaling": "strong",
+            "roofline_frac_algorithmic_per_gpu": gbs / world / peak,
+            "one_gpu_same_box": {"ms": one_ms, "us_per_day": 1e3 * one_ms / steps, "value": cells / (one_ms * 1e-3),
+                                 "roofline_frac_algorithmic": cells * 137.0 / (one_ms * 1e-3) / 1e9 / peak},
+            "speedup_vs_one_gpu": one_ms / best, "identical_to_one_gpu": bool(ok),
+            "compared": "all 11 arrays, every owned row, every time slot (NaN patterns and values) on the device",
+            "strip_status": "no time-out on any rank", "launches_per_day": 1,
+            "data": "synthetic (%d generated days repeated)" % gen_days}
+
+
+class _StandInUtils:
+    """What ``nesosim_b200.NESOSIM.main`` needs from the reference's ``utils`` module (grid, mask, calendar) when the
+    reference's own dependencies (pyproj, netCDF4, cartopy) are not installed: the closed-form EPSG:3413 grid and the
+    bundled regrid of region_n.msk from nesosim_b200.grid.  The writers are not called (saveData=0)."""
+
+    def __init__(self, dx):
+        from nesosim_b200 import grid
+        self.grid = grid
+        self.mask = grid.bundled_region_mask(dx)
+        self.getDays = grid.getDays
+
+    def create_grid(self, dxRes=50000):
+        return self.grid.create_grid(dxRes=dxRes)
+
+    def get_region_mask_pyproj(self, anc, proj, xypts_return=0):
+        x, y, lats, lons, _ = self.grid.create_grid(dxRes=DX)       # the mask "file" is already on the model grid
+        return self.mask, x, y, lons, lats
+
+
+def run_main_dropin():
+    """BASELINE configs[0]: one 100 km season (run_oneseason.py:40-48 dates and parameters) from forcing FILES.
+    A synthetic season is written as the pickle tree the reference's gridding scripts produce; timed are (ours)
+    nesosim_b200.NESOSIM.main(saveData=0, plotBudgets=0, plotdaily=0) -- read 5 files per day, stage, one GPU season
+    call, all arrays back on the host -- and (CPU) the reference's loop over the same files: loadData + calcBudget per
+    day (the numpy port).  Best of two passes each (the files are in the page cache for both)."""
+    import shutil
+    import tempfile
+    import types
+    from nesosim_b200 import NESOSIM as N, synthetic as S, grid
+    from oracle import nesosim_oracle as O           # the CPU loop below is the reference's path, not the product
+    y1, m1, d1, y2, m2, d2 = 2018, 8, 0, 2019, 3, 29          # run_oneseason.py: Sep 1 2018 - Apr 30 2019 (0-based)
+    startDay, numDays, nDaysY1, dateOut = grid.getDays(y1, m1, d1, y2, m2, d2)
+    mask = S.region_mask(dx=DX)
+    ny, nx = mask.shape
+    f = S.make_season(mask, numDays, seed=SEED)
+    ic = S.make_ic(mask, seed=SEED)
+    root = tempfile.mkdtemp(prefix="nesosim_dropin_")
+    try:
+        base = os.path.join(root, "forcing", "100km")
+        day, year = startDay, y1
+        for x in range(numDays):
+            if x < numDays - 1:
+                day = x + startDay
+                year = y1
+                if day >= nDaysY1:
+                    day -= nDaysY1
+                    year = y2
+                d = day
+            else:
+                d = day + 1
+            ds = "%03d" % d
+            for sub, name, arr in (("Precip/ERA5/%d" % year, "ERA5sf100km-%d_d%sv11" % (year, ds), f["precip"][x]),
+                                   ("Winds/ERA5/%d" % year, "ERA5winds100km-%d_d%sv11" % (year, ds), f["wind"][x]),
+                                   ("IceConc/CDR/%d" % year, "iceConcG_CDR100km-%d_d%sv11" % (year, ds), f["conc"][x]),
+                                   ("IceDrift/OSISAF/%d" % year, "OSISAF_driftG100km-%d_d%sv11" % (year, ds), f["drift"][x])):
+                os.makedirs(os.path.join(base, sub), exist_ok=True)
+                if not (sub.startswith("IceDrift") and np.isnan(arr).all()):      # an all-NaN day = a missing drift file
+                    np.ascontiguousarray(arr).dump(os.path.join(base, sub, name))
+        os.makedirs(os.path.join(base, "InitialConditions/ERA5"))
+        ic.dump(os.path.join(base, "InitialConditions/ERA5", "ICsnow100km-%dv11" % y1))
+        stand_in = types.ModuleType("utils")
+        su = _StandInUtils(DX)
+        for name in ("create_grid", "get_region_mask_pyproj", "getDays"):
+            setattr(stand_in, name, getattr(su, name))
+        saved = sys.modules.get("utils")
+        sys.modules["utils"] = stand_in
+        N.VERBOSE = False
+        kw = dict(outPathT=os.path.join(root, "out") + "/", forcingPathT=os.path.join(root, "forcing") + "/",
+                  anc_data_pathT="unused/", figPathT=os.path.join(root, "fig") + "/", precipVar="ERA5", windVar="ERA5",
+                  driftVar="OSISAF", concVar="CDR", icVar="ERA5", densityTypeT="variable", extraStr="v11", outStr="bench",
+                  IC=2, windPackFactorT=5.8e-7, windPackThreshT=5, leadLossFactorT=2.9e-7, atmLossFactorT=2.2e-8,
+                  dynamicsInc=1, leadlossInc=1, windpackInc=1, atmlossInc=0, saveData=0, plotBudgets=0, plotdaily=0, dx=DX)
+        ours = []
+        try:
+            for _ in range(3):
+                t0 = time.perf_counter()
+                N.main(y1, m1, d1, y2, m2, d2, **kw)
+                ours.append(time.perf_counter() - t0)
+            # where main's time goes: the stager alone, and the season + copies alone
+            t0 = time.perf_counter()
+            st = N.stage_season(y1, y2, startDay, numDays, nDaysY1, "ERA5", "ERA5", "CDR", "OSISAF", "100km", "v11")
+            t_stage = time.perf_counter() - t0
+            eng = N._engine(su.mask, numDays, DX, "variable", 1, 1, 1, 0)
+            import torch
+            t0 = time.perf_counter()
+            eng.set_forcing(st["precip"], st["conc"], st["wind"], st["drift"], None)
+            out = eng.run_season([[5.8e-7, 5., 2.9e-7, 2.2e-8]], ic)
+            got = {k: v[0].cpu().numpy() for k, v in out.items()}
+            t_gpu = time.perf_counter() - t0
+        finally:
+            if saved is None:
+                sys.modules.pop("utils", None)
+            else:
+                sys.modules["utils"] = saved
+        # ---- the reference's loop on the CPU over the same files (NESOSIM.py:614-649)
+        p = O.Params(windPackFactor=5.8e-7, windPackThresh=5., leadLossFactor=2.9e-7, atmLossFactor=2.2e-8)
+        fl = O.Flags(atmlossInc=0)
+        N.forcingPath = base + "/"
+        cpu = []
+        s = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            s = O.gen_empty_arrays(numDays, ny, nx)
+            icm = np.load(os.path.join(base, "InitialConditions/ERA5", "ICsnow100km-%dv11" % y1), allow_pickle=True)
+            day, year = startDay, y1
+            for x in range(numDays - 1):
+                day = x + startDay
+                year = y1
+                if day >= nDaysY1:
+                    day -= nDaysY1
+                    year = y2
+                conc, precip, drift, wind, temp = N.loadData(year, day, "ERA5", "ERA5", "CDR", "OSISAF", "100km", "v11")
+                if x == 0:
+                    half = O.initial_depths(icm, conc, p)
+                    s["snowDepths"][0, 0] = half
+                    s["snowDepths"][0, 1] = half
+                O.calc_budget(s, conc, precip, drift, wind, temp, mask, DX, x, p, fl)
+            cpu.append(time.perf_counter() - t0)
+        same = all(bool(np.array_equal(got[k], s[k], equal_nan=True)) for k in got)
+        cells = ny * nx * (numDays - 1)
+        return {"workload": "one 100 km season (Sep 1 2018 - Apr 30 2019, %d days) from forcing files through the drop-in "
+                            "main(saveData=0, plotBudgets=0, plotdaily=0)" % numDays,
+                "files": 4 * numDays, "ours_ms": 1e3 * min(ours), "ours_first_call_ms": 1e3 * ours[0],
+                "ours_stage_files_ms": 1e3 * t_stage, "ours_h2d_season_d2h_ms": 1e3 * t_gpu,
+                "cpu_loop_ms": 1e3 * min(cpu), "cpu_loop": "loadData + calcBudget per day (numpy port), 1 process",
+                "speedup": min(cpu) / min(ours), "value": cells / min(ours), "cpu_value": cells / min(cpu), "unit": UNIT,
+                "identical_to_cpu_loop": bool(same)}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
+
 def run_other_grids(peak):
     """The other single-GPU configurations of BASELINE.json on the general per-day path (one member, full 12-array
     output, forcing resident): the 25 km season and a short stretch of the 5 km grid.  Reported as an extra key next to
@@ -458,7 +856,7 @@ def run_other_grids(peak):
     rows = []
     for name, n, dx, T, gen_days in (("25 km Arctic grid, single season (general day kernel)", 357, 25000, NUM_DAYS, 8),
                                      ("5 km pan-Arctic grid, 40 steps (general day kernel)", 1785, 5000, 41, 4)):
-        mask = S.region_mask(dx=dx) if n == 357 else S.region_mask(shape=(n, n), kind="disc")
+        mask = S.region_mask(dx=dx)      # the real coastline (5 km: the 25 km regrid sampled at the 5 km cell centres)
         gen = S.make_season(mask, gen_days, seed=7)
         idx = np.arange(T) % gen_days
         f = {k: torch.from_numpy(v[idx]).cuda() for k, v in gen.items() if v is not None}
@@ -481,7 +879,8 @@ def run_other_grids(peak):
         gbs = cells * 137.0 / (best * 1e-3) / 1e9
         rows.append({"workload": name, "grid": [n, n], "num_days": T, "value": cells / (best * 1e-3), "unit": UNIT,
                      "us_per_day": 1e3 * best / (T - 1), "kernel": "day_step_kernel", "launches": T - 1,
-                     "roofline_frac_algorithmic": gbs / peak, "data": "synthetic (%d generated days repeated)" % gen_days})
+                     "roofline_frac_algorithmic": gbs / peak, "mask": "region_n.msk regridded (grid.bundled_region_mask)",
+                     "data": "synthetic (%d generated days repeated)" % gen_days})
         del out, f
         eng.close()
         torch.cuda.empty_cache()
@@ -502,6 +901,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     ap.add_argument("--no-other", action="store_true", help="skip the 25 km / 5 km general-path figures")
+    ap.add_argument("--no-extra", action="store_true", help="skip the multi-season, 5 km strips and drop-in main legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -593,7 +593,6 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
 
         if (TIMING && timing) tlast = clock64();
         for (int x = 0; x < steps; ++x) {
-            if (tid == 0) mbar_expect_tx(mbar_halo, (unsigned)a.st.halo_tx[k]);   // today's pushes from the neighbours
             fetch_cell_inputs(x);   // consumed in B, in flight during A
             if (TIMING && wtiming) tw0 = clock64();
 
@@ -652,7 +651,15 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
             if (TIMING && wtiming) twA += clock64() - tw0;
             ENS_TICK(0)   // A
             bar_sync(BAR_A, NTC);       // raw tiles complete; nobody in this CTA reads the halo rows of day x any more
-            if (tid == 0) {             // (1)
+            if (tid == 0) {
+                // Today's pushes from the neighbours are expected only now, behind the CTA barrier: every thread of this
+                // CTA has then finished waiting for YESTERDAY's phase of the halo barrier.  (Armed at the top of the day,
+                // a strip that expects no bytes at all -- all-land rows on both sides -- completed today's phase at once,
+                // thread 0 could arm and complete the next one, and a slower thread still waiting for yesterday's phase
+                // parity saw that parity as the current, incomplete phase: deadlock.)  The pushes themselves cannot
+                // arrive earlier: the neighbours wait for this CTA's "done reading" arrival right below.
+                mbar_expect_tx(mbar_halo, (unsigned)a.st.halo_tx[k]);
+                // (1)
                 if (rdone_up) mbar_arrive_remote_relaxed(rdone_up);
                 if (rdone_dn) mbar_arrive_remote_relaxed(rdone_dn);
             }

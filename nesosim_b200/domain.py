@@ -155,9 +155,11 @@ def run_decomposed_season_one_process(mask, num_days, dx, forcing, params_row, i
 
 # ------------------------------------------------------------------------------ fused peer-memory exchange
 
-def make_strip_engine(mask, num_days, dx, forcing, rank, world, device=0, timeout_s=None, **flags):
+def make_strip_engine(mask, num_days, dx, forcing, rank, world, device=0, timeout_s=None, day_index=None, **flags):
     """Engine on this rank's extended strip with its forcing staged and ``nesosim_strip_setup`` done.
-    Returns (engine, lo, hi, elo, ehi, ic_rows) -- ``ic_rows`` slices a global (ny, nx) array to the strip."""
+    Returns (engine, lo, hi, elo, ehi).  ``day_index`` (length ``num_days``): the forcing arrays hold a few generated
+    days and day x of the season is ``forcing[...][day_index[x]]`` -- the repetition happens on the device after the
+    rows have been sliced, so a benchmark never materialises the whole season of the whole grid on the host."""
     from .engine import SnowBudgetEngine
     ny = mask.shape[0]
     lo, hi, elo, ehi = strip_rows(ny, rank, world)
@@ -166,13 +168,29 @@ def make_strip_engine(mask, num_days, dx, forcing, rank, world, device=0, timeou
     eng = SnowBudgetEngine(np.ascontiguousarray(mask[elo:ehi]), num_days, dx, n_members=1, device=device, **flags)
     eng.set_path("general")
     f = slice_rows(forcing, elo, ehi)
+    if day_index is not None:
+        import torch
+        idx = torch.as_tensor(np.asarray(day_index), device="cuda:%d" % device, dtype=torch.long)
+        f = {k: (v if (v is None or k == "rho_clim") else eng._dev(v)[idx].contiguous()) for k, v in f.items()}
     eng.set_forcing(f["precip"], f["conc"], f["wind"], f["drift"], f.get("rho_clim"))
     eng.strip_setup(rank > 0, rank < world - 1, timeout_s=timeout_s)
     return eng, lo, hi, elo, ehi
 
 
+def check_strips(eng, rank, world, group=None):
+    """After a season: did any strip give up waiting for its neighbour?  A strip that timed out carried on with stale
+    ghost rows, so its results (and its neighbours') are wrong -- EVERY rank raises, together (the exchange of the
+    flags doubles as the barrier that ends the season)."""
+    import torch.distributed as dist
+    flags = [None] * world
+    dist.all_gather_object(flags, bool(eng.strip_timed_out()), group=group)
+    if any(flags):
+        raise RuntimeError("strip(s) %s did not receive their neighbours' ghost rows in time (nesosim_strip_status); "
+                           "the season's results are invalid" % [r for r, f in enumerate(flags) if f])
+
+
 def run_decomposed_season_peer(mask, num_days, dx, forcing, params_row, ic, rank, world, device=0, group=None,
-                               outputs=None, engine=None, timeout_s=None, **flags):
+                               outputs=None, engine=None, timeout_s=None, day_index=None, **flags):
     """This rank's strip of one season with the ghost-row exchange fused into the day kernel (peer memory).
     ``torch.distributed`` must be initialised (any backend: it moves 64-byte handles and barriers only).
     Returns (lo, hi, {array: device tensor of the OWNED rows}, engine); pass ``engine`` back in to run further seasons
@@ -181,7 +199,7 @@ def run_decomposed_season_peer(mask, num_days, dx, forcing, params_row, ic, rank
     import torch.distributed as dist
     if engine is None:
         eng, lo, hi, elo, ehi = make_strip_engine(mask, num_days, dx, forcing, rank, world, device=device,
-                                                  timeout_s=timeout_s, **flags)
+                                                  timeout_s=timeout_s, day_index=day_index, **flags)
         handles = [None] * world
         dist.all_gather_object(handles, eng.strip_export(), group=group)
         eng.strip_connect(handles[rank - 1] if rank > 0 else None, handles[rank + 1] if rank < world - 1 else None)
@@ -194,9 +212,7 @@ def run_decomposed_season_peer(mask, num_days, dx, forcing, params_row, ic, rank
     dist.barrier(group=group)              # every strip's previous season is complete and every mailbox attached
     out = eng.run_season([list(params_row)], ic_local, outputs)
     torch.cuda.synchronize(device)
-    if eng.strip_timed_out():
-        raise RuntimeError("rank %d: a neighbouring strip did not deliver its ghost rows in time" % rank)
-    dist.barrier(group=group)
+    check_strips(eng, rank, world, group)
     own = slice(lo - elo, lo - elo + (hi - lo))
     return lo, hi, {k: v[0][..., own, :] for k, v in out.items()}, eng
 

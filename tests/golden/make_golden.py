@@ -11,6 +11,10 @@ or the CUDA code.  Inputs are stored next to the outputs so the fixtures do not 
   season_small.npz       42x37 grid, 16 days, all inputs + all 15 arrays (two parameter sets, switches, clim)
   season_100km_digest.npz  90x90, 242 days (run_oneseason.py dates): inputs by seed, outputs as final/selected
                            planes + sha256 of every full array
+  season_25km_digest.npz   357x357, 260 days (Aug 15 - May 1), run_multiseason parameters: sha256 of every full array,
+                           of the last slot, and sampled rows of the last slot
+  steps_5km_digest.npz     1785x1785 (the bundled 5 km mask), 3 steps: sha256 of every full array + sampled rows
+(the two large cases take a few minutes of CPU: `python tests/golden/make_golden.py large`)
 """
 import hashlib
 import os
@@ -172,7 +176,42 @@ def season_100km_digest():
     print("season_100km_digest.npz", os.path.getsize(os.path.join(HERE, "season_100km_digest.npz")) // 1024, "KiB")
 
 
+def large_digest(fname, dx, T, seed, params, atm, sample_rows):
+    """A configuration at BASELINE's full grid size through the reference's own loop: only digests are kept (sha256 of
+    every full array and of its last slot) plus a few sampled rows of the last slot for diagnosis."""
+    mask = S.region_mask(dx=dx)
+    F = S.make_season(mask, T, seed=seed)
+    ic = S.make_ic(mask, seed=seed)
+    out = {"seed": np.array(seed), "T": np.array(T), "dx": np.array(dx), "params": np.array(params, dtype=np.float64),
+           "atmlossInc": np.array(atm), "sample_rows": np.array(sample_rows), "mask_sha": np.array(canon_sha(mask.astype(np.float64)))}
+    for k in ("precip", "conc", "wind", "drift"):
+        out["in_sha__" + k] = np.array(canon_sha(F[k]))
+    out["in_sha__ic"] = np.array(canon_sha(ic))
+    ref_loader.set_globals(ref, *params)
+    R = ref_loader.run_reference_season(ref, F, ic, mask.astype(np.float64), dx, dict(atmlossInc=atm))
+    for k, v in R.items():
+        if k in ("precipDays", "iceConcDays", "windDays", "tempDays"):
+            continue
+        out["sha__" + k] = np.array(canon_sha(v))
+        out["sha_last__" + k] = np.array(canon_sha(v[-1]))
+        out["rows_last__" + k] = v[-1][..., sample_rows, :]
+    np.savez_compressed(os.path.join(HERE, fname), **out)
+    print(fname, os.path.getsize(os.path.join(HERE, fname)) // 1024, "KiB")
+
+
+def season_25km_digest():
+    large_digest("season_25km_digest.npz", 25000, 260, 2025, (5.8e-7, 5., 1.45e-7, 2.2e-8), 1, list(range(5, 357, 50)))
+
+
+def steps_5km_digest():
+    large_digest("steps_5km_digest.npz", 5000, 4, 5005, (5.8e-7, 5., 1.45e-7, 2.2e-8), 1, list(range(7, 1785, 300)))
+
+
 if __name__ == "__main__":
-    kat_functions()
-    season_small()
-    season_100km_digest()
+    if len(sys.argv) > 1 and sys.argv[1] == "large":
+        season_25km_digest()
+        steps_5km_digest()
+    else:
+        kat_functions()
+        season_small()
+        season_100km_digest()
