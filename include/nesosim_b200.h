@@ -166,6 +166,29 @@ int nesosim_final_products(const double *depths_dev, const double *density_dev, 
                            float *snow_density_dev, float *ice_conc_dev, float *precip_out_dev, float *wind_out_dev,
                            void *stream);
 
+/* Calibration driver (the reference has no counterpart): the season of nesosim_run_season with the
+ * observation operator and the reduction FUSED into the season-resident kernel -- no output array is written at all.
+ * Observations are points (day slot 0..T-1, row, col, observed snow depth over ice [m]) in host arrays; for every member
+ * misfit_dev[m] = sum over observations of (model - observed)^2 with model = (h0+h1)/iceConc at that slot and cell (what
+ * main writes as snow depth, NESOSIM.py:654), skipping non-finite differences (land, NaN forcing, zero concentration),
+ * and count_dev[m] (may be NULL) = the number of observations used.  Every owned cell's thread walks its own
+ * observations; sums are formed per thread, per CTA and per member in a fixed order (deterministic).  Needs the
+ * season-resident path (grid up to 96 columns, variable density, one shared forcing); NESOSIM_ERR_ARG otherwise. */
+int nesosim_run_season_misfit(nesosim_ctx *ctx, const nesosim_member_params *params_host, const double *ic_dev,
+                              int ic_per_member, int64_t n_obs, const int32_t *obs_day_host, const int32_t *obs_row_host,
+                              const int32_t *obs_col_host, const double *obs_depth_host, double *misfit_dev,
+                              int64_t *count_dev, void *stream);
+
+/* Asynchronous mode.  By default nesosim_run_season on the season-resident path synchronises `stream` once to read
+ * the kernel's operand-range flag (see above).  With nesosim_set_async(ctx, 1) it never synchronises: the flag is copied
+ * to pinned host memory behind the kernel and examined by nesosim_sync (which waits for every season enqueued so far on
+ * this context, redoes with the general kernels any season whose flag is raised -- never on physical data -- and
+ * reports how many) or, without waiting, by later calls.  Contract in this mode: a season's outputs, its IC buffer and
+ * the forcing are final / reusable only after nesosim_sync; back-to-back seasons, the next forcing's upload and the
+ * previous outputs' download then overlap freely on the caller's streams.  nesosim_set_async(ctx, 0) syncs first. */
+int nesosim_set_async(nesosim_ctx *ctx, int on);
+int nesosim_sync(nesosim_ctx *ctx, int *seasons_redone);
+
 /* Kernel path of nesosim_run_season: 0 = automatic (default), 1 = general per-day kernel (any grid),
  * 2 = season-resident cluster kernel (grids up to 96x96, variable density, whole season; error otherwise).
  * Both paths produce identical values.  nesosim_last_path reports which one the last season used. */

@@ -156,7 +156,7 @@ __host__ __device__ inline EnsLayout ens_layout(int rows, int nx, int land_alloc
     L.off_adv = L.off_stage + (unsigned)(2 * L.PE * 8);
     L.tile_bytes = (unsigned)(((rows + 2) * ENS_SXR + 1) * 16);
     L.off_coef = L.off_adv + 2 * L.tile_bytes;
-    L.off_codes = L.off_coef + 10 * 8;
+    L.off_codes = L.off_coef + (10 + 64) * 8;   // 10 coefficient products + 64 doubles of reduction scratch (misfit mode)
     L.off_mbar = (L.off_codes + (unsigned)land_alloc * 2u + 15u) / 16u * 16u;
     // [0] staging loads, [8] halo pushes, [16] the strip ABOVE has finished reading its halo, [24] planes drained,
     // [32] the strip BELOW has finished reading its halo
@@ -198,6 +198,15 @@ struct EnsArgs {
     double w[9];
     Switches sw;
     StripTables st;
+    // misfit mode (calibration driver): point observations of snow depth over ice, sorted by owning
+    // cell and day; obs_first is indexed like `codes` (ocean list of every strip) and points at the cell's first
+    // observation, every cell's run ends with a sentinel day (INT_MAX).  Per member and CTA one partial sum of squared
+    // differences and one count leave the kernel: misfit_part / count_part [M][cluster].
+    const int *obs_first, *obs_day;
+    const double *obs_val;
+    const double *conc;                // ice concentration [T][plane] (the observation operator divides by it)
+    double *misfit_part;
+    long long *count_part;
     int dbg;                           // timing experiments only (NESOSIM_ENS_DBG): 1 forcing always from day 0, 2 no L2 prefetch, 4 no bulk stores
     int *status;                       // set to 1 if any operand left the fast divisions' proven range (host reruns)
     long long *timing;                 // debug: [gridDim.x][ENS_NTIMER] phase cycle totals (NULL = off)
@@ -295,7 +304,7 @@ __device__ __forceinline__ void st_cluster(unsigned addr, double v) {
 // bytes they deliver with st.async.  Cluster-wide barriers are used once per member only.
 // SETS: members may use different forcing sets / season lengths (compiled apart so that the plain ensemble keeps its
 // parameter-bank pointers and its uniform trip count)
-template <int NTC, int KR, int KO, bool TIMING, bool SETS>
+template <int NTC, int KR, int KO, bool TIMING, bool SETS, bool OBS = false>
 __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __grid_constant__ EnsArgs a) {
     constexpr int SXR = ENS_SXR;
     constexpr int NTH = NTC + 32;
@@ -396,13 +405,16 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
     // ---- the ocean cells this thread owns for the whole season (entries tid + j*NTC): offset of the cell in an
     // own-cells plane, of its top-left 3x3 tap in the raw tiles, and its mirror in a neighbour's halo
     unsigned b_ci[KO], b_t[KO], b_rem[KO];
+    int o_first[OBS ? KO : 1];         // misfit mode: the cell's first observation
 #pragma unroll
     for (int j = 0; j < KO; ++j) {
         const int idx = tid + j * NTC;
         b_t[j] = L.off_adv;
         b_ci[j] = 0;
         b_rem[j] = 0;
+        if (OBS) o_first[j] = -1;
         if (comp && idx < n_ocean) {
+            if (OBS) o_first[j] = a.obs_first[a.st.ocean_off[k] + idx];
             const unsigned code = a.st.codes[a.st.ocean_off[k] + idx];
             const int lr = (int)(code >> 7), c = (int)(code & 127u);
             b_t[j] = L.off_adv + (unsigned)(lr * SXR + c) * 16u;
@@ -556,6 +568,32 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
             r_h0[j] = LD(HOWN + b_ci[j]);
             r_h1[j] = LD(HOWN + PEXB + b_ci[j]);
             r_dn[j] = r_adv[j] = r_div[j] = r_lead[j] = r_atm[j] = r_wpl[j] = r_wpg[j] = r_wp[j] = 0.0;
+        }
+        // misfit mode: every owned cell walks its own (day-sorted) observations; the modelled quantity is what main writes
+        // as snow depth over ice, (h0+h1)/iceConc (NESOSIM.py:654); non-finite differences (NaN model values, zero
+        // concentration) are skipped.  Nothing but the per-CTA sums ever leaves the SM.
+        double m_acc = 0.0;
+        long long m_cnt = 0;
+        int o_idx[OBS ? KO : 1], o_day[OBS ? KO : 1];
+        auto obs_take = [&](int j, int slot) {
+            while (o_day[j] == slot) {
+                const double C = __ldg(a.conc + (SETS ? (long long)fset * a.T * plane : 0) + (long long)slot * plane + go_own + (b_ci[j] >> 3));
+                const double diff = sub(div_ieee(add(r_h0[j], r_h1[j]), C), __ldg(a.obs_val + o_idx[j]));
+                if (finite(diff)) {
+                    m_acc = add(m_acc, mul(diff, diff));
+                    ++m_cnt;
+                }
+                ++o_idx[j];
+                o_day[j] = __ldg(a.obs_day + o_idx[j]);
+            }
+        };
+        if (OBS) {
+#pragma unroll
+            for (int j = 0; j < KO; ++j) {
+                o_idx[j] = o_first[j];
+                o_day[j] = o_first[j] >= 0 ? __ldg(a.obs_day + o_idx[j]) : 0x7fffffff;
+                obs_take(j, 0);
+            }
         }
 
         // member-independent inputs are requested ahead of their phase: L2 latency never shows
@@ -729,6 +767,10 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
     if constexpr (KO >= n) { if (nqB == n) phaseB(std::integral_constant<int, n>{}); }
             ENS_B_CASE(1) ENS_B_CASE(2) ENS_B_CASE(3) ENS_B_CASE(4) ENS_B_CASE(5) ENS_B_CASE(6)
 #undef ENS_B_CASE
+            if (OBS) {
+#pragma unroll
+                for (int j = 0; j < KO; ++j) obs_take(j, x + 1);
+            }
             if (TIMING && wtiming) twB += clock64() - tw0;
             if ((nqA || hasE) && x + 1 < steps) fetch_raw_inputs(x + 1);   // consumed in the next A
             ENS_TICK(2)   // B compute
@@ -826,6 +868,25 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
             halo_parity ^= 1u;
             done_parity ^= 1u;
             ENS_TICK(7)
+        }
+        if (OBS) {
+            // this member's sum over the CTA, in a fixed order (lanes by shuffle, warps one after the other): deterministic
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                m_acc = add(m_acc, __shfl_down_sync(0xffffffffu, m_acc, off));
+                m_cnt += __shfl_down_sync(0xffffffffu, m_cnt, off);
+            }
+            double *red = reinterpret_cast<double *>(smem + L.off_coef + 80);
+            long long *redc = reinterpret_cast<long long *>(red + 32);
+            if ((tid & 31) == 0) { red[tid >> 5] = m_acc; redc[tid >> 5] = m_cnt; }
+            bar_sync(BAR_A, NTC);
+            if (tid == 0) {
+                double t = 0.0;
+                long long n = 0;
+                for (int w = 0; w < NTC / 32; ++w) { t = add(t, red[w]); n += redc[w]; }
+                a.misfit_part[(long long)m * CL + k] = t;
+                a.count_part[(long long)m * CL + k] = n;
+            }
         }
     }
     if (dma_lane) bulk_wait_all();

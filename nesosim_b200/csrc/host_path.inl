@@ -167,7 +167,11 @@ extern "C" int nesosim_run_season_host(nesosim_ctx *ctx, const double *precip, c
     if (share && (harr[2] || harr[3])) {
         CU(cudaEventSynchronize(hp->shared_ready));
         const long long n = var_elems_per_member(ctx, 2), hstride = out_host->plane_member_stride;
-        const int nthreads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+        // replication threads: at most 8, and no more than this process' share of the host cores when every visible GPU
+        // runs a rank of its own (one process per GPU: 8 ranks x 8 threads oversubscribed the memory bus of the box);
+        // NESOSIM_HOST_THREADS overrides
+        int nthreads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / (unsigned)std::max(1, nesosim_device_count())));
+        if (const char *e = getenv("NESOSIM_HOST_THREADS")) nthreads = std::max(1, atoi(e));
         std::vector<std::thread> pool;
         for (int t = 0; t < nthreads; ++t)
             pool.emplace_back([=]() {

@@ -142,6 +142,17 @@ struct HostPath {
 
 }  // namespace
 
+// A season-resident launch whose operand-range flag has not been looked at yet (asynchronous mode, nesosim_set_async).
+struct PendingSeason {
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;   // around the kernel; after the flag's copy to the host
+    int *flag_host = nullptr;                                    // pinned
+    const double *ic_dev = nullptr;
+    int ic_per_member = 0, m0 = 0, mcount = 0;
+    nesosim_outputs out;
+    std::vector<nesosim_member_params> params;                   // of the whole context (the rerun uploads them again)
+    cudaStream_t stream = nullptr;
+};
+
 struct nesosim_ctx {
     nesosim_config cfg;
     long long plane;
@@ -164,6 +175,11 @@ struct nesosim_ctx {
     int n_sets = 1;                 // forcing sets (nesosim_set_forcing_sets); 1 = plain season
     int *member_set_dev = nullptr, *set_steps_dev = nullptr;
     int ens_status = 0;             // flag read back from the last season-resident launch (1 = rerun needed)
+    bool async_mode = false;        // nesosim_set_async: run_season never synchronises; flags are resolved by nesosim_sync
+    std::vector<PendingSeason> pending;
+    int *flag_pool = nullptr;       // pinned host slots the pending seasons' flags are copied into
+    unsigned flag_next = 0;
+    std::vector<nesosim_member_params> last_params;
     long long ens_reruns = 0;
     uint8_t *tile_land_dev = nullptr;   // per day-kernel tile: no ocean cell inside (day_step_land_tile)
     bool land_shortcut = true;
@@ -268,6 +284,20 @@ int check_outputs(const nesosim_ctx *ctx, const nesosim_outputs *o) {
 // doubles, then the two flags, the two CTA counters and the time-out mark.
 // Day kernels are launched with programmatic stream serialization (see pdl_wait in day_kernels.cuh): the next day's
 // CTAs may start their day-independent prologue while this day's last CTAs finish.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_day_kernel_smem(void (*kern)(KArgs...), dim3 grid, int threads, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
 template <typename... KArgs, typename... Args>
 cudaError_t launch_day_kernel(void (*kern)(KArgs...), dim3 grid, int threads, cudaStream_t st, bool pdl, Args... args) {
     cudaLaunchConfig_t cfg = {};
@@ -389,7 +419,8 @@ int launch_day(nesosim_ctx *ctx, int x, const double *P, const double *C, const 
         return NESOSIM_OK;
     }
     dim3 grid((a.nx + TX - 1) / TX, (a.ny + TY - 1) / TY, mcount);
-    if (strip_step && ctx->strip.on && a.sw.dynamics && (ctx->strip.has_up || ctx->strip.has_dn)) {
+    const bool stripped = strip_step && ctx->strip.on && a.sw.dynamics && (ctx->strip.has_up || ctx->strip.has_dn);
+    if (stripped) {
         StripLink s;
         strip_link(ctx, x, grid, &s);
         if (ctx->day_variant == 512) CU(launch_day_kernel(day_step_strip_kernel_512, grid, 512, st, pdl, a, s));
@@ -441,10 +472,11 @@ struct EnsVariant {
     void (*kernel)(const EnsArgs);
     void (*kernel_timing)(const EnsArgs);
     void (*kernel_sets)(const EnsArgs);    // members on different forcing sets (nesosim_set_forcing_sets)
+    void (*kernel_obs)(const EnsArgs);     // misfit mode: observations reduced inside the kernel (nesosim_run_season_misfit)
 };
 #define ENS_V(ntc, kr, ko) \
     {"t" #ntc "r" #kr "o" #ko, ntc, kr, ko, ensemble_season_kernel<ntc, kr, ko, false, false>, ensemble_season_kernel<ntc, kr, ko, true, false>, \
-     ensemble_season_kernel<ntc, kr, ko, false, true>}
+     ensemble_season_kernel<ntc, kr, ko, false, true>, ensemble_season_kernel<ntc, kr, ko, false, false, true>}
 const EnsVariant *ens_variants(int *n) {
     static const EnsVariant v[] = {
         ENS_V(352, 3, 2), ENS_V(224, 4, 3), ENS_V(480, 2, 2), ENS_V(608, 2, 1), ENS_V(480, 2, 1), ENS_V(736, 2, 1), ENS_V(352, 6, 5),
@@ -692,8 +724,15 @@ bool ensemble_eligible(nesosim_ctx *ctx, int first_step, int num_steps, const ne
     return true;
 }
 
+struct ObsDevice {                      // misfit mode: device arrays of the sorted observations (see EnsArgs)
+    const int *first = nullptr, *day = nullptr;
+    const double *val = nullptr;
+    double *misfit_part = nullptr;
+    long long *count_part = nullptr;
+};
+
 int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, const nesosim_outputs *out, int m0,
-                 int mcount, cudaStream_t st) {
+                 int mcount, cudaStream_t st, const ObsDevice *obs = nullptr) {
     const nesosim_config &c = ctx->cfg;
     const long long plane = ctx->plane;
     const int steps = c.num_days - 1;
@@ -727,7 +766,7 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     const EnsVariant *v = &ens_variants(&nv_)[e.variant];
     const int cl = e.tables.cluster;
     const bool dbg_timing = getenv("NESOSIM_ENS_TIMING") != nullptr;   // debug aid: per-phase cycle totals to stderr
-    void (*kernel)(const EnsArgs) = ctx->member_set_dev ? v->kernel_sets : (dbg_timing ? v->kernel_timing : v->kernel);
+    void (*kernel)(const EnsArgs) = obs ? v->kernel_obs : ctx->member_set_dev ? v->kernel_sets : (dbg_timing ? v->kernel_timing : v->kernel);
     CU(cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem_bytes));
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[1];
@@ -762,9 +801,15 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     a.sw = Switches{c.dynamicsInc == 1, c.leadlossInc == 1, c.windpackInc == 1, c.atmlossInc == 1, 0};
     a.st = e.tables;
     a.status = ctx->flags_dev;
+    a.obs_first = obs ? obs->first : nullptr;
+    a.obs_day = obs ? obs->day : nullptr;
+    a.obs_val = obs ? obs->val : nullptr;
+    a.conc = ctx->C;
+    a.misfit_part = obs ? obs->misfit_part : nullptr;
+    a.count_part = obs ? obs->count_part : nullptr;
     a.dbg = getenv("NESOSIM_ENS_DBG") ? atoi(getenv("NESOSIM_ENS_DBG")) : 0;
     a.timing = nullptr;
-    if (dbg_timing && !ctx->member_set_dev) {
+    if (dbg_timing && !ctx->member_set_dev && !obs) {
         CU(cudaMalloc(&a.timing, sizeof(long long) * ENS_NTIMER * ncl * cl));
         CU(cudaMemset(a.timing, 0, sizeof(long long) * ENS_NTIMER * ncl * cl));
     }
@@ -780,6 +825,25 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     CU(cudaGetLastError());
     // The kernel only carries the fast divisions; if an operand left their proven range the season is redone by
     // the general kernels (run_members looks at ens_status).  Reading the flag needs the stream to finish.
+    if (ctx->async_mode && !dbg_timing && !obs) {
+        // Asynchronous mode: the flag travels to pinned host memory behind the kernel and is looked at by nesosim_sync
+        // (or by a later call, without waiting).  The launch keeps its own pair of timing events.
+        PendingSeason p;
+        p.ev0 = ctx->ens_ev[0];
+        p.ev1 = ctx->ens_ev[1];
+        ctx->ens_ev[0] = ctx->ens_ev[1] = nullptr;
+        CU(cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming));
+        p.flag_host = ctx->flag_pool + (ctx->flag_next++ % 256);      // (at most 64 seasons are ever pending)
+        *p.flag_host = 0;
+        CU(cudaMemcpyAsync(p.flag_host, ctx->flags_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(p.done, st));
+        p.ic_dev = ic_dev; p.ic_per_member = ic_per_member; p.m0 = m0; p.mcount = mcount; p.out = *out;
+        p.params = ctx->last_params;
+        p.stream = st;
+        ctx->pending.push_back(std::move(p));
+        ctx->ens_status = 0;
+        return NESOSIM_OK;
+    }
     CU(cudaMemcpyAsync(&ctx->ens_status, ctx->flags_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     {
@@ -789,7 +853,7 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
             ctx->ens_kernel_launches++;
         }
     }
-    if (dbg_timing && !ctx->member_set_dev) {
+    if (dbg_timing && !ctx->member_set_dev && !obs) {
         std::vector<long long> h(ENS_NTIMER * ncl * cl);
         CU(cudaMemcpy(h.data(), a.timing, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(a.timing);
@@ -808,6 +872,55 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
             fprintf(stderr, "\n");
         }
     }
+    return NESOSIM_OK;
+}
+
+int run_members(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, const nesosim_outputs *out, int m0,
+                int mcount, int first_step, int num_steps, cudaStream_t st);
+
+void pending_release(PendingSeason &p) {
+    if (p.ev0) cudaEventDestroy(p.ev0);
+    if (p.ev1) cudaEventDestroy(p.ev1);
+    if (p.done) cudaEventDestroy(p.done);
+    p.ev0 = p.ev1 = p.done = nullptr;
+    p.flag_host = nullptr;
+}
+
+// Look at the flags of the asynchronous season launches that have finished (`block`: wait for all of them).  A season
+// whose operands left the fast divisions' range is redone by the general kernels here, as the synchronous mode does
+// inside nesosim_run_season.  Returns the number of seasons redone through *redone.
+int resolve_pending(nesosim_ctx *ctx, bool block, int *redone) {
+    size_t keep = 0;
+    for (size_t i = 0; i < ctx->pending.size(); ++i) {
+        PendingSeason &p = ctx->pending[i];
+        cudaError_t e = block ? cudaEventSynchronize(p.done) : cudaEventQuery(p.done);
+        if (e == cudaErrorNotReady) {
+            cudaGetLastError();
+            if (keep != i) ctx->pending[keep] = std::move(p);
+            ++keep;
+            continue;
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "waiting for an asynchronous season");
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.ev0, p.ev1) == cudaSuccess) {
+            ctx->ens_kernel_ms += ms;
+            ctx->ens_kernel_launches++;
+        }
+        const int flag = *p.flag_host;
+        if (flag) {
+            ctx->ens_reruns++;
+            if (redone) ++*redone;
+            const int saved = ctx->path;
+            ctx->path = 1;
+            int rc = upload_coef(ctx, p.params.data(), p.stream);
+            if (!rc) rc = run_members(ctx, p.ic_dev, p.ic_per_member, &p.out, p.m0, p.mcount, 0, -1, p.stream);
+            ctx->path = saved;
+            if (rc) return rc;
+            CU(cudaStreamSynchronize(p.stream));
+        }
+        pending_release(p);
+    }
+    ctx->pending.resize(keep);
     return NESOSIM_OK;
 }
 
@@ -928,6 +1041,12 @@ int nesosim_destroy(nesosim_ctx *ctx) {
     if (!ctx) return NESOSIM_OK;
     cudaSetDevice(ctx->cfg.device);
     ensemble_release(ctx->ens);
+    for (auto &p : ctx->pending) {
+        if (p.done) cudaEventSynchronize(p.done);
+        pending_release(p);
+    }
+    ctx->pending.clear();
+    if (ctx->flag_pool) cudaFreeHost(ctx->flag_pool);
     for (int i = 0; i < 2; ++i)
         if (ctx->ens_ev[i]) cudaEventDestroy(ctx->ens_ev[i]);
     strip_release(ctx);
@@ -1003,8 +1122,129 @@ int nesosim_run_season(nesosim_ctx *ctx, const nesosim_member_params *params_hos
     if (rc) return rc;
     CU(cudaSetDevice(ctx->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->async_mode) {
+        ctx->last_params.assign(params_host, params_host + ctx->cfg.n_members);
+        if ((rc = resolve_pending(ctx, ctx->pending.size() >= 64, nullptr))) return rc;   // finished ones only, unless the list is long
+    }
     if ((rc = upload_coef(ctx, params_host, st))) return rc;
     return run_members(ctx, ic_dev, ic_per_member, out, 0, ctx->cfg.n_members, first_step, num_steps, st);
+}
+
+__global__ void misfit_finish_kernel(const double *part, const long long *cpart, int cl, int M, double *misfit, long long *count) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    double t = 0.0;
+    long long n = 0;
+    for (int k = 0; k < cl; ++k) {          // strips in order: deterministic
+        t = __dadd_rn(t, part[(long long)m * cl + k]);
+        n += cpart[(long long)m * cl + k];
+    }
+    misfit[m] = t;
+    if (count) count[m] = n;
+}
+
+int nesosim_run_season_misfit(nesosim_ctx *ctx, const nesosim_member_params *params_host, const double *ic_dev,
+                              int ic_per_member, int64_t n_obs, const int32_t *obs_day_host, const int32_t *obs_row_host,
+                              const int32_t *obs_col_host, const double *obs_depth_host, double *misfit_dev,
+                              int64_t *count_dev, void *stream) {
+    if (!ctx || !params_host || !misfit_dev || n_obs < 0) return fail(NESOSIM_ERR_ARG, "bad argument");
+    if (n_obs > 0 && (!obs_day_host || !obs_row_host || !obs_col_host || !obs_depth_host)) return fail(NESOSIM_ERR_ARG, "NULL observation array");
+    if (!ctx->P) return fail(NESOSIM_ERR_STATE, "nesosim_set_forcing has not been called");
+    if (ctx->member_set_dev) return fail(NESOSIM_ERR_ARG, "misfit mode runs on one shared forcing");
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const nesosim_config &c = ctx->cfg;
+    const int T = c.num_days, ny = c.ny, nx = c.nx, M = c.n_members;
+    nesosim_outputs none{};
+    none.depth_member_stride = (int64_t)T * 2 * ctx->plane;
+    none.plane_member_stride = (int64_t)T * ctx->plane;
+    const char *why = "";
+    if (!ensemble_eligible(ctx, 0, T - 1, &none, &why))
+        return fail(NESOSIM_ERR_ARG, std::string("misfit mode needs the season-resident kernel: ") + why);
+    int rc = upload_coef(ctx, params_host, st);
+    if (rc) return rc;
+    // observations -> (strip, index in the strip's ocean list), sorted by owner and day, one sentinel per ocean cell
+    const StripTables &t = ctx->ens.tables;
+    const int cl = t.cluster;
+    std::vector<int> owner((size_t)ny * nx, -1);        // position in the concatenated code lists (ocean_off[k] + idx)
+    int list_end = 0;
+    for (int k = 0; k < cl; ++k) {
+        int idx = 0;
+        for (int r = t.row0[k]; r < t.row0[k + 1]; ++r)
+            for (int col = 0; col < nx; ++col) {
+                const uint8_t m = ctx->mask_host[(size_t)r * nx + col];
+                if (!(m > 10 || m < 1)) owner[(size_t)r * nx + col] = t.ocean_off[k] + idx++;
+            }
+        list_end = std::max(list_end, t.ocean_off[k] + idx);
+    }
+    struct Ob { int owner, day; double val; };
+    std::vector<Ob> obs;
+    obs.reserve((size_t)n_obs);
+    for (int64_t i = 0; i < n_obs; ++i) {
+        const int d = obs_day_host[i], r = obs_row_host[i], col = obs_col_host[i];
+        if (d < 0 || d >= T || r < 0 || r >= ny || col < 0 || col >= nx) return fail(NESOSIM_ERR_ARG, "observation outside the grid or the season");
+        const int o = owner[(size_t)r * nx + col];
+        if (o < 0) continue;                             // land / lake: the model value is NaN, the observation is skipped
+        obs.push_back(Ob{o, d, obs_depth_host[i]});
+    }
+    std::stable_sort(obs.begin(), obs.end(), [](const Ob &x, const Ob &y) { return x.owner != y.owner ? x.owner < y.owner : x.day < y.day; });
+    std::vector<int> first((size_t)list_end + 1, -1), days;
+    std::vector<double> vals;
+    days.reserve(obs.size() + list_end + 1);
+    vals.reserve(obs.size() + list_end + 1);
+    size_t p = 0;
+    for (int o = 0; o < list_end; ++o) {
+        first[o] = (int)days.size();
+        while (p < obs.size() && obs[p].owner == o) { days.push_back(obs[p].day); vals.push_back(obs[p].val); ++p; }
+        days.push_back(0x7fffffff);                      // sentinel
+        vals.push_back(0.0);
+    }
+    // device copies (stream-ordered allocations: freed behind the kernel)
+    int *d_first = nullptr, *d_day = nullptr;
+    double *d_val = nullptr, *d_part = nullptr;
+    long long *d_cnt = nullptr;
+    CU(cudaMallocAsync(&d_first, first.size() * sizeof(int), st));
+    CU(cudaMallocAsync(&d_day, days.size() * sizeof(int), st));
+    CU(cudaMallocAsync(&d_val, vals.size() * sizeof(double), st));
+    CU(cudaMallocAsync(&d_part, (size_t)M * cl * sizeof(double), st));
+    CU(cudaMallocAsync(&d_cnt, (size_t)M * cl * sizeof(long long), st));
+    CU(cudaMemcpyAsync(d_first, first.data(), first.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_day, days.data(), days.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_val, vals.data(), vals.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(d_part, 0, (size_t)M * cl * sizeof(double), st));
+    CU(cudaMemsetAsync(d_cnt, 0, (size_t)M * cl * sizeof(long long), st));
+    ObsDevice od;
+    od.first = d_first; od.day = d_day; od.val = d_val; od.misfit_part = d_part; od.count_part = d_cnt;
+    ctx->last_path = 2;
+    rc = run_ensemble(ctx, ic_dev, ic_per_member, &none, 0, M, st, &od);     // synchronises the stream (operand-range flag)
+    if (!rc) {
+        misfit_finish_kernel<<<(M + 127) / 128, 128, 0, st>>>(d_part, d_cnt, cl, M, misfit_dev, (long long *)count_dev);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = fail(NESOSIM_ERR_CUDA, "misfit_finish_kernel launch");
+    }
+    cudaFreeAsync(d_first, st); cudaFreeAsync(d_day, st); cudaFreeAsync(d_val, st); cudaFreeAsync(d_part, st); cudaFreeAsync(d_cnt, st);
+    if (rc) return rc;
+    if (ctx->ens_status) return fail(NESOSIM_ERR_ARG, "an operand left the range of the season-resident kernel's fast divisions; misfit mode has no general-path fallback");
+    return NESOSIM_OK;
+}
+
+int nesosim_set_async(nesosim_ctx *ctx, int on) {
+    if (!ctx) return fail(NESOSIM_ERR_ARG, "NULL context");
+    CU(cudaSetDevice(ctx->cfg.device));
+    if (!on) {
+        int rc = resolve_pending(ctx, true, nullptr);
+        if (rc) return rc;
+    }
+    if (on && !ctx->flag_pool) CU(cudaMallocHost(&ctx->flag_pool, 256 * sizeof(int)));
+    ctx->async_mode = on != 0;
+    return NESOSIM_OK;
+}
+
+int nesosim_sync(nesosim_ctx *ctx, int *seasons_redone) {
+    if (!ctx) return fail(NESOSIM_ERR_ARG, "NULL context");
+    CU(cudaSetDevice(ctx->cfg.device));
+    if (seasons_redone) *seasons_redone = 0;
+    return resolve_pending(ctx, true, seasons_redone);
 }
 
 int nesosim_step_day(nesosim_ctx *ctx, int x, const double *conc_dev, const double *precip_dev,
@@ -1124,7 +1364,7 @@ int64_t nesosim_launch_count(const nesosim_ctx *ctx) { return ctx ? ctx->launche
 int64_t nesosim_rerun_count(const nesosim_ctx *ctx) { return ctx ? ctx->ens_reruns : 0; }
 int nesosim_season_kernel_time(const nesosim_ctx *ctx, double *total_ms, int64_t *launches) {
     if (!ctx || !total_ms || !launches) return fail(NESOSIM_ERR_ARG, "NULL argument");
-    *total_ms = ctx->ens_kernel_ms;
+    *total_ms = ctx->ens_kernel_ms;           // (asynchronous launches count once nesosim_sync / a later call has seen them)
     *launches = ctx->ens_kernel_launches;
     return NESOSIM_OK;
 }

@@ -29,8 +29,10 @@ def depth_misfit(snowDepths, conc, obs):
     return torch.where(ok, diff * diff, torch.zeros_like(diff)).sum(dim=1), ok.sum(dim=1)
 
 
-def run_ensemble(mask, forcing, ic, params, dx, obs, rank=0, world=1, device=0, group=None, **flags):
-    """Returns (misfit[M], n_used[M]) as numpy arrays in member order (identical on every rank)."""
+def run_ensemble(mask, forcing, ic, params, dx, obs, rank=0, world=1, device=0, group=None, fused=None, **flags):
+    """Returns (misfit[M], n_used[M]) as numpy arrays in member order (identical on every rank).  ``fused``: None =
+    inside the season kernel where it applies, True = insist on it, False = depths to HBM + reduction there (the
+    round-1 path, kept as the cross-check)."""
     import torch
     from .engine import SnowBudgetEngine
     params = np.asarray(params, dtype=np.float64).reshape(-1, 4)
@@ -39,8 +41,19 @@ def run_ensemble(mask, forcing, ic, params, dx, obs, rank=0, world=1, device=0, 
     T = forcing["precip"].shape[0]
     eng = SnowBudgetEngine(mask, T, dx, n_members=hi - lo, device=device, **flags)
     eng.set_forcing(forcing["precip"], forcing["conc"], forcing["wind"], forcing["drift"])
-    out = eng.run_season(params[lo:hi], ic, eng.alloc_outputs(names=("snowDepths",)))
-    mis, used = depth_misfit(out["snowDepths"], eng._forcing[1], obs)
+    from . import _lib
+    try:
+        # fused: the observation operator and the reduction run inside the season-resident kernel, nothing is stored
+        mis, used = eng.run_season_misfit(params[lo:hi], ic, obs)
+    except _lib.NesosimError as e:
+        if fused is True or e.code != _lib.ERR_ARG:
+            raise
+        # grids the season-resident kernel does not take: depths to HBM, reduced there (still nothing crosses PCIe)
+        out = eng.run_season(params[lo:hi], ic, eng.alloc_outputs(names=("snowDepths",)))
+        mis, used = depth_misfit(out["snowDepths"], eng._forcing[1], obs)
+    if fused is False:
+        out = eng.run_season(params[lo:hi], ic, eng.alloc_outputs(names=("snowDepths",)))
+        mis, used = depth_misfit(out["snowDepths"], eng._forcing[1], obs)
     eng.close()
     if world > 1:
         mis = sharding.gather_member_results(mis, M, rank, world, group)

@@ -583,6 +583,52 @@ def test_tall_narrow_grid_is_not_taken_by_the_season_kernel(cuda):
     compare_all(got, refs)
 
 
+def test_asynchronous_mode_back_to_back_seasons(cuda):
+    """nesosim_set_async: run_season never synchronises; three seasons with different parameters are enqueued back to
+    back into three output sets, nesosim_sync then resolves their operand-range flags (none raised)."""
+    from nesosim_b200.engine import SnowBudgetEngine
+    mask = S.region_mask(dx=100000)
+    T, M = 20, 4
+    forcing = S.make_season(mask, T, seed=61)
+    ic = S.make_ic(mask, seed=61)
+    eng = SnowBudgetEngine(mask, T, 100000, n_members=M, atmlossInc=1)
+    eng.set_path("ensemble")
+    eng.set_forcing(forcing["precip"], forcing["conc"], forcing["wind"], forcing["drift"])
+    eng.set_async(True)
+    ic_dev = eng._dev(ic)
+    sets = [S.ensemble_params(M, seed=61 + i) for i in range(3)]
+    outs = [eng.run_season(p, ic_dev, eng.alloc_outputs()) for p in sets]
+    assert eng.sync() == 0
+    k0 = eng.season_kernel_time()
+    assert k0[1] == 3 and k0[0] > 0
+    for p, out in zip(sets, outs):
+        for m in range(M):
+            ref = O.run_season(forcing, ic, mask, 100000, oracle_params(p[m]), O.Flags(atmlossInc=1))
+            for name in out:
+                assert_parity(out[name][m].cpu().numpy(), ref[name], name)
+    eng.set_async(False)
+    eng.close()
+
+
+def test_asynchronous_mode_redoes_an_out_of_range_season_at_sync(cuda):
+    from nesosim_b200.engine import SnowBudgetEngine
+    mask = S.region_mask(dx=100000)
+    T = 6
+    forcing = S.make_season(mask, T, seed=62)
+    ic = S.make_ic(mask, seed=62) * 1e-299
+    eng = SnowBudgetEngine(mask, T, 100000, n_members=2, atmlossInc=1)
+    eng.set_forcing(forcing["precip"], forcing["conc"], forcing["wind"], forcing["drift"])
+    eng.set_async(True)
+    params = S.ensemble_params(2, seed=62)
+    out = eng.run_season(params, eng._dev(ic))
+    assert eng.sync() == 1 and eng.rerun_count() == 1
+    for m in range(2):
+        ref = O.run_season(forcing, ic, mask, 100000, oracle_params(params[m]), O.Flags(atmlossInc=1))
+        for name in out:
+            assert_parity(out[name][m].cpu().numpy(), ref[name], name)
+    eng.close()
+
+
 # ------------------------------------------------------------------------------------ per-function KATs
 
 def test_smooth_plain_and_nan_branch(cuda):
@@ -643,7 +689,7 @@ def test_ensemble_driver_reduces_on_the_device(cuda):
     pick = ocean[rng.choice(len(ocean), 200, replace=False)]
     day = rng.integers(1, T, 200)
     obs = (day, pick[:, 0], pick[:, 1], 0.2 * rng.random(200))
-    mis, used = ENS.run_ensemble(mask, forcing, ic, params, 100000, obs, atmlossInc=1)
+    mis, used = ENS.run_ensemble(mask, forcing, ic, params, 100000, obs, atmlossInc=1, fused=False)
     for m in range(M):
         ref = O.run_season(forcing, ic, mask, 100000, oracle_params(params[m]), O.Flags(atmlossInc=1))
         with np.errstate(all="ignore"):
@@ -653,6 +699,66 @@ def test_ensemble_driver_reduces_on_the_device(cuda):
         ok = np.isfinite(d)
         assert used[m] == ok.sum() and used[m] > 20
         assert np.isclose(mis[m], np.sum(d[ok] ** 2), rtol=1e-12)
+
+
+@pytest.mark.parametrize("cluster", [None, "8"])
+def test_misfit_fused_into_the_season_kernel(cuda, cluster, monkeypatch):
+    """N3 fused: the observation operator (snow depth over ice at a day, row, col) and the per-member sum of squares run
+    INSIDE the season-resident kernel, which stores no output array at all.  Observations on land, on day 0, on the last
+    day, repeated at one cell and day, in every strip; result equal to the oracle's to 1e-12 (the sums are formed in a
+    different order), counts exact, and bit-identical from run to run."""
+    from nesosim_b200.engine import SnowBudgetEngine
+    if cluster:
+        monkeypatch.setenv("NESOSIM_ENS_CLUSTER", cluster)
+    mask = S.region_mask(dx=100000)
+    T, M = 30, 9
+    forcing = S.make_season(mask, T, seed=63)
+    ic = S.make_ic(mask, seed=63) * 3
+    params = S.ensemble_params(M, seed=63)
+    rng = np.random.default_rng(63)
+    n = 1500
+    row, col = rng.integers(0, 90, n), rng.integers(0, 90, n)          # a good half of them on land
+    day = rng.integers(0, T, n)
+    day[:40] = 0
+    day[40:80] = T - 1
+    row[100:110], col[100:110], day[100:110] = row[100], col[100], day[100]      # ten observations of one cell and day
+    depth = 0.3 * rng.random(n)
+    obs = (day, row, col, depth)
+    eng = SnowBudgetEngine(mask, T, 100000, n_members=M, atmlossInc=1)
+    eng.set_forcing(forcing["precip"], forcing["conc"], forcing["wind"], forcing["drift"])
+    l0 = eng.launch_count()
+    mis, used = eng.run_season_misfit(params, ic, obs)
+    mis, used = mis.cpu().numpy(), used.cpu().numpy()
+    assert eng.launch_count() - l0 == 4          # pre-pass (2), season kernel, the M-scalar finish: nothing else
+    again = eng.run_season_misfit(params, ic, obs)[0].cpu().numpy()
+    assert np.array_equal(mis, again)
+    eng.close()
+    for m in range(M):
+        ref = O.run_season(forcing, ic, mask, 100000, oracle_params(params[m]), O.Flags(atmlossInc=1))
+        with np.errstate(all="ignore"):
+            model = (ref["snowDepths"][day, 0, row, col] + ref["snowDepths"][day, 1, row, col]) / forcing["conc"][day, row, col]
+        d = model - depth
+        ok = np.isfinite(d)
+        assert used[m] == ok.sum() and used[m] > 100
+        assert np.isclose(mis[m], np.sum(d[ok] ** 2), rtol=1e-12, atol=0.0)
+    # the driver takes the fused path by default and agrees with the HBM round trip
+    from nesosim_b200 import ensemble as ENS
+    a = ENS.run_ensemble(mask, forcing, ic, params, 100000, obs, atmlossInc=1, fused=True)
+    b = ENS.run_ensemble(mask, forcing, ic, params, 100000, obs, atmlossInc=1, fused=False)
+    assert np.allclose(a[0], b[0], rtol=1e-12, atol=0.0) and np.array_equal(a[1], b[1])
+
+
+def test_misfit_mode_refuses_grids_the_season_kernel_does_not_take(cuda):
+    from nesosim_b200 import _lib
+    from nesosim_b200.engine import SnowBudgetEngine
+    mask = S.region_mask(shape=(40, 130), kind="disc")
+    forcing = S.make_season(mask, 4, seed=64)
+    eng = SnowBudgetEngine(mask, 4, 50000, n_members=2)
+    eng.set_forcing(forcing["precip"], forcing["conc"], forcing["wind"], forcing["drift"])
+    with pytest.raises(_lib.NesosimError) as e:
+        eng.run_season_misfit(S.ensemble_params(2, seed=1), None, ([1], [5], [5], [0.1]))
+    assert e.value.code == _lib.ERR_ARG and "nx > 96" in str(e.value)
+    eng.close()
 
 
 def test_op_dynamics(cuda):
