@@ -231,10 +231,21 @@ def measured_peak():
 def run_ours(args):
     import torch
     rank, world, local = dist_env()
+    torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
+        # NCCL prints its version banner on stdout when the communicator comes up: keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     from nesosim_b200 import build
     if rank == 0:
         build.build(verbose=False)
@@ -548,7 +559,8 @@ def d2h_ceiling(world, gib=1.0, reps=3):
 
 def run_misfit_mode(eng, mask, forcing, params, ic, world, cells_per_step, barrier, n_obs=20000, reps=5):
     """nesosim_run_season_misfit: every member's sum of squared differences to `n_obs` point observations of snow depth
-    over ice, formed inside the season-resident kernel; nothing but M scalars is written.  Labelled apart from the
+    over ice; the season-resident kernel stores only the depths of the observed cell-days (8 B each), a per-member
+    epilogue reduces them to M scalars.  Labelled apart from the
     headline: without the 96 B per member-cell-day of output stores the algorithmic HBM bytes are 41/M per member-cell-day,
     so the bound of this mode is the kernel's fp64 / shared-memory work, not HBM."""
     import torch
@@ -556,14 +568,15 @@ def run_misfit_mode(eng, mask, forcing, params, ic, world, cells_per_step, barri
     ocean = np.argwhere((mask <= 10) & (mask >= 1))
     pick = ocean[rng.integers(0, len(ocean), n_obs)]
     obs = (rng.integers(0, eng.T, n_obs), pick[:, 0], pick[:, 1], 0.3 * rng.random(n_obs))
-    mis, used = eng.run_season_misfit(params, ic, obs)
+    eng.set_observations(obs)                      # compiled against the kernel's cell ownership once, kept on the device
+    mis, used = eng.run_season_misfit(params, ic)
     ref = mis.clone()
     best = None
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        mis, used = eng.run_season_misfit(params, ic, obs)
+        mis, used = eng.run_season_misfit(params, ic)
         e1.record()
         torch.cuda.synchronize()
         best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
@@ -573,12 +586,12 @@ def run_misfit_mode(eng, mask, forcing, params, ic, world, cells_per_step, barri
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     M = eng.M
-    return {"workload": "the headline season, misfit against %d point observations reduced inside the season kernel, no output "
-                        "array stored (calibration mode)" % n_obs,
+    return {"workload": "the headline season in calibration mode: %d point observations sampled inside the season kernel, no output "
+                        "array stored, per-member misfit from a one-CTA-per-member epilogue" % n_obs,
             "ms_per_season": ms, "value": world * cells_per_step / (ms * 1e-3), "unit": UNIT,
             "bytes_per_member_cell_day": 41.0 / M, "bound": "fp64 / shared memory of the season kernel (not HBM: no output stores)",
             "d2h_bytes": 16 * M, "observations_used_member0": int(used[0].item()), "deterministic": bool(torch.equal(ref, mis)),
-            "includes": "observation sort + upload on the host, pre-pass, season kernel, M-scalar finish"}
+            "includes": "pre-pass, season kernel, epilogue (the observations are registered once, outside the timing)"}
 
 
 MULTI_YEARS = list(range(1980, 2021))      # 41 start years, Sep 1 - Apr 30 (run_multiseason.py:30-50)
@@ -659,6 +672,18 @@ def run_multiseason_41(rank, world, local, barrier, peak):
             "identical_to_single_season_run": same, "data": "synthetic, one seed per start year"}
 
 
+def nvlink_tx_kib(index):
+    """Sum of the NVLink data-transmit counters of one GPU (nvidia-smi nvlink -gt d), KiB; None if unavailable."""
+    import re
+    try:
+        txt = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], stdout=subprocess.PIPE,
+                             stderr=subprocess.DEVNULL, text=True, timeout=20).stdout
+        vals = [int(v) for v in re.findall(r"Data Tx:\s*(\d+)\s*KiB", txt)]
+        return sum(vals) if vals else None
+    except Exception:
+        return None
+
+
 def run_domain_5km(rank, world, local, peak, steps=40, gen_days=4, reps=3):
     """5 km pan-Arctic grid (1785 x 1785, real coastline) as `world` row strips, one per GPU, the ghost-row exchange
     fused into the day kernel over peer memory (nesosim_strip_*; domain.run_decomposed_season_peer).  Also runs the
@@ -714,6 +739,7 @@ def run_domain_5km(rank, world, local, peak, steps=40, gen_days=4, reps=3):
     lo_, hi_, elo, ehi = eng._strip_rows
     ic_dev = eng._dev(np.ascontiguousarray(ic[elo:ehi]))
     best = None
+    tx0 = nvlink_tx_kib(local) if rank == 0 else None
     for r in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -727,6 +753,13 @@ def run_domain_5km(rank, world, local, peak, steps=40, gen_days=4, reps=3):
         ms = max_over_ranks(e0.elapsed_time(e1))
         best = ms if best is None else min(best, ms)
 
+    tx1 = nvlink_tx_kib(local) if rank == 0 else None
+    nvlink = None
+    if tx0 is not None and tx1 is not None:
+        nvlink = {"rank0_tx_bytes_per_day_measured": (tx1 - tx0) * 1024.0 / (reps * steps),
+                  "rank0_tx_bytes_per_day_algorithmic": 2 * 2 * n * 8 + 8,
+                  "note": "rank 0 has one neighbour: 2 layers x 2 rows x nx doubles + the 8-byte flag per day, stored by the day "
+                          "kernel straight into the neighbour GPU's memory (nvidia-smi nvlink -gt d, KiB resolution)"}
     # ---- every owned row of every array against the one-GPU run (gathered to rank 0 over NCCL, compared on the device)
     own = slice(lo - elo, lo - elo + (hi - lo))
     names = sorted(outs)
@@ -763,7 +796,7 @@ def run_domain_5km(rank, world, local, peak, steps=40, gen_days=4, reps=3):
                                  "roofline_frac_algorithmic": cells * 137.0 / (one_ms * 1e-3) / 1e9 / peak},
             "speedup_vs_one_gpu": one_ms / best, "identical_to_one_gpu": bool(ok),
             "compared": "all 11 arrays, every owned row, every time slot (NaN patterns and values) on the device",
-            "strip_status": "no time-out on any rank", "launches_per_day": 1,
+            "strip_status": "no time-out on any rank", "launches_per_day": 1, "nvlink": nvlink,
             "data": "synthetic (%d generated days repeated)" % gen_days}
 
 

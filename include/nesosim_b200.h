@@ -167,17 +167,21 @@ int nesosim_final_products(const double *depths_dev, const double *density_dev, 
                            void *stream);
 
 /* Calibration driver (the reference has no counterpart): the season of nesosim_run_season with the
- * observation operator and the reduction FUSED into the season-resident kernel -- no output array is written at all.
- * Observations are points (day slot 0..T-1, row, col, observed snow depth over ice [m]) in host arrays; for every member
- * misfit_dev[m] = sum over observations of (model - observed)^2 with model = (h0+h1)/iceConc at that slot and cell (what
- * main writes as snow depth, NESOSIM.py:654), skipping non-finite differences (land, NaN forcing, zero concentration),
- * and count_dev[m] (may be NULL) = the number of observations used.  Every owned cell's thread walks its own
- * observations; sums are formed per thread, per CTA and per member in a fixed order (deterministic).  Needs the
- * season-resident path (grid up to 96 columns, variable density, one shared forcing); NESOSIM_ERR_ARG otherwise. */
+ * observation sampling FUSED into the season-resident kernel -- no output array is written at all.
+ * nesosim_set_observations registers point observations (day slot 0..T-1, row, col, observed snow depth over ice [m];
+ * host arrays, copied): they are compiled against the kernel's cell ownership once (distinct (cell, day) pairs =
+ * "sample slots", sorted per owning thread) and stay on the device until replaced.  During nesosim_run_season_misfit the
+ * thread that owns an observed cell stores the total depth h0+h1 of the observed days -- 8 bytes per observed cell-day
+ * instead of 96 per cell-day, nothing on the day's critical path waits for it -- and a one-CTA-per-member epilogue forms
+ * model = (h0+h1)/iceConc at that slot and cell (what main writes as snow depth, NESOSIM.py:654) and
+ * misfit_dev[m] = sum over the observations of (model - observed)^2, skipping non-finite differences (land, NaN forcing,
+ * zero concentration); count_dev[m] (may be NULL) = the number of observations used.  Sums are formed in a fixed order
+ * (bit-reproducible).  Needs the season-resident path (grid up to 96 columns, variable density, one shared forcing);
+ * NESOSIM_ERR_ARG otherwise. */
+int nesosim_set_observations(nesosim_ctx *ctx, int64_t n_obs, const int32_t *obs_day_host, const int32_t *obs_row_host,
+                             const int32_t *obs_col_host, const double *obs_depth_host);
 int nesosim_run_season_misfit(nesosim_ctx *ctx, const nesosim_member_params *params_host, const double *ic_dev,
-                              int ic_per_member, int64_t n_obs, const int32_t *obs_day_host, const int32_t *obs_row_host,
-                              const int32_t *obs_col_host, const double *obs_depth_host, double *misfit_dev,
-                              int64_t *count_dev, void *stream);
+                              int ic_per_member, double *misfit_dev, int64_t *count_dev, void *stream);
 
 /* Asynchronous mode.  By default nesosim_run_season on the season-resident path synchronises `stream` once to read
  * the kernel's operand-range flag (see above).  With nesosim_set_async(ctx, 1) it never synchronises: the flag is copied

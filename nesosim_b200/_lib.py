@@ -81,9 +81,10 @@ _SIGNATURES = {
     "nesosim_strip_connect_local": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "nesosim_strip_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "nesosim_strip_set_timeout": (C.c_int, [C.c_void_p, C.c_double]),
-    "nesosim_run_season_misfit": (C.c_int, [C.c_void_p, C.POINTER(MemberParams), C.c_void_p, C.c_int, C.c_int64,
-                                            C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
-                                            C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nesosim_set_observations": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                           C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
+    "nesosim_run_season_misfit": (C.c_int, [C.c_void_p, C.POINTER(MemberParams), C.c_void_p, C.c_int, C.c_void_p,
+                                            C.c_void_p, C.c_void_p]),
     "nesosim_set_async": (C.c_int, [C.c_void_p, C.c_int]),
     "nesosim_sync": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "nesosim_set_path": (C.c_int, [C.c_void_p, C.c_int]),

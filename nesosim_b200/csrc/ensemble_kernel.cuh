@@ -198,15 +198,15 @@ struct EnsArgs {
     double w[9];
     Switches sw;
     StripTables st;
-    // misfit mode (calibration driver): point observations of snow depth over ice, sorted by owning
-    // cell and day; obs_first is indexed like `codes` (ocean list of every strip) and points at the cell's first
-    // observation, every cell's run ends with a sentinel day (INT_MAX).  Per member and CTA one partial sum of squared
-    // differences and one count leave the kernel: misfit_part / count_part [M][cluster].
+    // misfit mode (calibration driver): the (cell, day) pairs at which snow depth is observed, sorted by
+    // owning cell and day ("sample slots"); obs_first is indexed like `codes` (ocean list of every strip) and points at
+    // the cell's first slot, every cell's run ends with a sentinel day (INT_MAX).  The thread that owns a cell stores the
+    // total depth h0+h1 of the observed days into sample_depth[member][slot] -- 8 bytes per observed cell-day instead of
+    // 96 per cell-day -- fire and forget: nothing on the day's critical path waits for memory.  The observation operator
+    // proper (division by the ice concentration) and the sum of squares run in a small epilogue kernel.
     const int *obs_first, *obs_day;
-    const double *obs_val;
-    const double *conc;                // ice concentration [T][plane] (the observation operator divides by it)
-    double *misfit_part;
-    long long *count_part;
+    double *sample_depth;
+    long long sample_stride;
     int dbg;                           // timing experiments only (NESOSIM_ENS_DBG): 1 forcing always from day 0, 2 no L2 prefetch, 4 no bulk stores
     int *status;                       // set to 1 if any operand left the fast divisions' proven range (host reruns)
     long long *timing;                 // debug: [gridDim.x][ENS_NTIMER] phase cycle totals (NULL = off)
@@ -569,20 +569,14 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
             r_h1[j] = LD(HOWN + PEXB + b_ci[j]);
             r_dn[j] = r_adv[j] = r_div[j] = r_lead[j] = r_atm[j] = r_wpl[j] = r_wpg[j] = r_wp[j] = 0.0;
         }
-        // misfit mode: every owned cell walks its own (day-sorted) observations; the modelled quantity is what main writes
-        // as snow depth over ice, (h0+h1)/iceConc (NESOSIM.py:654); non-finite differences (NaN model values, zero
-        // concentration) are skipped.  Nothing but the per-CTA sums ever leaves the SM.
-        double m_acc = 0.0;
-        long long m_cnt = 0;
+        // misfit mode: every owned cell walks its own (day-sorted) sample slots; on an observed day the total depth
+        // goes to the member's sample array and the cursor moves on (the next slot's day is needed tomorrow at the
+        // earliest: its load is never waited for)
         int o_idx[OBS ? KO : 1], o_day[OBS ? KO : 1];
+        double *const m_samples = OBS ? a.sample_depth + (long long)m * a.sample_stride : nullptr;
         auto obs_take = [&](int j, int slot) {
-            while (o_day[j] == slot) {
-                const double C = __ldg(a.conc + (SETS ? (long long)fset * a.T * plane : 0) + (long long)slot * plane + go_own + (b_ci[j] >> 3));
-                const double diff = sub(div_ieee(add(r_h0[j], r_h1[j]), C), __ldg(a.obs_val + o_idx[j]));
-                if (finite(diff)) {
-                    m_acc = add(m_acc, mul(diff, diff));
-                    ++m_cnt;
-                }
+            if (o_day[j] == slot) {
+                m_samples[o_idx[j]] = add(r_h0[j], r_h1[j]);      // snowDepths[:, 0] + snowDepths[:, 1]   (NESOSIM.py:654)
                 ++o_idx[j];
                 o_day[j] = __ldg(a.obs_day + o_idx[j]);
             }
@@ -868,25 +862,6 @@ __global__ void __launch_bounds__(NTC + 32, 1) ensemble_season_kernel(const __gr
             halo_parity ^= 1u;
             done_parity ^= 1u;
             ENS_TICK(7)
-        }
-        if (OBS) {
-            // this member's sum over the CTA, in a fixed order (lanes by shuffle, warps one after the other): deterministic
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                m_acc = add(m_acc, __shfl_down_sync(0xffffffffu, m_acc, off));
-                m_cnt += __shfl_down_sync(0xffffffffu, m_cnt, off);
-            }
-            double *red = reinterpret_cast<double *>(smem + L.off_coef + 80);
-            long long *redc = reinterpret_cast<long long *>(red + 32);
-            if ((tid & 31) == 0) { red[tid >> 5] = m_acc; redc[tid >> 5] = m_cnt; }
-            bar_sync(BAR_A, NTC);
-            if (tid == 0) {
-                double t = 0.0;
-                long long n = 0;
-                for (int w = 0; w < NTC / 32; ++w) { t = add(t, red[w]); n += redc[w]; }
-                a.misfit_part[(long long)m * CL + k] = t;
-                a.count_part[(long long)m * CL + k] = n;
-            }
         }
     }
     if (dma_lane) bulk_wait_all();

@@ -175,6 +175,15 @@ struct nesosim_ctx {
     int n_sets = 1;                 // forcing sets (nesosim_set_forcing_sets); 1 = plain season
     int *member_set_dev = nullptr, *set_steps_dev = nullptr;
     int ens_status = 0;             // flag read back from the last season-resident launch (1 = rerun needed)
+    struct {                        // observations of the calibration driver (nesosim_set_observations)
+        bool ready = false;
+        int *first = nullptr, *day = nullptr;            // sample slots: first slot of every owned cell, day of every slot
+        double *samples = nullptr;                       // [M][stride] total depth at every slot (written by the season kernel)
+        long long stride = 0;
+        double *val = nullptr;                           // per observation: value, sample slot, day, cell
+        int *o_slot = nullptr, *o_day = nullptr, *o_cell = nullptr;
+        long long n_used = 0;
+    } obs;
     bool async_mode = false;        // nesosim_set_async: run_season never synchronises; flags are resolved by nesosim_sync
     std::vector<PendingSeason> pending;
     int *flag_pool = nullptr;       // pinned host slots the pending seasons' flags are copied into
@@ -724,11 +733,10 @@ bool ensemble_eligible(nesosim_ctx *ctx, int first_step, int num_steps, const ne
     return true;
 }
 
-struct ObsDevice {                      // misfit mode: device arrays of the sorted observations (see EnsArgs)
+struct ObsDevice {                      // misfit mode: device arrays of the sample slots (see EnsArgs)
     const int *first = nullptr, *day = nullptr;
-    const double *val = nullptr;
-    double *misfit_part = nullptr;
-    long long *count_part = nullptr;
+    double *sample_depth = nullptr;
+    long long sample_stride = 0;
 };
 
 int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, const nesosim_outputs *out, int m0,
@@ -803,10 +811,8 @@ int run_ensemble(nesosim_ctx *ctx, const double *ic_dev, int ic_per_member, cons
     a.status = ctx->flags_dev;
     a.obs_first = obs ? obs->first : nullptr;
     a.obs_day = obs ? obs->day : nullptr;
-    a.obs_val = obs ? obs->val : nullptr;
-    a.conc = ctx->C;
-    a.misfit_part = obs ? obs->misfit_part : nullptr;
-    a.count_part = obs ? obs->count_part : nullptr;
+    a.sample_depth = obs ? obs->sample_depth : nullptr;
+    a.sample_stride = obs ? obs->sample_stride : 0;
     a.dbg = getenv("NESOSIM_ENS_DBG") ? atoi(getenv("NESOSIM_ENS_DBG")) : 0;
     a.timing = nullptr;
     if (dbg_timing && !ctx->member_set_dev && !obs) {
@@ -1047,6 +1053,8 @@ int nesosim_destroy(nesosim_ctx *ctx) {
     }
     ctx->pending.clear();
     if (ctx->flag_pool) cudaFreeHost(ctx->flag_pool);
+    cudaFree(ctx->obs.first); cudaFree(ctx->obs.day); cudaFree(ctx->obs.val); cudaFree(ctx->obs.samples);
+    cudaFree(ctx->obs.o_slot); cudaFree(ctx->obs.o_day); cudaFree(ctx->obs.o_cell);
     for (int i = 0; i < 2; ++i)
         if (ctx->ens_ev[i]) cudaEventDestroy(ctx->ens_ev[i]);
     strip_release(ctx);
@@ -1130,40 +1138,65 @@ int nesosim_run_season(nesosim_ctx *ctx, const nesosim_member_params *params_hos
     return run_members(ctx, ic_dev, ic_per_member, out, 0, ctx->cfg.n_members, first_step, num_steps, st);
 }
 
-__global__ void misfit_finish_kernel(const double *part, const long long *cpart, int cl, int M, double *misfit, long long *count) {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= M) return;
-    double t = 0.0;
-    long long n = 0;
-    for (int k = 0; k < cl; ++k) {          // strips in order: deterministic
-        t = __dadd_rn(t, part[(long long)m * cl + k]);
-        n += cpart[(long long)m * cl + k];
+// Epilogue of the misfit mode: one CTA per member.  model = sampled depth / ice concentration of that day and cell
+// (what main writes as snow depth over ice, NESOSIM.py:654); squared differences to the observations are summed in a
+// fixed order (observation i belongs to thread i % 256, threads are combined by shuffles, warps one after the other).
+struct MisfitArgs {
+    const double *sample_depth;     // [M][stride]
+    long long stride;
+    const int *obs_slot, *obs_day, *obs_cell;
+    const double *obs_val;
+    const double *conc;             // [T][plane]
+    long long plane, n_obs;
+    double *misfit;
+    long long *count;
+};
+__global__ void __launch_bounds__(256) misfit_finish_kernel(const __grid_constant__ MisfitArgs a) {
+    const int m = blockIdx.x;
+    const double *samp = a.sample_depth + (long long)m * a.stride;
+    double acc = 0.0;
+    long long cnt = 0;
+    for (long long i = threadIdx.x; i < a.n_obs; i += 256) {
+        const double C = __ldg(a.conc + (long long)a.obs_day[i] * a.plane + a.obs_cell[i]);
+        const double diff = sub(div_ieee(samp[a.obs_slot[i]], C), a.obs_val[i]);
+        if (nesosim::finite(diff)) {
+            acc = add(acc, mul(diff, diff));
+            ++cnt;
+        }
     }
-    misfit[m] = t;
-    if (count) count[m] = n;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        acc = add(acc, __shfl_down_sync(0xffffffffu, acc, off));
+        cnt += __shfl_down_sync(0xffffffffu, cnt, off);
+    }
+    __shared__ double red[8];
+    __shared__ long long redc[8];
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = acc; redc[threadIdx.x >> 5] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        long long n = 0;
+        for (int w = 0; w < 8; ++w) { t = add(t, red[w]); n += redc[w]; }
+        a.misfit[m] = t;
+        if (a.count) a.count[m] = n;
+    }
 }
 
-int nesosim_run_season_misfit(nesosim_ctx *ctx, const nesosim_member_params *params_host, const double *ic_dev,
-                              int ic_per_member, int64_t n_obs, const int32_t *obs_day_host, const int32_t *obs_row_host,
-                              const int32_t *obs_col_host, const double *obs_depth_host, double *misfit_dev,
-                              int64_t *count_dev, void *stream) {
-    if (!ctx || !params_host || !misfit_dev || n_obs < 0) return fail(NESOSIM_ERR_ARG, "bad argument");
+// Observations of the calibration driver, compiled against the strip tables and kept on the device until they are
+// replaced: -> (strip, index in the strip's ocean list), sorted by owner and day, one sentinel per ocean cell.
+int nesosim_set_observations(nesosim_ctx *ctx, int64_t n_obs, const int32_t *obs_day_host, const int32_t *obs_row_host,
+                             const int32_t *obs_col_host, const double *obs_depth_host) {
+    if (!ctx || n_obs < 0) return fail(NESOSIM_ERR_ARG, "bad argument");
     if (n_obs > 0 && (!obs_day_host || !obs_row_host || !obs_col_host || !obs_depth_host)) return fail(NESOSIM_ERR_ARG, "NULL observation array");
-    if (!ctx->P) return fail(NESOSIM_ERR_STATE, "nesosim_set_forcing has not been called");
-    if (ctx->member_set_dev) return fail(NESOSIM_ERR_ARG, "misfit mode runs on one shared forcing");
     CU(cudaSetDevice(ctx->cfg.device));
-    cudaStream_t st = (cudaStream_t)stream;
     const nesosim_config &c = ctx->cfg;
-    const int T = c.num_days, ny = c.ny, nx = c.nx, M = c.n_members;
+    const int T = c.num_days, ny = c.ny, nx = c.nx;
     nesosim_outputs none{};
     none.depth_member_stride = (int64_t)T * 2 * ctx->plane;
     none.plane_member_stride = (int64_t)T * ctx->plane;
     const char *why = "";
     if (!ensemble_eligible(ctx, 0, T - 1, &none, &why))
         return fail(NESOSIM_ERR_ARG, std::string("misfit mode needs the season-resident kernel: ") + why);
-    int rc = upload_coef(ctx, params_host, st);
-    if (rc) return rc;
-    // observations -> (strip, index in the strip's ocean list), sorted by owner and day, one sentinel per ocean cell
     const StripTables &t = ctx->ens.tables;
     const int cl = t.cluster;
     std::vector<int> owner((size_t)ny * nx, -1);        // position in the concatenated code lists (ocean_off[k] + idx)
@@ -1177,7 +1210,7 @@ int nesosim_run_season_misfit(nesosim_ctx *ctx, const nesosim_member_params *par
             }
         list_end = std::max(list_end, t.ocean_off[k] + idx);
     }
-    struct Ob { int owner, day; double val; };
+    struct Ob { int owner, day, cell; double val; };
     std::vector<Ob> obs;
     obs.reserve((size_t)n_obs);
     for (int64_t i = 0; i < n_obs; ++i) {
@@ -1185,45 +1218,84 @@ int nesosim_run_season_misfit(nesosim_ctx *ctx, const nesosim_member_params *par
         if (d < 0 || d >= T || r < 0 || r >= ny || col < 0 || col >= nx) return fail(NESOSIM_ERR_ARG, "observation outside the grid or the season");
         const int o = owner[(size_t)r * nx + col];
         if (o < 0) continue;                             // land / lake: the model value is NaN, the observation is skipped
-        obs.push_back(Ob{o, d, obs_depth_host[i]});
+        obs.push_back(Ob{o, d, r * nx + col, obs_depth_host[i]});
     }
     std::stable_sort(obs.begin(), obs.end(), [](const Ob &x, const Ob &y) { return x.owner != y.owner ? x.owner < y.owner : x.day < y.day; });
-    std::vector<int> first((size_t)list_end + 1, -1), days;
-    std::vector<double> vals;
-    days.reserve(obs.size() + list_end + 1);
-    vals.reserve(obs.size() + list_end + 1);
+    // sample slots: the distinct (cell, day) pairs, per owning cell in day order, one sentinel behind every cell's run
+    std::vector<int> first((size_t)list_end + 1, -1), slot_day, o_slot(obs.size()), o_day(obs.size()), o_cell(obs.size());
+    std::vector<double> o_val(obs.size());
+    slot_day.reserve(obs.size() + list_end + 1);
     size_t p = 0;
     for (int o = 0; o < list_end; ++o) {
-        first[o] = (int)days.size();
-        while (p < obs.size() && obs[p].owner == o) { days.push_back(obs[p].day); vals.push_back(obs[p].val); ++p; }
-        days.push_back(0x7fffffff);                      // sentinel
-        vals.push_back(0.0);
+        first[o] = (int)slot_day.size();
+        while (p < obs.size() && obs[p].owner == o) {
+            if (slot_day.size() == (size_t)first[o] || slot_day.back() != obs[p].day) slot_day.push_back(obs[p].day);
+            o_slot[p] = (int)slot_day.size() - 1;
+            o_day[p] = obs[p].day;
+            o_cell[p] = obs[p].cell;
+            o_val[p] = obs[p].val;
+            ++p;
+        }
+        slot_day.push_back(0x7fffffff);                  // sentinel
     }
-    // device copies (stream-ordered allocations: freed behind the kernel)
-    int *d_first = nullptr, *d_day = nullptr;
-    double *d_val = nullptr, *d_part = nullptr;
-    long long *d_cnt = nullptr;
-    CU(cudaMallocAsync(&d_first, first.size() * sizeof(int), st));
-    CU(cudaMallocAsync(&d_day, days.size() * sizeof(int), st));
-    CU(cudaMallocAsync(&d_val, vals.size() * sizeof(double), st));
-    CU(cudaMallocAsync(&d_part, (size_t)M * cl * sizeof(double), st));
-    CU(cudaMallocAsync(&d_cnt, (size_t)M * cl * sizeof(long long), st));
-    CU(cudaMemcpyAsync(d_first, first.data(), first.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d_day, days.data(), days.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d_val, vals.data(), vals.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(d_part, 0, (size_t)M * cl * sizeof(double), st));
-    CU(cudaMemsetAsync(d_cnt, 0, (size_t)M * cl * sizeof(long long), st));
+    auto &ob = ctx->obs;
+    CU(cudaDeviceSynchronize());                         // nothing in flight still reads the previous set
+    cudaFree(ob.first); cudaFree(ob.day); cudaFree(ob.val); cudaFree(ob.samples); cudaFree(ob.o_slot); cudaFree(ob.o_day); cudaFree(ob.o_cell);
+    ob = {};
+    const int M = c.n_members;
+    ob.stride = (long long)((slot_day.size() + 1) / 2 * 2);
+    ob.n_used = (long long)obs.size();
+    CU(cudaMalloc(&ob.first, first.size() * sizeof(int)));
+    CU(cudaMalloc(&ob.day, slot_day.size() * sizeof(int)));
+    CU(cudaMalloc(&ob.samples, (size_t)M * ob.stride * sizeof(double)));
+    CU(cudaMalloc(&ob.val, std::max<size_t>(1, obs.size()) * sizeof(double)));
+    CU(cudaMalloc(&ob.o_slot, std::max<size_t>(1, obs.size()) * sizeof(int)));
+    CU(cudaMalloc(&ob.o_day, std::max<size_t>(1, obs.size()) * sizeof(int)));
+    CU(cudaMalloc(&ob.o_cell, std::max<size_t>(1, obs.size()) * sizeof(int)));
+    CU(cudaMemcpy(ob.first, first.data(), first.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ob.day, slot_day.data(), slot_day.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemset(ob.samples, 0, (size_t)M * ob.stride * sizeof(double)));
+    if (!obs.empty()) {
+        CU(cudaMemcpy(ob.val, o_val.data(), obs.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(ob.o_slot, o_slot.data(), obs.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(ob.o_day, o_day.data(), obs.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(ob.o_cell, o_cell.data(), obs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    ob.ready = true;
+    return NESOSIM_OK;
+}
+
+int nesosim_run_season_misfit(nesosim_ctx *ctx, const nesosim_member_params *params_host, const double *ic_dev,
+                              int ic_per_member, double *misfit_dev, int64_t *count_dev, void *stream) {
+    if (!ctx || !params_host || !misfit_dev) return fail(NESOSIM_ERR_ARG, "bad argument");
+    if (!ctx->P) return fail(NESOSIM_ERR_STATE, "nesosim_set_forcing has not been called");
+    if (!ctx->obs.ready) return fail(NESOSIM_ERR_STATE, "nesosim_set_observations has not been called");
+    if (ctx->member_set_dev) return fail(NESOSIM_ERR_ARG, "misfit mode runs on one shared forcing");
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const nesosim_config &c = ctx->cfg;
+    const int T = c.num_days, M = c.n_members;
+    nesosim_outputs none{};
+    none.depth_member_stride = (int64_t)T * 2 * ctx->plane;
+    none.plane_member_stride = (int64_t)T * ctx->plane;
+    const char *why = "";
+    if (!ensemble_eligible(ctx, 0, T - 1, &none, &why))
+        return fail(NESOSIM_ERR_ARG, std::string("misfit mode needs the season-resident kernel: ") + why);
+    int rc = upload_coef(ctx, params_host, st);
+    if (rc) return rc;
     ObsDevice od;
-    od.first = d_first; od.day = d_day; od.val = d_val; od.misfit_part = d_part; od.count_part = d_cnt;
+    od.first = ctx->obs.first; od.day = ctx->obs.day; od.sample_depth = ctx->obs.samples; od.sample_stride = ctx->obs.stride;
     ctx->last_path = 2;
     rc = run_ensemble(ctx, ic_dev, ic_per_member, &none, 0, M, st, &od);     // synchronises the stream (operand-range flag)
-    if (!rc) {
-        misfit_finish_kernel<<<(M + 127) / 128, 128, 0, st>>>(d_part, d_cnt, cl, M, misfit_dev, (long long *)count_dev);
-        ctx->launches++;
-        if (cudaGetLastError() != cudaSuccess) rc = fail(NESOSIM_ERR_CUDA, "misfit_finish_kernel launch");
-    }
-    cudaFreeAsync(d_first, st); cudaFreeAsync(d_day, st); cudaFreeAsync(d_val, st); cudaFreeAsync(d_part, st); cudaFreeAsync(d_cnt, st);
     if (rc) return rc;
+    MisfitArgs ma;
+    ma.sample_depth = ctx->obs.samples; ma.stride = ctx->obs.stride;
+    ma.obs_slot = ctx->obs.o_slot; ma.obs_day = ctx->obs.o_day; ma.obs_cell = ctx->obs.o_cell; ma.obs_val = ctx->obs.val;
+    ma.conc = ctx->C; ma.plane = ctx->plane; ma.n_obs = ctx->obs.n_used;
+    ma.misfit = misfit_dev; ma.count = (long long *)count_dev;
+    misfit_finish_kernel<<<M, 256, 0, st>>>(ma);
+    ctx->launches++;
+    CU(cudaGetLastError());
     if (ctx->ens_status) return fail(NESOSIM_ERR_ARG, "an operand left the range of the season-resident kernel's fast divisions; misfit mode has no general-path fallback");
     return NESOSIM_OK;
 }

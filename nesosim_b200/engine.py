@@ -231,27 +231,32 @@ class SnowBudgetEngine:
         _lib.check(self.lib.nesosim_strip_status(self.handle, C.byref(v)))
         return bool(v.value)
 
-    def run_season_misfit(self, params, ic, obs):
-        """The season with the calibration misfit reduced INSIDE the season-resident kernel (nesosim_run_season_misfit):
-        ``obs`` = (day, row, col, depth) arrays; returns CUDA tensors (misfit[M] float64, used[M] int64).  No output
-        array is written."""
-        torch = _torch()
-        p = _lib.member_params_array(params)
-        assert len(p) == self.M
-        ic_t = None if ic is None else self._dev(ic)
-        per_member = 1 if (ic_t is not None and ic_t.dim() == 3 and self.M > 1) else 0
+    def set_observations(self, obs):
+        """Register point observations ``(day, row, col, depth)`` for ``run_season_misfit`` (copied to the device once)."""
         day, row, col = (np.ascontiguousarray(np.asarray(a), dtype=np.int32) for a in obs[:3])
         depth = np.ascontiguousarray(np.asarray(obs[3]), dtype=np.float64)
         n = len(day)
         assert len(row) == n and len(col) == n and len(depth) == n
+        i32 = C.POINTER(C.c_int32)
+        _lib.check(self.lib.nesosim_set_observations(self.handle, n, day.ctypes.data_as(i32), row.ctypes.data_as(i32),
+                                                     col.ctypes.data_as(i32), depth.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def run_season_misfit(self, params, ic, obs=None):
+        """The season with the calibration misfit reduced INSIDE the season-resident kernel (nesosim_run_season_misfit)
+        against the registered observations (``obs`` given: registered first); returns CUDA tensors (misfit[M] float64,
+        used[M] int64).  No output array is written."""
+        torch = _torch()
+        if obs is not None:
+            self.set_observations(obs)
+        p = _lib.member_params_array(params)
+        assert len(p) == self.M
+        ic_t = None if ic is None else self._dev(ic)
+        per_member = 1 if (ic_t is not None and ic_t.dim() == 3 and self.M > 1) else 0
         dev = "cuda:%d" % self.device
         mis = torch.empty(self.M, dtype=torch.float64, device=dev)
         used = torch.empty(self.M, dtype=torch.int64, device=dev)
-        i32 = C.POINTER(C.c_int32)
-        _lib.check(self.lib.nesosim_run_season_misfit(self.handle, p, None if ic_t is None else ic_t.data_ptr(), per_member, n,
-                                                      day.ctypes.data_as(i32), row.ctypes.data_as(i32), col.ctypes.data_as(i32),
-                                                      depth.ctypes.data_as(C.POINTER(C.c_double)), mis.data_ptr(),
-                                                      used.data_ptr(), self._stream()))
+        _lib.check(self.lib.nesosim_run_season_misfit(self.handle, p, None if ic_t is None else ic_t.data_ptr(), per_member,
+                                                      mis.data_ptr(), used.data_ptr(), self._stream()))
         self._keep = (ic_t, mis, used)
         return mis, used
 

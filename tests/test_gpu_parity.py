@@ -703,8 +703,9 @@ def test_ensemble_driver_reduces_on_the_device(cuda):
 
 @pytest.mark.parametrize("cluster", [None, "8"])
 def test_misfit_fused_into_the_season_kernel(cuda, cluster, monkeypatch):
-    """N3 fused: the observation operator (snow depth over ice at a day, row, col) and the per-member sum of squares run
-    INSIDE the season-resident kernel, which stores no output array at all.  Observations on land, on day 0, on the last
+    """N3 fused: the season-resident kernel stores no output array at all; the thread that owns an observed cell writes
+    the total depth of the observed days (8 bytes per observed cell-day), a one-CTA-per-member epilogue applies the
+    observation operator (snow depth over ice at a day, row, col) and sums the squares.  Observations on land, on day 0, on the last
     day, repeated at one cell and day, in every strip; result equal to the oracle's to 1e-12 (the sums are formed in a
     different order), counts exact, and bit-identical from run to run."""
     from nesosim_b200.engine import SnowBudgetEngine
@@ -729,7 +730,7 @@ def test_misfit_fused_into_the_season_kernel(cuda, cluster, monkeypatch):
     l0 = eng.launch_count()
     mis, used = eng.run_season_misfit(params, ic, obs)
     mis, used = mis.cpu().numpy(), used.cpu().numpy()
-    assert eng.launch_count() - l0 == 4          # pre-pass (2), season kernel, the M-scalar finish: nothing else
+    assert eng.launch_count() - l0 == 4          # pre-pass (2), season kernel, the per-member epilogue: nothing else
     again = eng.run_season_misfit(params, ic, obs)[0].cpu().numpy()
     assert np.array_equal(mis, again)
     eng.close()

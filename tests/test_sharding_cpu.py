@@ -73,3 +73,16 @@ def test_two_gloo_ranks_reproduce_the_single_process_ensemble():
     params = S.ensemble_params(M, seed=3)
     exp = np.array([_member_metric(forcing, ic, mask, row) for row in params])
     assert np.array_equal(got, exp)
+
+
+def test_multiseason_batch_of_the_bench_matches_baseline_step_count():
+    """BASELINE.json configs[3]: 41 seasons, Sep 1 - Apr 30, 9891 steps in all; dealt round-robin."""
+    import bench
+    assert len(bench.MULTI_YEARS) == 41 and bench.MULTI_YEARS[0] == 1980 and bench.MULTI_YEARS[-1] == 2020
+    days = [bench.season_days(y) for y in bench.MULTI_YEARS]
+    assert set(days) == {242, 243} and sum(d - 1 for d in days) == 9891
+    assert bench.season_days(1983) == 243 and bench.season_days(1999) == 243 and bench.season_days(2018) == 242
+    for world in (1, 2, 4, 8):
+        parts = [sharding.season_assignment(bench.MULTI_YEARS, r, world) for r in range(world)]
+        assert sorted(y for p in parts for y in p) == bench.MULTI_YEARS
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
