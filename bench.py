@@ -121,6 +121,21 @@ def cpu_baseline(members_per_core=1, cores=None, num_days=NUM_DAYS, target_secon
         pool.close()
 
 
+def verbatim_note():
+    """The reference's own loop executed verbatim can only be timed where /root/reference exists (the build container):
+    profiles/r02_reference_verbatim.json (tools/time_reference_verbatim.py) holds that figure next to the port's on the
+    same core, with identical outputs -- the port this bench times is the faster of the two, i.e. a conservative baseline."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_reference_verbatim.json")) as f:
+            d = json.load(f)
+        return {"reference_verbatim_cell_days_per_s_per_core": d["reference_verbatim"]["cell_days_per_s_per_core"],
+                "numpy_port_cell_days_per_s_per_core_same_core": d["numpy_port"]["cell_days_per_s_per_core"],
+                "port_over_verbatim": d["port_over_verbatim"], "identical_outputs": d["identical_outputs"],
+                "where": d["where"], "source": "profiles/r02_reference_verbatim.json"}
+    except Exception:
+        return None
+
+
 def run_reference(args):
     """The reference's CPU path (the numpy port of its calcBudget loop: the reference itself is pure Python whose
     dependencies are absent) on all host cores.  One step = one bounded sample of the workload, sized so that
@@ -149,7 +164,8 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(MEMBERS_PER_GPU, args.gpus),
             "reference_step": "bounded sample: " + sample,
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "verbatim_reference": verbatim_note()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -426,7 +442,8 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, cores, sample, _ = cpu_baseline(1)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+               "verbatim_reference": verbatim_note()}
 
     other = None
     if rank == 0 and world == 1 and not args.no_e2e and not args.no_other:

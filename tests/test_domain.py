@@ -240,3 +240,55 @@ def test_peer_strips_across_processes_over_cuda_ipc(cuda):
     for rank, lo, hi, part in parts:
         for k in NAMES:
             assert np.array_equal(part[k], ref[k][..., lo:hi, :], equal_nan=True), (k, rank)
+
+
+def _peer_rank_with_a_silent_neighbour(rank, world, port, q, n_dev):
+    """Rank 0 runs its season; rank 1 attaches its mailboxes but never launches: rank 0's boundary CTAs give up after the
+    time-out, and the check that ends the season must fail on BOTH ranks."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dev = rank % n_dev
+    torch.cuda.set_device(dev)
+    mask = S.region_mask(shape=(120, 80), kind="disc")
+    T = 4
+    forcing = S.make_season(mask, T, seed=9)
+    ic = S.make_ic(mask, seed=9)
+    eng, lo, hi, elo, ehi = domain.make_strip_engine(mask, T, 25000, forcing, rank, world, device=dev, timeout_s=0.3, atmlossInc=1)
+    handles = [None] * world
+    dist.all_gather_object(handles, eng.strip_export())
+    eng.strip_connect(handles[rank - 1] if rank > 0 else None, handles[rank + 1] if rank < world - 1 else None)
+    dist.barrier()
+    if rank == 0:
+        eng.run_season([list(PARAMS)], np.ascontiguousarray(ic[elo:ehi]))
+        torch.cuda.synchronize(dev)
+    failed = False
+    try:
+        domain.check_strips(eng, rank, world)
+    except RuntimeError as e:
+        failed = "did not receive" in str(e)
+    q.put((rank, failed, bool(eng.strip_timed_out())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_a_strip_time_out_fails_the_season_on_every_rank(cuda):
+    """A neighbour that never delivers: the waiting strip's kernels give up after the time-out (no hung GPU), its own
+    status says so, and ``domain.check_strips`` raises on every rank -- the results of such a season are invalid."""
+    if cuda.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (one process per strip)")
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_rank_with_a_silent_neighbour, args=(r, world, port, q, cuda.cuda.device_count())) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0] == (0, True, True)          # rank 0 timed out itself ...
+    assert got[1] == (1, True, False)         # ... and rank 1, which did not, fails with it
