@@ -81,10 +81,12 @@ extern "C" int nesosim_run_season_host(nesosim_ctx *ctx, const double *precip, c
     if ((rc = upload_coef(ctx, params, hp->compute))) return rc;
     up += (int64_t)sizeof(MemberCoef) * M;
 
-    // batch size: two device buffers of <= NESOSIM_HOST_BATCH_GB (default 8 GiB) each
+    // batch size: two device buffers of <= NESOSIM_HOST_BATCH_GB (default 16 GiB) each.  Measured on a B200 box
+    // (tools/e2e_variants.py, 128 members x 260 days, 21.6 GB to the host): 2 GiB 452 ms, 8 GiB 462 ms, 16 GiB 427 ms --
+    // fewer, longer copies keep the link busier (53.9 GB/s is what a plain pinned copy reaches there).
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    double cap_gb = 8.0;
+    double cap_gb = 16.0;
     if (const char *e = getenv("NESOSIM_HOST_BATCH_GB")) cap_gb = atof(e);
     size_t cap = (size_t)(cap_gb * (1ull << 30));
     if (!hp->outbuf[0] && cap * 2 > free_b / 10 * 8) cap = free_b / 10 * 4;
@@ -167,10 +169,11 @@ extern "C" int nesosim_run_season_host(nesosim_ctx *ctx, const double *precip, c
     if (share && (harr[2] || harr[3])) {
         CU(cudaEventSynchronize(hp->shared_ready));
         const long long n = var_elems_per_member(ctx, 2), hstride = out_host->plane_member_stride;
-        // replication threads: at most 8, and no more than this process' share of the host cores when every visible GPU
-        // runs a rank of its own (one process per GPU: 8 ranks x 8 threads oversubscribed the memory bus of the box);
-        // NESOSIM_HOST_THREADS overrides
-        int nthreads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / (unsigned)std::max(1, nesosim_device_count())));
+        // replication threads: this process' share of the host cores when every visible GPU runs a rank of its own (one
+        // process per GPU), at most 16.  The copy into the other members' slots is on the critical path of the call
+        // when it is too slow (same box: 2 threads 604 ms, 4 495 ms, 8 462 ms, 16 458 ms; without sharing 480 ms), and
+        // 8 ranks x 8 threads oversubscribed the memory bus of a box.  NESOSIM_HOST_THREADS overrides
+        int nthreads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency() / (unsigned)std::max(1, nesosim_device_count())));
         if (const char *e = getenv("NESOSIM_HOST_THREADS")) nthreads = std::max(1, atoi(e));
         std::vector<std::thread> pool;
         for (int t = 0; t < nthreads; ++t)
