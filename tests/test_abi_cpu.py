@@ -79,6 +79,11 @@ def test_argument_validation_and_no_cpu_fallback(lib):
     assert lib.nesosim_strip_block(None, None, None) == _lib.ERR_STATE
     assert lib.nesosim_strip_connect(None, None, None) == _lib.ERR_STATE
     assert lib.nesosim_strip_connect_local(None, None, None) == _lib.ERR_STATE
+    # asynchronous and calibration modes
+    assert lib.nesosim_set_async(None, 1) == _lib.ERR_ARG
+    assert lib.nesosim_sync(None, None) == _lib.ERR_ARG
+    assert lib.nesosim_set_observations(None, 0, None, None, None, None) == _lib.ERR_ARG
+    assert lib.nesosim_run_season_misfit(None, None, None, 0, None, None, None) == _lib.ERR_ARG
 
 
 def test_missing_library_is_an_import_error(monkeypatch):
