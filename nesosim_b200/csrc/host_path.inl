@@ -31,6 +31,18 @@ extern "C" int nesosim_run_season_host(nesosim_ctx *ctx, const double *precip, c
     if (!ctx || !precip || !conc || !wind || !drift || !params || !out_host) return fail(NESOSIM_ERR_ARG, "NULL argument");
     if (ctx->cfg.density_clim && !rho_clim) return fail(NESOSIM_ERR_ARG, "density_clim=1 needs rho_clim");
     CU(cudaSetDevice(ctx->cfg.device));
+    // this call copies every batch's results to the host itself, so the season kernel's operand-range flag must be
+    // looked at before the copy: asynchronous mode (nesosim_set_async) is suspended for its duration
+    struct AsyncOff {
+        nesosim_ctx *c;
+        bool was;
+        explicit AsyncOff(nesosim_ctx *c_) : c(c_), was(c_->async_mode) { c->async_mode = false; }
+        ~AsyncOff() { c->async_mode = was; }
+    } async_off(ctx);
+    if (async_off.was) {
+        int rc0 = resolve_pending(ctx, true, nullptr);
+        if (rc0) return rc0;
+    }
     const int M = ctx->cfg.n_members;
     const long long T = ctx->cfg.num_days, plane = ctx->plane;
     HostPath *hp = &ctx->hp;

@@ -606,6 +606,15 @@ def test_asynchronous_mode_back_to_back_seasons(cuda):
             ref = O.run_season(forcing, ic, mask, 100000, oracle_params(p[m]), O.Flags(atmlossInc=1))
             for name in out:
                 assert_parity(out[name][m].cpu().numpy(), ref[name], name)
+    # the host-buffer call suspends asynchronous mode for its duration (it copies the results out itself)
+    host, _, _ = eng.run_season_host(forcing, sets[0], ic, names=("snowDepths", "density"))
+    ref = O.run_season(forcing, ic, mask, 100000, oracle_params(sets[0][1]), O.Flags(atmlossInc=1))
+    for name in host:
+        assert_parity(host[name][1], ref[name], name + " (host call in asynchronous mode)")
+    more = eng.run_season(sets[1], ic_dev, eng.alloc_outputs())          # ... and the mode is still on afterwards
+    assert eng.sync() == 0
+    assert_parity(more["density"][0].cpu().numpy(), O.run_season(forcing, ic, mask, 100000, oracle_params(sets[1][0]),
+                                                                 O.Flags(atmlossInc=1))["density"], "density")
     eng.set_async(False)
     eng.close()
 
