@@ -39,6 +39,16 @@ UNIT = "cell-days/s"
 SEED = 2024
 
 
+_T0 = time.perf_counter()
+
+
+def stamp(label):
+    """Progress line on stderr (rank 0): where the wall time of a bench run goes."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        sys.stderr.write("[bench %7.1f s] %s\n" % (time.perf_counter() - _T0, label))
+        sys.stderr.flush()
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -270,6 +280,7 @@ def run_ours(args):
     from nesosim_b200 import synthetic as S
     from nesosim_b200.engine import SnowBudgetEngine
 
+    stamp("library ready")
     M = args.members
     T = args.days
     mask = S.region_mask(dx=DX)
@@ -356,6 +367,7 @@ def run_ours(args):
         except Exception:
             pass
 
+    stamp("headline timed (%d steps)" % args.steps)
     # end to end through the host-buffer C-ABI call
     e2e = None
     try:
@@ -367,6 +379,7 @@ def run_ours(args):
 
     # the same season when only the final NetCDF product's six float32 fields go back to the host (labelled apart:
     # it is NOT the full 12-array contract the headline e2e figure keeps)
+    stamp("e2e (host buffers) done")
     e2e_final = None
     try:
         if args.no_e2e:
@@ -385,6 +398,7 @@ def run_ours(args):
         except Exception as ex:
             e2e["link_error"] = str(ex)[:200]
 
+    stamp("e2e (final products) and link ceiling done")
     kernel_path = eng.last_path()
     failures = []
     if redone:
@@ -402,6 +416,7 @@ def run_ours(args):
     eng.close()
     torch.cuda.empty_cache()
 
+    stamp("calibration mode done")
     # BASELINE configs[3]: the 1980-2021 multi-season batch, seasons dealt over the ranks
     multi = None
     if not args.no_extra:
@@ -412,6 +427,7 @@ def run_ours(args):
         except Exception as ex:
             multi = {"error": str(ex)[:300]}      # (a leg that could not run is reported, not fatal; a wrong result is)
 
+    stamp("multi-season batch done")
     # BASELINE configs[4]: the 5 km grid as row strips over the ranks, ghost rows exchanged inside the day kernel
     dom = None
     if world > 1 and not args.no_extra:
@@ -428,6 +444,7 @@ def run_ours(args):
         dist.all_gather_object(flags, failures)
         failures = sorted({f for fl in flags for f in fl})
 
+    stamp("5 km strips done" if world > 1 else "(5 km strips: N > 1 only)")
     # BASELINE configs[0]: the drop-in main() over a season of forcing files, next to the CPU loop over the same files
     dropin = None
     if rank == 0 and world == 1 and not args.no_cpu and not args.no_extra:
@@ -438,12 +455,14 @@ def run_ours(args):
         except Exception as ex:
             dropin = {"error": str(ex)[:300]}
 
+    stamp("drop-in main done")
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, cores, sample, _ = cpu_baseline(1)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                "verbatim_reference": verbatim_note()}
 
+    stamp("cpu baseline done")
     other = None
     if rank == 0 and world == 1 and not args.no_e2e and not args.no_other:
         try:
@@ -451,6 +470,7 @@ def run_ours(args):
         except Exception as ex:
             other = {"error": str(ex)[:200]}
 
+    stamp("other grids done")
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True,
