@@ -103,6 +103,49 @@ def test_two_gloo_ranks_exchange_ghost_rows():
             assert np.array_equal(part[k], ref[k][..., lo:hi, :], equal_nan=True), (k, rank)
 
 
+class _FakeStrip:
+    def __init__(self, timed_out):
+        self._t = timed_out
+
+    def strip_timed_out(self):
+        return self._t
+
+
+def _check_rank(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out = []
+    for flags in ((False, False), (False, True)):
+        try:
+            domain.check_strips(_FakeStrip(flags[rank]), rank, world)
+            out.append("ok")
+        except RuntimeError as e:
+            out.append(str(e))
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_a_strip_time_out_is_raised_on_every_rank():
+    """domain.check_strips: the ranks exchange their time-out marks; one mark fails the season everywhere."""
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_check_rank, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank in range(world):
+        assert got[rank][0] == "ok"
+        assert "strip(s) [1] did not receive" in got[rank][1]
+
+
 @pytest.mark.gpu
 def test_gpu_strips_reproduce_the_single_domain_run(cuda):
     mask = S.region_mask(dx=100000)

@@ -758,6 +758,36 @@ def test_misfit_fused_into_the_season_kernel(cuda, cluster, monkeypatch):
     assert np.allclose(a[0], b[0], rtol=1e-12, atol=0.0) and np.array_equal(a[1], b[1])
 
 
+def test_misfit_with_per_member_initial_conditions_and_replaced_observations(cuda):
+    """Per-member ICs; no observation at all (zero misfit, zero count); a second set of observations replaces the
+    first on the same context."""
+    from nesosim_b200.engine import SnowBudgetEngine
+    mask = S.region_mask(dx=100000)
+    T, M = 12, 5
+    forcing = S.make_season(mask, T, seed=65)
+    rng = np.random.default_rng(65)
+    ic = S.make_ic(mask, seed=65)[None] * rng.uniform(0.5, 3.0, (M, 1, 1))
+    params = S.ensemble_params(M, seed=65)
+    eng = SnowBudgetEngine(mask, T, 100000, n_members=M, atmlossInc=1)
+    eng.set_forcing(forcing["precip"], forcing["conc"], forcing["wind"], forcing["drift"])
+    mis, used = eng.run_season_misfit(params, ic, ([], [], [], []))
+    assert not mis.cpu().numpy().any() and not used.cpu().numpy().any()
+    refs = [O.run_season(forcing, ic[m], mask, 100000, oracle_params(params[m]), O.Flags(atmlossInc=1)) for m in range(M)]
+    for n in (40, 700):
+        day, row, col = rng.integers(0, T, n), rng.integers(0, 90, n), rng.integers(0, 90, n)
+        depth = 0.3 * rng.random(n)
+        mis, used = eng.run_season_misfit(params, ic, (day, row, col, depth))
+        mis, used = mis.cpu().numpy(), used.cpu().numpy()
+        for m in range(M):
+            with np.errstate(all="ignore"):
+                model = (refs[m]["snowDepths"][day, 0, row, col] + refs[m]["snowDepths"][day, 1, row, col]) / forcing["conc"][day, row, col]
+            d = model - depth
+            ok = np.isfinite(d)
+            assert used[m] == ok.sum()
+            assert np.isclose(mis[m], np.sum(d[ok] ** 2), rtol=1e-12, atol=0.0)
+    eng.close()
+
+
 def test_misfit_mode_refuses_grids_the_season_kernel_does_not_take(cuda):
     from nesosim_b200 import _lib
     from nesosim_b200.engine import SnowBudgetEngine
