@@ -770,7 +770,7 @@ def run_domain_5km(rank, world, local, peak, steps=40, gen_days=4, reps=3):
 
     # ---- the strips
     lo, hi, part, eng = domain.run_decomposed_season_peer(mask, T, dx, gen, params, ic, rank, world, device=local,
-                                                          day_index=idx, atmlossInc=1, timeout_s=20.0)
+                                                          day_index=idx, atmlossInc=1, timeout_s=20.0, balance=True)
     outs = eng._keep[1]
     lo_, hi_, elo, ehi = eng._strip_rows
     ic_dev = eng._dev(np.ascontiguousarray(ic[elo:ehi]))
@@ -833,6 +833,7 @@ def run_domain_5km(rank, world, local, peak, steps=40, gen_days=4, reps=3):
             "speedup_vs_one_gpu": one_ms / best, "identical_to_one_gpu": bool(ok),
             "compared": "all 11 arrays, every owned row, every time slot (NaN patterns and values) on the device",
             "strip_status": "no time-out on any rank", "launches_per_day": 1, "nvlink": nvlink,
+            "strip_rows": [b[1] - b[0] for b in bounds], "strip_cut": "rows cut for equal modelled cost (domain.balanced_cuts)",
             "data": "synthetic (%d generated days repeated)" % gen_days}
 
 

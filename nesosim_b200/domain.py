@@ -35,6 +35,37 @@ def strip_rows(ny, rank, world):
     return lo, hi, max(lo - GHOST, 0), min(hi + GHOST, ny)
 
 
+def balanced_cuts(mask, world, ocean_weight=2.3):
+    """Row boundaries ``[0, c1, ..., ny]`` of ``world`` strips with (nearly) equal modelled cost instead of equal height:
+    a day costs roughly ``ocean_weight`` on an ocean cell for 1 on a land cell (all-land tiles take the closed-form
+    shortcut), and the ocean is not spread evenly over the rows of the polar grid -- at eight strips of the 5 km grid
+    the heaviest equal-height strip carries 11 % more than the mean, and the slowest strip sets the pace of all.
+    Deterministic in the mask, so every rank computes the same cuts; every strip keeps at least 2*GHOST rows."""
+    mask = np.asarray(mask)
+    ny = mask.shape[0]
+    land = (mask > 10) | (mask < 1)
+    row_cost = mask.shape[1] + (ocean_weight - 1.0) * (~land).sum(axis=1)
+    cum = np.concatenate([[0.0], np.cumsum(row_cost)])
+    cuts = [0]
+    for r in range(1, world):
+        c = int(np.searchsorted(cum, cum[-1] * r / world))
+        c = max(c, cuts[-1] + 2 * GHOST)
+        c = min(c, ny - 2 * GHOST * (world - r))
+        cuts.append(c)
+    cuts.append(ny)
+    if any(b - a < GHOST for a, b in zip(cuts[:-1], cuts[1:])):
+        raise ValueError("strips must own at least %d rows (ny=%d over %d ranks)" % (GHOST, ny, world))
+    return cuts
+
+
+def strip_rows_balanced(mask, rank, world):
+    """Like ``strip_rows`` but with the cost-balanced cuts of ``balanced_cuts``."""
+    cuts = balanced_cuts(mask, world)
+    ny = np.asarray(mask).shape[0]
+    lo, hi = cuts[rank], cuts[rank + 1]
+    return lo, hi, max(lo - GHOST, 0), min(hi + GHOST, ny)
+
+
 class GpuStripStepper:
     """One strip on one GPU through the C ABI (``nesosim_run_season`` one day at a time, general kernels)."""
 
@@ -155,14 +186,15 @@ def run_decomposed_season_one_process(mask, num_days, dx, forcing, params_row, i
 
 # ------------------------------------------------------------------------------ fused peer-memory exchange
 
-def make_strip_engine(mask, num_days, dx, forcing, rank, world, device=0, timeout_s=None, day_index=None, **flags):
+def make_strip_engine(mask, num_days, dx, forcing, rank, world, device=0, timeout_s=None, day_index=None, balance=False,
+                      **flags):
     """Engine on this rank's extended strip with its forcing staged and ``nesosim_strip_setup`` done.
     Returns (engine, lo, hi, elo, ehi).  ``day_index`` (length ``num_days``): the forcing arrays hold a few generated
     days and day x of the season is ``forcing[...][day_index[x]]`` -- the repetition happens on the device after the
     rows have been sliced, so a benchmark never materialises the whole season of the whole grid on the host."""
     from .engine import SnowBudgetEngine
     ny = mask.shape[0]
-    lo, hi, elo, ehi = strip_rows(ny, rank, world)
+    lo, hi, elo, ehi = strip_rows_balanced(mask, rank, world) if balance else strip_rows(ny, rank, world)
     if hi - lo < GHOST:
         raise ValueError("strips must own at least %d rows (ny=%d over %d ranks)" % (GHOST, ny, world))
     eng = SnowBudgetEngine(np.ascontiguousarray(mask[elo:ehi]), num_days, dx, n_members=1, device=device, **flags)
@@ -190,7 +222,7 @@ def check_strips(eng, rank, world, group=None):
 
 
 def run_decomposed_season_peer(mask, num_days, dx, forcing, params_row, ic, rank, world, device=0, group=None,
-                               outputs=None, engine=None, timeout_s=None, day_index=None, **flags):
+                               outputs=None, engine=None, timeout_s=None, day_index=None, balance=False, **flags):
     """This rank's strip of one season with the ghost-row exchange fused into the day kernel (peer memory).
     ``torch.distributed`` must be initialised (any backend: it moves 64-byte handles and barriers only).
     Returns (lo, hi, {array: device tensor of the OWNED rows}, engine); pass ``engine`` back in to run further seasons
@@ -199,7 +231,7 @@ def run_decomposed_season_peer(mask, num_days, dx, forcing, params_row, ic, rank
     import torch.distributed as dist
     if engine is None:
         eng, lo, hi, elo, ehi = make_strip_engine(mask, num_days, dx, forcing, rank, world, device=device,
-                                                  timeout_s=timeout_s, day_index=day_index, **flags)
+                                                  timeout_s=timeout_s, day_index=day_index, balance=balance, **flags)
         handles = [None] * world
         dist.all_gather_object(handles, eng.strip_export(), group=group)
         eng.strip_connect(handles[rank - 1] if rank > 0 else None, handles[rank + 1] if rank < world - 1 else None)
@@ -218,7 +250,7 @@ def run_decomposed_season_peer(mask, num_days, dx, forcing, params_row, ic, rank
 
 
 def run_decomposed_season_peer_one_process(mask, num_days, dx, forcing, params_row, ic, n_strips, device=0,
-                                           whole_season_per_strip=False, **flags):
+                                           whole_season_per_strip=False, balance=False, **flags):
     """All strips as separate contexts on ONE GPU, wired through device pointers instead of IPC handles: the same day
     kernel, mailboxes and flags as the multi-GPU run.  Default: the strips take turns day by day on one stream (no wait
     ever spins).  ``whole_season_per_strip``: each strip's whole season is enqueued on its own stream, so the strips
@@ -227,7 +259,7 @@ def run_decomposed_season_peer_one_process(mask, num_days, dx, forcing, params_r
     ny = mask.shape[0]
     strips = []
     for r in range(n_strips):
-        eng, lo, hi, elo, ehi = make_strip_engine(mask, num_days, dx, forcing, r, n_strips, device=device, **flags)
+        eng, lo, hi, elo, ehi = make_strip_engine(mask, num_days, dx, forcing, r, n_strips, device=device, balance=balance, **flags)
         strips.append([eng, lo, hi, elo, ehi, eng.alloc_outputs(), None if ic is None else np.ascontiguousarray(ic[elo:ehi])])
     blocks = [s[0].strip_block() for s in strips]
     for r, s in enumerate(strips):

@@ -65,6 +65,30 @@ def test_strip_rows_cover_the_grid_with_two_ghost_rows():
         assert prev_hi == ny
 
 
+def test_cost_balanced_cuts_cover_the_grid():
+    """domain.balanced_cuts: contiguous strips over all rows, no strip thinner than its ghost rows, every strip's
+    modelled cost within a row's worth of the mean, and closer to it than equal-height strips are."""
+    from nesosim_b200 import sharding
+    mask = S.region_mask(dx=25000)
+    land = (mask > 10) | (mask < 1)
+    row_cost = mask.shape[1] + 1.3 * (~land).sum(axis=1)
+    for world in (2, 3, 8):
+        cuts = domain.balanced_cuts(mask, world)
+        assert cuts[0] == 0 and cuts[-1] == mask.shape[0] and len(cuts) == world + 1
+        assert all(b - a >= 2 * domain.GHOST for a, b in zip(cuts[:-1], cuts[1:]))
+        cost = np.array([row_cost[a:b].sum() for a, b in zip(cuts[:-1], cuts[1:])])
+        equal = np.array([row_cost[slice(*sharding.member_range(mask.shape[0], r, world))].sum() for r in range(world)])
+        assert cost.max() - cost.mean() <= row_cost.max() + 1e-9
+        assert cost.max() <= equal.max() + 1e-9
+        for r in range(world):
+            lo, hi, elo, ehi = domain.strip_rows_balanced(mask, r, world)
+            assert (lo, hi) == (cuts[r], cuts[r + 1]) and elo == max(lo - 2, 0) and ehi == min(hi + 2, mask.shape[0])
+    tiny = S.region_mask(shape=(13, 9), kind="disc")
+    assert domain.balanced_cuts(tiny, 3)[-1] == 13
+    with pytest.raises(ValueError):
+        domain.balanced_cuts(tiny, 8)
+
+
 @pytest.mark.parametrize("n_strips", [2, 3, 5])
 def test_strips_in_one_process_reproduce_the_single_domain_run(n_strips):
     mask, forcing, ic, ref = setup()
@@ -198,6 +222,21 @@ def test_peer_strips_match_the_single_domain_run(cuda, ny, nx, n_strips, concurr
                                                         whole_season_per_strip=concurrent, atmlossInc=1)
     for k in NAMES:
         assert np.array_equal(got[k], ref[k], equal_nan=True), k
+
+
+@pytest.mark.gpu
+def test_cost_balanced_peer_strips_match_the_single_domain_run(cuda):
+    """Strips of unequal height (rows cut for equal modelled cost) through the mailboxes, concurrent streams."""
+    mask = S.region_mask(dx=25000)
+    T = 7
+    forcing = S.make_season(mask, T, seed=29)
+    ic = S.make_ic(mask, seed=29)
+    ref = _gpu_reference(mask, T, 25000, forcing, ic, atmlossInc=1)
+    for n_strips in (3, 6):
+        got = domain.run_decomposed_season_peer_one_process(mask, T, 25000, forcing, PARAMS, ic, n_strips,
+                                                            whole_season_per_strip=True, balance=True, atmlossInc=1)
+        for k in NAMES:
+            assert np.array_equal(got[k], ref[k], equal_nan=True), (k, n_strips)
 
 
 @pytest.mark.gpu
