@@ -373,7 +373,7 @@ def run_ours(args):
     try:
         if args.no_e2e:
             raise RuntimeError("skipped (--no-e2e)")
-        e2e = run_e2e(args, eng, forcing, params, ic, rank, world, cells_per_step, barrier)
+        e2e = run_e2e(args, eng, forcing, params, ic, rank, world, cells_per_step, barrier, out)
     except Exception as ex:   # keep the headline line even if the host path cannot allocate
         e2e = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
 
@@ -401,6 +401,8 @@ def run_ours(args):
     stamp("e2e (final products) and link ceiling done")
     kernel_path = eng.last_path()
     failures = []
+    if isinstance(e2e, dict) and e2e.get("host_arrays_identical_to_device_result") is False:
+        failures.append("e2e: the host arrays differ from the device-resident season")
     if redone:
         failures.append("%d season(s) of the synthetic workload left the season kernel's operand range and were redone" % redone)
 
@@ -489,10 +491,16 @@ def run_ours(args):
         sys.exit(3)
 
 
-def run_e2e(args, eng, forcing, params, ic, rank, world, cells_per_step, barrier):
-    """Season through nesosim_run_season_host: pinned HOST forcing in, all 12 HOST arrays out, every step."""
+def run_e2e(args, eng, forcing, params, ic, rank, world, cells_per_step, barrier, dev_out=None):
+    """Season through nesosim_run_season_host: pinned HOST forcing in, all 12 HOST arrays out, every step.  The
+    library picks the drain: every byte of the arrays over the link, or -- when this rank has enough host threads --
+    ocean cells only with the land cells filled in on the host (same arrays in the caller's memory either way; checked
+    below against the device-resident result of the headline run)."""
     import torch
     M, T, ny, nx = eng.M, eng.T, eng.ny, eng.nx
+    # host threads of this rank: its share of the cores (the library's own default assumes a rank per visible GPU)
+    threads = max(1, min(32, (os.cpu_count() or 1) // world))
+    os.environ.setdefault("NESOSIM_HOST_THREADS", str(threads))
     names = list(__import__("nesosim_b200._lib", fromlist=["x"]).OUTPUT_NAMES)
     need = 12 * M * T * ny * nx * 8
     avail = None
@@ -526,8 +534,21 @@ def run_e2e(args, eng, forcing, params, ic, rank, world, cells_per_step, barrier
         import torch.distributed as dist
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
-    return {"value": world * cells_per_step * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(up),
-            "d2h_bytes_per_step": int(down), "steps": steps, "ms_per_step": 1e3 * dt / steps, "outputs": note}
+    compacted, full_chunks = eng.host_drain_info()
+    res = {"value": world * cells_per_step * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(up),
+           "d2h_bytes_per_step": int(down), "steps": steps, "ms_per_step": 1e3 * dt / steps, "outputs": note,
+           "host_array_bytes_per_step": int(sum(v.numel() * 8 for v in host_out.values())),
+           "drain": ("compacted: ocean cells of the ten member-dependent arrays + the land cells of the first three time slots "
+                     "cross the link, %s host threads scatter them into the caller's arrays" % os.environ["NESOSIM_HOST_THREADS"])
+           if compacted else "full: every byte of the arrays crosses the link",
+           "host_threads": int(os.environ["NESOSIM_HOST_THREADS"]), "chunks_copied_in_full": full_chunks}
+    if dev_out is not None:       # the caller's arrays against the device-resident season of the headline run
+        same = True
+        for n in host_out:
+            for m in sorted({0, M // 2, M - 1}):
+                same = same and bool(torch.equal(host_out[n][m].nan_to_num(nan=-7.0), dev_out[n][m].cpu().nan_to_num(nan=-7.0)))
+        res["host_arrays_identical_to_device_result"] = same
+    return res
 
 
 def run_e2e_final(args, eng, forcing, params, ic, dev_out, world, cells_per_step, barrier):

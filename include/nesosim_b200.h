@@ -235,6 +235,20 @@ double nesosim_const_div_eval_host(double x, double c);
 /* Seasons the season-resident path had to hand back to the general kernels (see nesosim_run_season). */
 int64_t nesosim_rerun_count(const nesosim_ctx *ctx);
 
+/* How the last nesosim_run_season_host drained its results: *compacted = 1 if only the ocean cells (and the land cells
+ * of the first three time slots) of the member-dependent arrays crossed the link and host threads scattered them into
+ * the caller's arrays; *full_chunks = chunks of members (since creation) for which that was given up because their land
+ * cells were not constant in time, and which were copied in full instead.  The caller's arrays are the same either way
+ * (the reference's genEmptyArrays contract, NESOSIM.py:350-376). */
+int nesosim_host_drain_info(const nesosim_ctx *ctx, int *compacted, int64_t *full_chunks);
+
+/* Host half of that drain, on its own: one member's packed block of one array -- [planes_per_slot*num_days][n_ocean]
+ * ocean values (cells with mask 1..10, ascending), then [planes_per_slot*min(3,num_days)][n_land] land values of the
+ * first slots -- scattered into the full planes dst[planes_per_slot*num_days][plane]; later slots repeat the land cells
+ * of the third.  No device involved. */
+int nesosim_unpack_member_array(const uint8_t *mask, int64_t plane, int planes_per_slot, int num_days,
+                                const double *packed, double *dst);
+
 /* Device time of the season-resident kernel's launches so far (CUDA events on the launching stream) and their
  * number: what bench.py divides the algorithmic bytes per launch by for its roofline figure. */
 int nesosim_season_kernel_time(const nesosim_ctx *ctx, double *total_ms, int64_t *launches);

@@ -8,7 +8,109 @@
 // coefficient, no depth -- so with one shared forcing every member's copy is the same array: only member 0's crosses
 // PCIe, and host threads replicate it into the other members' slots while the remaining arrays are still draining
 // (2 of the 12 arrays per member: 16 % fewer bytes on the link that bounds this call).
+//
+// Compacted drain (drain_kernels.cuh; NESOSIM_HOST_COMPACT=0/1 overrides the choice): of the ten member-dependent arrays
+// only the ocean cells (43 % of the polar grid) and the land cells of the first three time slots cross the link, in
+// chunks of a few members that land in a ring of pinned slots; a pool of host threads scatters every chunk into the
+// caller's arrays -- plane by plane through a cache-resident scratch plane and out with streaming stores -- while the
+// next chunks are on the link.  A chunk whose land cells turn out not to be constant is copied in full instead.
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 namespace {
+
+// dst <- src (n doubles) with non-temporal stores: the caller's arrays are written once and not read by this call, so
+// going around the cache saves the read-for-ownership of every line (half of the memory traffic of the scatter)
+void stream_plane(double *dst, const double *src, long long n) {
+#if defined(__SSE2__)
+    long long i = 0;
+    if (((uintptr_t)dst & 15) && n) { dst[0] = src[0]; i = 1; }
+    for (; i + 8 <= n; i += 8) {
+        _mm_stream_pd(dst + i, _mm_loadu_pd(src + i));
+        _mm_stream_pd(dst + i + 2, _mm_loadu_pd(src + i + 2));
+        _mm_stream_pd(dst + i + 4, _mm_loadu_pd(src + i + 4));
+        _mm_stream_pd(dst + i + 6, _mm_loadu_pd(src + i + 6));
+    }
+    for (; i + 2 <= n; i += 2) _mm_stream_pd(dst + i, _mm_loadu_pd(src + i));
+    if (i < n) dst[i] = src[i];
+#else
+    std::memcpy(dst, src, (size_t)n * 8);
+#endif
+}
+
+// One member's packed block of one array -> the caller's full planes.  oc: [pps*T][n_ocean]; the land cells of the
+// first `head` slots follow; a later slot repeats the land cells of slot head-1 (they stay in the scratch plane).
+void scatter_member_array(const std::vector<int> &ocean_idx, const std::vector<int> &land_idx, long long plane, int pps,
+                          int T, int head, const double *oc, double *dst, double *scratch) {
+    const long long n_ocean = (long long)ocean_idx.size(), n_land = (long long)land_idx.size();
+    const double *ld = oc + (long long)pps * T * n_ocean;
+    const int *oi = ocean_idx.data(), *li = land_idx.data();
+    for (int layer = 0; layer < pps; ++layer)
+        for (int slot = 0; slot < T; ++slot) {
+            const long long q = (long long)slot * pps + layer;
+            if (slot < head) {
+                const double *l = ld + q * n_land;
+                for (long long i = 0; i < n_land; ++i) scratch[li[i]] = l[i];
+            }
+            const double *o = oc + q * n_ocean;
+            for (long long i = 0; i < n_ocean; ++i) scratch[oi[i]] = o[i];
+            stream_plane(dst + q * plane, scratch, plane);
+        }
+#if defined(__SSE2__)
+    _mm_sfence();
+#endif
+}
+
+// Host threads of one call: a queue of closures; the main thread keeps the link busy and hands out the work.
+struct DrainPool {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::function<void(double *)>> q;
+    std::vector<std::thread> th;
+    bool stop = false;
+    void start(int n, size_t scratch_elems) {
+        for (int t = 0; t < n; ++t)
+            th.emplace_back([this, scratch_elems]() {
+                std::vector<double> scratch(scratch_elems);
+                for (;;) {
+                    std::function<void(double *)> f;
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [this] { return stop || !q.empty(); });
+                        if (q.empty()) return;
+                        f = std::move(q.front());
+                        q.pop_front();
+                    }
+                    f(scratch.data());
+                }
+            });
+    }
+    void push(std::function<void(double *)> f) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            q.push_back(std::move(f));
+        }
+        cv.notify_one();
+    }
+    void finish() {   // run the queue dry, then join
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv.notify_all();
+        for (auto &t : th) t.join();
+        th.clear();
+    }
+    ~DrainPool() { finish(); }
+};
+
+int host_threads() {
+    // this process' share of the host cores when every visible GPU runs a rank of its own (one process per GPU), at most
+    // 16; NESOSIM_HOST_THREADS overrides (bench.py sets it to cores / world size)
+    int n = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency() / (unsigned)std::max(1, nesosim_device_count())));
+    if (const char *e = getenv("NESOSIM_HOST_THREADS")) n = std::max(1, atoi(e));
+    return n;
+}
 
 long long var_elems_per_member(const nesosim_ctx *ctx, int v) {   // v indexes the 11 arrays of nesosim_outputs
     const long long T = ctx->cfg.num_days;
@@ -23,6 +125,18 @@ double *const *host_arrays(const nesosim_outputs *o, double *tmp[11]) {
 }
 
 }  // namespace
+
+// The host half of the compacted drain on its own (no device involved): one member's packed block of one array ->
+// full planes.  What nesosim_run_season_host's threads run; exported so that the layout has a test without a GPU.
+extern "C" int nesosim_unpack_member_array(const uint8_t *mask, int64_t plane, int planes_per_slot, int num_days,
+                                           const double *packed, double *dst) {
+    if (!mask || !packed || !dst || plane < 1 || planes_per_slot < 1 || num_days < 1) return fail(NESOSIM_ERR_ARG, "bad argument");
+    std::vector<int> oi, li;
+    for (int64_t c = 0; c < plane; ++c) ((mask[c] > 10 || mask[c] < 1) ? li : oi).push_back((int)c);
+    std::vector<double> scratch((size_t)plane);
+    scatter_member_array(oi, li, plane, planes_per_slot, num_days, (int)std::min<long long>(DRAIN_HEAD, num_days), packed, dst, scratch.data());
+    return NESOSIM_OK;
+}
 
 extern "C" int nesosim_run_season_host(nesosim_ctx *ctx, const double *precip, const double *conc,
                                        const double *wind, const double *drift, const double *rho_clim,
@@ -93,12 +207,42 @@ extern "C" int nesosim_run_season_host(nesosim_ctx *ctx, const double *precip, c
     if ((rc = upload_coef(ctx, params, hp->compute))) return rc;
     up += (int64_t)sizeof(MemberCoef) * M;
 
-    // batch size: two device buffers of <= NESOSIM_HOST_BATCH_GB (default 16 GiB) each.  Measured on a B200 box
-    // (tools/e2e_variants.py, 128 members x 260 days, 21.6 GB to the host): 2 GiB 452 ms, 8 GiB 462 ms, 16 GiB 427 ms --
-    // fewer, longer copies keep the link busier (53.9 GB/s is what a plain pinned copy reaches there).
+    // ---- which drain?  The compacted one pays when the link is slower than this process' host threads can scatter.
+    const int nthreads = host_threads();
+    const bool share = M > 1 && ctx->n_sets == 1 && !getenv("NESOSIM_HOST_NO_SHARE");
+    if (hp->n_ocean < 0) {
+        for (long long c = 0; c < plane; ++c) {
+            const uint8_t mk = ctx->mask_host[(size_t)c];
+            ((mk > 10 || mk < 1) ? hp->land_idx : hp->ocean_idx).push_back((int)c);
+        }
+        hp->n_ocean = (int)hp->ocean_idx.size();
+        hp->n_land = (int)hp->land_idx.size();
+    }
+    int carr[DRAIN_MAX_ARRAYS], n_carr = 0;        // the member-dependent arrays that were asked for
+    for (int v = 0; v < 11; ++v)
+        if (harr[v] && v != 2 && v != 3) carr[n_carr++] = v;
+    // Measured on a 16-core B200 box (128 members x 260 days, 21.6 GB of arrays; tools/e2e_variants.py): plain drain
+    // 425-455 ms (the link: 54 GB/s); compacted 1186 ms with 2 threads, 665 with 4, 372 with 8, 325 with 12 or 16 (the
+    // host's memory system: the scatter writes 26 GB and the ring is written and read once more).
+    bool compact = n_carr > 0 && T > DRAIN_HEAD && plane < (1ll << 31) && nthreads >= 8 && (double)hp->n_ocean <= 0.6 * (double)plane;
+    if (const char *e = getenv("NESOSIM_HOST_COMPACT")) compact = n_carr > 0 && plane < (1ll << 31) && atoi(e) != 0;
+    int head = (int)std::min<long long>(DRAIN_HEAD, T);
+    // (tests only: fewer head slots than the model needs, so that the land-cell check trips and the chunk is copied in full)
+    if (const char *e = getenv("NESOSIM_DRAIN_HEAD")) head = std::max(1, std::min(head, atoi(e)));
+    long long rec_elems = 0, rec_off[DRAIN_MAX_ARRAYS];
+    for (int i = 0; i < n_carr; ++i) {
+        const int pps = carr[i] == 0 ? 2 : 1;
+        rec_off[i] = rec_elems;
+        rec_elems += (long long)pps * T * hp->n_ocean + (long long)pps * head * hp->n_land;
+    }
+
+    // batch size: two device buffers of <= NESOSIM_HOST_BATCH_GB each (default 16 GiB; 4 GiB for the compacted drain,
+    // whose first chunk cannot leave before the first batch is computed and packed).  Measured on a B200 box
+    // (tools/e2e_variants.py, 128 members x 260 days, 21.6 GB to the host, full drain): 2 GiB 452 ms, 8 GiB 462 ms,
+    // 16 GiB 427 ms -- fewer, longer copies keep the link busier (53.9 GB/s is what a plain pinned copy reaches there).
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    double cap_gb = 16.0;
+    double cap_gb = compact ? 4.0 : 16.0;
     if (const char *e = getenv("NESOSIM_HOST_BATCH_GB")) cap_gb = atof(e);
     size_t cap = (size_t)(cap_gb * (1ull << 30));
     if (!hp->outbuf[0] && cap * 2 > free_b / 10 * 8) cap = free_b / 10 * 4;
@@ -125,80 +269,299 @@ extern "C" int nesosim_run_season_host(nesosim_ctx *ctx, const double *precip, c
         hp->outbuf_bytes = need_bytes;
     }
     batch = (int)std::max<long long>(1, std::min<long long>(batch, (long long)(hp->outbuf_bytes / ((size_t)per_member * 8))));
+    const int n_batches = (M + batch - 1) / batch;
 
-    // member-independent arrays (v = 2 snowAcc, v = 3 snowOcean): one device->host copy, replicated on the host
-    const bool share = M > 1 && ctx->n_sets == 1 && !getenv("NESOSIM_HOST_NO_SHARE");
+    // compacted drain: the packed blocks -- one per (member, array), contiguous in member-major order -- travel in chunks
+    // of NESOSIM_HOST_CHUNK_MB (default 32) into a ring of NESOSIM_HOST_RING (default 6) pinned slots
+    int RING = 6;
+    if (const char *e = getenv("NESOSIM_HOST_RING")) RING = std::max(2, std::min(32, atoi(e)));
+    long long chunk_target = 32ll << 20;
+    if (const char *e = getenv("NESOSIM_HOST_CHUNK_MB")) chunk_target = (long long)(atof(e) * (1 << 20));
+    struct Chunk {
+        int nb;                 // batch
+        int t0, t1;             // blocks [t0, t1) of the batch; block t = member-in-batch * n_carr + array
+        long long off, elems;   // inside the batch's packed buffer
+    };
+    std::vector<Chunk> chunks;
+    std::vector<int> batch_last_chunk(n_batches, -1);
+    long long max_chunk_elems = 0;
+    int max_chunk_blocks = 0;
+    auto block_elems = [&](int i) { return (i + 1 < n_carr ? rec_off[i + 1] : rec_elems) - rec_off[i]; };
+    if (compact) {
+        for (int nb = 0; nb < n_batches; ++nb) {
+            const int cnt = std::min(batch, M - nb * batch), nblk = cnt * n_carr;
+            for (int t = 0; t < nblk;) {
+                Chunk c{nb, t, t, (long long)(t / n_carr) * rec_elems + rec_off[t % n_carr], 0};
+                do {
+                    c.elems += block_elems(c.t1 % n_carr);
+                    ++c.t1;
+                } while (c.t1 < nblk && (c.elems + block_elems(c.t1 % n_carr)) * 8 <= chunk_target);
+                t = c.t1;
+                max_chunk_elems = std::max(max_chunk_elems, c.elems);
+                max_chunk_blocks = std::max(max_chunk_blocks, c.t1 - c.t0);
+                chunks.push_back(c);
+            }
+            batch_last_chunk[nb] = (int)chunks.size() - 1;
+        }
+        if (!hp->cells_dev) {
+            CU(cudaMalloc(&hp->cells_dev, (size_t)plane * sizeof(int)));
+            CU(cudaMemcpy(hp->cells_dev, hp->ocean_idx.data(), (size_t)hp->n_ocean * sizeof(int), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(hp->cells_dev + hp->n_ocean, hp->land_idx.data(), (size_t)hp->n_land * sizeof(int), cudaMemcpyHostToDevice));
+        }
+        const size_t pk = (size_t)batch * rec_elems * 8;
+        if (hp->packed_bytes < pk) {
+            for (int i = 0; i < 2; ++i) {
+                cudaFree(hp->packed[i]);
+                hp->packed[i] = nullptr;
+            }
+            hp->packed_bytes = 0;
+            for (int i = 0; i < 2; ++i) CU(cudaMalloc(&hp->packed[i], pk));
+            hp->packed_bytes = pk;
+        }
+        // a ring slot: the chunk's blocks, then one counter per block
+        const size_t slot_bytes = (size_t)max_chunk_elems * 8 + (size_t)max_chunk_blocks * 8;
+        if (hp->ring_bytes < RING * slot_bytes) {
+            if (hp->ring) cudaFreeHost(hp->ring);
+            hp->ring = nullptr;
+            hp->ring_bytes = 0;
+            CU(cudaHostAlloc((void **)&hp->ring, RING * slot_bytes, cudaHostAllocDefault));
+            hp->ring_bytes = RING * slot_bytes;
+        }
+        while ((int)hp->arrived.size() < RING) {
+            cudaEvent_t ev;
+            CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            hp->arrived.push_back(ev);
+        }
+        if (hp->chunk_flags_n < (size_t)2 * batch * n_carr) {
+            cudaFree(hp->chunk_flags);
+            hp->chunk_flags = nullptr;
+            hp->chunk_flags_n = 0;
+            CU(cudaMalloc(&hp->chunk_flags, (size_t)2 * batch * n_carr * sizeof(unsigned long long)));
+            hp->chunk_flags_n = (size_t)2 * batch * n_carr;
+        }
+    }
+    const size_t slot_bytes = (size_t)max_chunk_elems * 8 + (size_t)max_chunk_blocks * 8;
     if (share && !hp->shared_ready) CU(cudaEventCreateWithFlags(&hp->shared_ready, cudaEventDisableTiming));
 
-    int nb = 0;
-    for (int m0 = 0; m0 < M; m0 += batch, ++nb) {
-        const int cnt = std::min(batch, M - m0);
+    // progress of the scatter, one counter per chunk of the call (guarded by prog_mu); declared before the pool, whose
+    // destructor runs the queue dry
+    std::mutex prog_mu;
+    std::vector<int> pending(chunks.size() + 1, 0);
+    DrainPool pool;
+    const bool need_pool = compact || (share && (harr[2] || harr[3]));
+    if (need_pool) pool.start(nthreads, compact ? (size_t)plane : 1);
+
+    struct BatchView {
+        int m0 = 0, cnt = 0;
+        double *darr[11];
+    };
+    std::vector<BatchView> views(n_batches);
+
+    // ---- compute (and pack) of batch nb, on the compute stream
+    auto launch = [&](int nb) -> int {
+        BatchView &bv = views[nb];
+        bv.m0 = nb * batch;
+        bv.cnt = std::min(batch, M - bv.m0);
         const int b = nb & 1;
-        if (nb >= 2) CU(cudaStreamWaitEvent(hp->compute, hp->drained[b], 0));
+        if (nb >= 2 && !compact) CU(cudaStreamWaitEvent(hp->compute, hp->drained[b], 0));
         // device views of this batch, variable-major inside the buffer
         nesosim_outputs dev{};
-        double *darr[11];
         long long off = 0;
         for (int v = 0; v < 11; ++v) {
-            darr[v] = nullptr;
+            bv.darr[v] = nullptr;
             if (!harr[v]) continue;
-            darr[v] = hp->outbuf[b] + off;
-            off += var_elems_per_member(ctx, v) * cnt;
+            bv.darr[v] = hp->outbuf[b] + off;
+            off += var_elems_per_member(ctx, v) * bv.cnt;
         }
+        double **darr = bv.darr;
         dev.snowDepths = darr[0]; dev.density = darr[1]; dev.snowAcc = darr[2]; dev.snowOcean = darr[3];
         dev.snowAdv = darr[4]; dev.snowDiv = darr[5]; dev.snowLead = darr[6]; dev.snowAtm = darr[7];
         dev.snowWindPackLoss = darr[8]; dev.snowWindPackGain = darr[9]; dev.snowWindPack = darr[10];
         dev.depth_member_stride = 2 * T * plane;
         dev.plane_member_stride = T * plane;
-        rc = run_members(ctx, ic ? hp->ic : nullptr, ic_per_member, &dev, m0, cnt, 0, -1, hp->compute);
-        if (rc) return rc;
+        int rc_ = run_members(ctx, ic ? hp->ic : nullptr, ic_per_member, &dev, bv.m0, bv.cnt, 0, -1, hp->compute);
+        if (rc_) return rc_;
+        if (compact) {
+            PackArgs pa{};
+            pa.n_arrays = n_carr; pa.T = (int)T; pa.head = head;
+            pa.plane = (int)plane; pa.n_ocean = hp->n_ocean; pa.n_land = hp->n_land;
+            pa.ocean_idx = hp->cells_dev; pa.land_idx = hp->cells_dev + hp->n_ocean;
+            pa.rec_elems = rec_elems;
+            pa.plane0[0] = 0;
+            for (int i = 0; i < n_carr; ++i) {
+                const int v = carr[i];
+                pa.pps[i] = v == 0 ? 2 : 1;
+                pa.mstride[i] = var_elems_per_member(ctx, v);
+                pa.rec_off[i] = rec_off[i];
+                pa.plane0[i + 1] = pa.plane0[i] + pa.pps[i] * (int)T;
+                pa.src[i] = darr[v];
+            }
+            pa.dst = hp->packed[b];
+            pa.flag = hp->chunk_flags + (size_t)b * batch * n_carr;
+            CU(cudaMemsetAsync(pa.flag, 0, (size_t)bv.cnt * n_carr * sizeof(unsigned long long), hp->compute));
+            pack_ocean_kernel<<<dim3((unsigned)pa.plane0[n_carr], (unsigned)bv.cnt), 256, 0, hp->compute>>>(pa);
+            CU(cudaGetLastError());
+            ctx->launches += 1;
+        }
         CU(cudaEventRecord(hp->done[b], hp->compute));
-        CU(cudaStreamWaitEvent(hp->copy, hp->done[b], 0));
-        if (share && m0 == 0) {       // first on the link, so the host threads can start replicating early
-            for (int v = 2; v <= 3; ++v) {
-                if (!harr[v]) continue;
-                const long long n = var_elems_per_member(ctx, v);
-                CU(cudaMemcpyAsync(harr[v], darr[v], (size_t)n * 8, cudaMemcpyDeviceToHost, hp->copy));
-                down += n * 8;
-            }
-            CU(cudaEventRecord(hp->shared_ready, hp->copy));
-        }
-        for (int v = 0; v < 11; ++v) {
-            if (!harr[v] || (share && (v == 2 || v == 3))) continue;
+        return NESOSIM_OK;
+    };
+
+    // ---- member-independent arrays (v = 2 snowAcc, v = 3 snowOcean): one device->host copy, replicated on the host
+    auto drain_shared = [&](const BatchView &bv) -> int {
+        for (int v = 2; v <= 3; ++v) {
+            if (!harr[v]) continue;
             const long long n = var_elems_per_member(ctx, v);
-            const long long hstride = (v == 0) ? out_host->depth_member_stride : out_host->plane_member_stride;
-            if (hstride == n) {
-                CU(cudaMemcpyAsync(harr[v] + (long long)m0 * hstride, darr[v], (size_t)n * cnt * 8, cudaMemcpyDeviceToHost, hp->copy));
-            } else {
-                for (int m = 0; m < cnt; ++m)
-                    CU(cudaMemcpyAsync(harr[v] + (long long)(m0 + m) * hstride, darr[v] + (long long)m * n, (size_t)n * 8,
-                                       cudaMemcpyDeviceToHost, hp->copy));
-            }
-            down += n * cnt * 8;
+            CU(cudaMemcpyAsync(harr[v], bv.darr[v], (size_t)n * 8, cudaMemcpyDeviceToHost, hp->copy));
+            down += n * 8;
         }
-        CU(cudaEventRecord(hp->drained[b], hp->copy));
+        CU(cudaEventRecord(hp->shared_ready, hp->copy));
+        return NESOSIM_OK;
+    };
+    auto copy_full = [&](const BatchView &bv, int v, int ml, int cnt) -> int {   // members ml .. ml+cnt-1 of the batch
+        const long long n = var_elems_per_member(ctx, v);
+        const long long hstride = (v == 0) ? out_host->depth_member_stride : out_host->plane_member_stride;
+        if (hstride == n) {
+            CU(cudaMemcpyAsync(harr[v] + (long long)(bv.m0 + ml) * hstride, bv.darr[v] + (long long)ml * n, (size_t)n * cnt * 8,
+                               cudaMemcpyDeviceToHost, hp->copy));
+        } else {
+            for (int m = ml; m < ml + cnt; ++m)
+                CU(cudaMemcpyAsync(harr[v] + (long long)(bv.m0 + m) * hstride, bv.darr[v] + (long long)m * n, (size_t)n * 8,
+                                   cudaMemcpyDeviceToHost, hp->copy));
+        }
+        down += n * cnt * 8;
+        return NESOSIM_OK;
+    };
+    bool replication_queued = false;
+    auto queue_replication = [&]() {
+        if (replication_queued || !share || !(harr[2] || harr[3])) return;
+        replication_queued = true;
+        const long long n = var_elems_per_member(ctx, 2), hstride = out_host->plane_member_stride;
+        for (int m = 1; m < M; ++m)
+            for (int v = 2; v <= 3; ++v)
+                if (harr[v]) {
+                    double *dst = harr[v] + (long long)m * hstride;
+                    const double *src = harr[v];
+                    pool.push([=](double *) { stream_plane(dst, src, n); });
+                }
+    };
+
+    if (!compact) {
+        // ---- plain drain: batch nb drains on the copy stream while batch nb+1 computes
+        for (int nb = 0; nb < n_batches; ++nb) {
+            if ((rc = launch(nb))) return rc;
+            const BatchView &bv = views[nb];
+            const int b = nb & 1;
+            CU(cudaStreamWaitEvent(hp->copy, hp->done[b], 0));
+            if (share && nb == 0 && (rc = drain_shared(bv))) return rc;   // first on the link: replication starts early
+            for (int v = 0; v < 11; ++v) {
+                if (!harr[v] || (share && (v == 2 || v == 3))) continue;
+                if ((rc = copy_full(bv, v, 0, bv.cnt))) return rc;
+            }
+            CU(cudaEventRecord(hp->drained[b], hp->copy));
+        }
+    } else {
+        // ---- compacted drain: one pipeline over all the chunks of the call.  The main thread launches batches as their
+        // buffers come free, keeps up to RING chunk copies queued on the link and hands every arrived chunk to the pool.
+        const int NC = (int)chunks.size();
+        int launched = 0, issued = 0, taken = 0;
+        bool plain_copies = false;      // copies out of a batch's full arrays are queued on the copy stream
+        auto slot_free = [&](int ch) {  // has the chunk that used this ring slot before been scattered?
+            if (ch < RING) return true;
+            std::lock_guard<std::mutex> lk(prog_mu);
+            return pending[ch - RING] == 0;
+        };
+        while (taken < NC) {
+            bool progress = false;
+            // a batch may start when every packed chunk of the batch two before it has reached the host
+            if (launched < n_batches && (launched < 2 || taken > batch_last_chunk[launched - 2])) {
+                if (launched >= 2 && plain_copies) {
+                    CU(cudaStreamSynchronize(hp->copy));
+                    plain_copies = false;
+                }
+                if ((rc = launch(launched))) return rc;
+                const BatchView &bv = views[launched];
+                CU(cudaStreamWaitEvent(hp->copy, hp->done[launched & 1], 0));
+                if (launched == 0 && share && (harr[2] || harr[3]) && (rc = drain_shared(bv))) return rc;
+                if (!share)
+                    for (int v = 2; v <= 3; ++v)
+                        if (harr[v]) {
+                            if ((rc = copy_full(bv, v, 0, bv.cnt))) return rc;
+                            plain_copies = true;
+                        }
+                ++launched;
+                progress = true;
+            }
+            while (issued < NC && chunks[issued].nb < launched && issued < taken + RING && slot_free(issued)) {
+                const Chunk &c = chunks[issued];
+                char *slot = (char *)hp->ring + (size_t)(issued % RING) * slot_bytes;
+                const int b = c.nb & 1;
+                CU(cudaMemcpyAsync(slot, hp->packed[b] + c.off, (size_t)c.elems * 8, cudaMemcpyDeviceToHost, hp->copy));
+                CU(cudaMemcpyAsync(slot + (size_t)max_chunk_elems * 8, hp->chunk_flags + (size_t)b * batch * n_carr + c.t0,
+                                   (size_t)(c.t1 - c.t0) * 8, cudaMemcpyDeviceToHost, hp->copy));
+                CU(cudaEventRecord(hp->arrived[issued % RING], hp->copy));
+                down += (int64_t)c.elems * 8 + (c.t1 - c.t0) * 8;
+                ++issued;
+                progress = true;
+            }
+            if (share && !replication_queued && cudaEventQuery(hp->shared_ready) == cudaSuccess) {
+                queue_replication();
+                progress = true;
+            }
+            if (taken < issued) {
+                const cudaError_t q_ = cudaEventQuery(hp->arrived[taken % RING]);
+                if (q_ == cudaSuccess) {
+                    const Chunk &c = chunks[taken];
+                    const BatchView &bv = views[c.nb];
+                    const char *slot = (const char *)hp->ring + (size_t)(taken % RING) * slot_bytes;
+                    const unsigned long long *bad = (const unsigned long long *)(slot + (size_t)max_chunk_elems * 8);
+                    int n_tasks = 0;
+                    for (int t = c.t0; t < c.t1; ++t) n_tasks += bad[t - c.t0] == 0;
+                    {
+                        std::lock_guard<std::mutex> lk(prog_mu);
+                        pending[taken] = n_tasks;
+                    }
+                    long long boff = 0;      // of the block inside the slot
+                    for (int t = c.t0; t < c.t1; ++t) {
+                        const int ml = t / n_carr, i = t % n_carr, v = carr[i], pps = v == 0 ? 2 : 1;
+                        const double *oc = (const double *)slot + boff;
+                        boff += block_elems(i);
+                        if (bad[t - c.t0]) {     // land cells not constant: the plain copy of this member's array
+                            if ((rc = copy_full(bv, v, ml, 1))) return rc;
+                            plain_copies = true;
+                            ctx->hp_full_chunks++;
+                            continue;
+                        }
+                        const long long hstride = (v == 0) ? out_host->depth_member_stride : out_host->plane_member_stride;
+                        double *dst = harr[v] + (long long)(bv.m0 + ml) * hstride;
+                        int *cnt_p = &pending[taken];
+                        std::mutex *mu_p = &prog_mu;
+                        const std::vector<int> *oi = &hp->ocean_idx, *li = &hp->land_idx;
+                        const int T_ = (int)T;
+                        pool.push([=](double *scratch) {
+                            scatter_member_array(*oi, *li, plane, pps, T_, head, oc, dst, scratch);
+                            std::lock_guard<std::mutex> lk(*mu_p);
+                            --*cnt_p;
+                        });
+                    }
+                    ++taken;
+                    progress = true;
+                } else if (q_ != cudaErrorNotReady) {
+                    return cuda_fail(q_, "device->host copy of a packed chunk");
+                }
+            }
+            if (!progress) std::this_thread::sleep_for(std::chrono::microseconds(10));
+        }
     }
     if (share && (harr[2] || harr[3])) {
         CU(cudaEventSynchronize(hp->shared_ready));
-        const long long n = var_elems_per_member(ctx, 2), hstride = out_host->plane_member_stride;
-        // replication threads: this process' share of the host cores when every visible GPU runs a rank of its own (one
-        // process per GPU), at most 16.  The copy into the other members' slots is on the critical path of the call
-        // when it is too slow (same box: 2 threads 604 ms, 4 495 ms, 8 462 ms, 16 458 ms; without sharing 480 ms), and
-        // 8 ranks x 8 threads oversubscribed the memory bus of a box.  NESOSIM_HOST_THREADS overrides
-        int nthreads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency() / (unsigned)std::max(1, nesosim_device_count())));
-        if (const char *e = getenv("NESOSIM_HOST_THREADS")) nthreads = std::max(1, atoi(e));
-        std::vector<std::thread> pool;
-        for (int t = 0; t < nthreads; ++t)
-            pool.emplace_back([=]() {
-                for (int m = 1 + t; m < M; m += nthreads)
-                    for (int v = 2; v <= 3; ++v)
-                        if (harr[v]) std::memcpy(harr[v] + (long long)m * hstride, harr[v], (size_t)n * 8);
-            });
-        for (auto &th : pool) th.join();
+        queue_replication();
     }
+    pool.finish();
     CU(cudaStreamSynchronize(hp->compute));
     CU(cudaStreamSynchronize(hp->copy));
     if (h2d_bytes) *h2d_bytes = up;
     if (d2h_bytes) *d2h_bytes = down;
+    ctx->hp_last_compact = compact ? 1 : 0;
     return NESOSIM_OK;
 }

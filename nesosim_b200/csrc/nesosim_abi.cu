@@ -1,12 +1,17 @@
 // nesosim_abi.cu -- C ABI (include/nesosim_b200.h) over the sm_100a kernels.  No torch, no CPU fallback.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -15,6 +20,7 @@
 #include "../../include/nesosim_b200.h"
 #include "day_kernels.cuh"
 #include "ensemble_kernel.cuh"
+#include "drain_kernels.cuh"
 
 using namespace nesosim;
 
@@ -137,6 +143,18 @@ struct HostPath {
     cudaEvent_t done[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr};
     cudaEvent_t shared_ready = nullptr;   // member 0's snowAcc / snowOcean have reached the host
     size_t ic_elems = 0;
+    // compacted drain (drain_kernels.cuh): packed records on the device (one buffer per output buffer), a ring of pinned
+    // host slots the chunks land in, the cell lists of the mask, one "land cells not constant" counter per chunk
+    double *packed[2] = {nullptr, nullptr};
+    size_t packed_bytes = 0;
+    double *ring = nullptr;               // pinned
+    size_t ring_bytes = 0;
+    std::vector<cudaEvent_t> arrived;     // one per ring slot
+    int *cells_dev = nullptr;             // ocean list, then land list
+    int n_ocean = -1, n_land = 0;
+    std::vector<int> ocean_idx, land_idx;
+    unsigned long long *chunk_flags = nullptr;   // device
+    size_t chunk_flags_n = 0;
 };
 
 
@@ -196,6 +214,8 @@ struct nesosim_ctx {
     int day_variant = 256;          // threads per CTA of the day kernel (256 x 2 cells or 512 x 1 cell)
     int path = 0;                   // 0 auto, 1 general per-day launches, 2 season-resident ensemble kernel
     int last_path = 0;              // which path the last run_season used (1 or 2)
+    int hp_last_compact = 0;        // nesosim_run_season_host: did the last call use the compacted drain?
+    long long hp_full_chunks = 0;   // chunks of a compacted drain that had to be copied in full (land cells not constant)
     // row-strip domain decomposition over peer memory (nesosim_strip_*; StripLink in day_kernels.cuh)
     struct {
         bool on = false;
@@ -1073,6 +1093,11 @@ int nesosim_destroy(nesosim_ctx *ctx) {
         if (ctx->hp.drained[i]) cudaEventDestroy(ctx->hp.drained[i]);
     }
     if (ctx->hp.shared_ready) cudaEventDestroy(ctx->hp.shared_ready);
+    for (int i = 0; i < 2; ++i) cudaFree(ctx->hp.packed[i]);
+    if (ctx->hp.ring) cudaFreeHost(ctx->hp.ring);
+    for (cudaEvent_t e : ctx->hp.arrived) cudaEventDestroy(e);
+    cudaFree(ctx->hp.cells_dev);
+    cudaFree(ctx->hp.chunk_flags);
     if (ctx->hp.compute) cudaStreamDestroy(ctx->hp.compute);
     if (ctx->hp.copy) cudaStreamDestroy(ctx->hp.copy);
     delete ctx;
@@ -1434,6 +1459,13 @@ int nesosim_final_products(const double *depths_dev, const double *density_dev, 
 
 int64_t nesosim_launch_count(const nesosim_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int64_t nesosim_rerun_count(const nesosim_ctx *ctx) { return ctx ? ctx->ens_reruns : 0; }
+
+int nesosim_host_drain_info(const nesosim_ctx *ctx, int *compacted, int64_t *full_chunks) {
+    if (!ctx) return fail(NESOSIM_ERR_ARG, "NULL context");
+    if (compacted) *compacted = ctx->hp_last_compact;
+    if (full_chunks) *full_chunks = ctx->hp_full_chunks;
+    return NESOSIM_OK;
+}
 int nesosim_season_kernel_time(const nesosim_ctx *ctx, double *total_ms, int64_t *launches) {
     if (!ctx || !total_ms || !launches) return fail(NESOSIM_ERR_ARG, "NULL argument");
     *total_ms = ctx->ens_kernel_ms;           // (asynchronous launches count once nesosim_sync / a later call has seen them)

@@ -195,6 +195,13 @@ class SnowBudgetEngine:
         """Seasons the season-resident kernel handed back to the general kernels (operand-range flag)."""
         return int(self.lib.nesosim_rerun_count(self.handle))
 
+    def host_drain_info(self):
+        """(compacted, full_chunks): whether the last `run_season_host` shipped ocean cells only, and how many chunks
+        of members had to be copied in full since creation because their land cells were not constant."""
+        c, n = C.c_int(0), C.c_int64(0)
+        _lib.check(self.lib.nesosim_host_drain_info(self.handle, C.byref(c), C.byref(n)))
+        return bool(c.value), int(n.value)
+
     def season_kernel_time(self):
         """(total device ms, launches) of the season-resident kernel so far."""
         ms, n = C.c_double(0), C.c_int64(0)

@@ -112,3 +112,30 @@ def test_constant_division_is_exact(lib):
     # grid spacings, the fresh-snow density and the Gaussian kernel sum must all take the 3-operation path
     for c in (100000., 200000., 25000., 50000., 5000., 10000., 200., ksum):
         assert lib.nesosim_const_div_is_fast(c) == 1, c
+
+
+@pytest.mark.parametrize("pps,T,offset", [(1, 7, 0), (2, 5, 0), (1, 2, 0), (2, 9, 1)])
+def test_unpack_member_array_layout(lib, pps, T, offset):
+    """The host half of the compacted drain (drain_kernels.cuh layout): ocean cells of every plane + land cells of the
+    first three slots -> full planes, later slots repeating the third slot's land cells; NaNs keep their bits; a
+    destination that is only 8-byte aligned (odd offset) takes the unaligned path of the streaming stores."""
+    rng = np.random.default_rng(pps * 100 + T)
+    ny, nx = 9, 11
+    mask = rng.choice(np.array([0, 3, 8, 8, 11, 12], dtype=np.uint8), size=(ny, nx))
+    plane = ny * nx
+    land = ((mask > 10) | (mask < 1)).ravel()
+    full = rng.normal(size=(T, pps, plane))
+    full[rng.random(full.shape) < 0.1] = np.nan
+    head = min(3, T)
+    for s in range(head, T):                      # the contract of the packed form: land constant after the head slots
+        full[s][:, land] = full[head - 1][:, land]
+    planes = full.reshape(T * pps, plane)
+    packed = np.concatenate([planes[:, ~land].ravel(), planes[:head * pps][:, land].ravel()])
+    buf = np.full(T * pps * plane + 2, -7.0)
+    dst = buf[offset:offset + T * pps * plane]
+    rc = lib.nesosim_unpack_member_array(mask.ctypes.data_as(C.c_void_p), plane, pps, T,
+                                         packed.ctypes.data_as(C.c_void_p), dst.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    assert np.array_equal(dst.view(np.uint64), planes.ravel().view(np.uint64))
+    assert buf[offset + T * pps * plane:].tolist() == [-7.0] * (2 - offset) and (offset == 0 or buf[0] == -7.0)
+    assert lib.nesosim_unpack_member_array(None, plane, pps, T, packed.ctypes.data_as(C.c_void_p), dst.ctypes.data_as(C.c_void_p)) != 0

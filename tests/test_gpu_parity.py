@@ -490,8 +490,9 @@ def test_outputs_subset_on_the_general_path_with_mixed_member_strides(cuda):
     eng.close()
 
 
-def test_host_path_end_to_end(cuda):
+def test_host_path_end_to_end(cuda, monkeypatch):
     from nesosim_b200.engine import SnowBudgetEngine
+    monkeypatch.setenv("NESOSIM_HOST_COMPACT", "0")     # the plain drain: every byte of the contract crosses the link
     mask = S.region_mask(dx=100000)
     T = 10
     forcing = S.make_season(mask, T, seed=22)
@@ -512,11 +513,12 @@ def test_host_path_end_to_end(cuda):
             assert_parity(out[name][m], ref[name], name)
 
 
-def test_host_path_regrows_its_staging_when_more_outputs_are_asked_for(cuda):
+def test_host_path_regrows_its_staging_when_more_outputs_are_asked_for(cuda, monkeypatch):
     """One engine, first a season with only snowDepths requested, then with all eleven arrays and the same member
     batch: the cached device staging is sized in bytes, so the second call must regrow it (it used to be cached by
     the batch count and the second season wrote up to 6x past the allocation)."""
     from nesosim_b200.engine import SnowBudgetEngine
+    monkeypatch.setenv("NESOSIM_HOST_COMPACT", "0")
     mask = S.region_mask(dx=100000)
     T, M = 9, 3
     forcing = S.make_season(mask, T, seed=31)
@@ -535,6 +537,93 @@ def test_host_path_regrows_its_staging_when_more_outputs_are_asked_for(cuda):
         for name in again:
             assert_parity(again[name][m], ref[name], name + " (third call)")
     eng.close()
+
+
+def _host_season(eng, forcing, params, ic, monkeypatch, compact, names=None, **env):
+    monkeypatch.setenv("NESOSIM_HOST_COMPACT", "1" if compact else "0")
+    for k in ("NESOSIM_HOST_BATCH_GB", "NESOSIM_HOST_CHUNK_MB", "NESOSIM_DRAIN_HEAD", "NESOSIM_HOST_THREADS"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    kw = {} if names is None else {"names": names}
+    # poisoned destination: every cell the drain does not write would show
+    out = None
+    if names is None:
+        from nesosim_b200 import _lib
+        names = _lib.OUTPUT_NAMES
+    out = {n: np.full((eng.M, eng.T, 2, eng.ny, eng.nx) if n == "snowDepths" else (eng.M, eng.T, eng.ny, eng.nx), -3.25)
+           for n in names}
+    res, up, down = eng.run_season_host(forcing, params, ic, outputs=out, **kw)
+    return res, down, eng.host_drain_info()
+
+
+@pytest.mark.parametrize("path", ["ensemble", "general"])
+def test_host_path_compacted_drain_matches_the_plain_one_bit_for_bit(cuda, monkeypatch, path):
+    """nesosim_run_season_host with the compacted drain (ocean cells + the land cells of the first three slots cross the
+    link, host threads scatter) against the plain copy of every array: same bits in the caller's arrays -- NaNs
+    included -- through one batch and one chunk, through several batches, and through more chunks than the pinned ring
+    has slots; and well under half of the bytes on the link."""
+    from nesosim_b200.engine import SnowBudgetEngine
+    mask = S.region_mask(dx=100000)
+    T, M = 12, 7
+    forcing = S.make_season(mask, T, seed=41)
+    ic = S.make_ic(mask, seed=41)
+    ic[:3] = 0.07                                   # snow on land in the initial condition: slot 1 differs from slot 2 there
+    params = S.ensemble_params(M, seed=41)
+    eng = SnowBudgetEngine(mask, T, 100000, n_members=M, atmlossInc=1)
+    eng.set_path(path)
+    plain, down_plain, info = _host_season(eng, forcing, params, ic, monkeypatch, False)
+    assert info[0] is False
+    ref0 = O.run_season(forcing, ic, mask, 100000, oracle_params(params[0]), O.Flags(atmlossInc=1))
+    for name in plain:
+        assert_parity(plain[name][0], ref0[name], name)
+    for env in ({}, {"NESOSIM_HOST_BATCH_GB": "0.03"}, {"NESOSIM_HOST_CHUNK_MB": "1.5"},
+                {"NESOSIM_HOST_CHUNK_MB": "0.1", "NESOSIM_HOST_THREADS": "3"},
+                {"NESOSIM_HOST_BATCH_GB": "0.05", "NESOSIM_HOST_CHUNK_MB": "0.1", "NESOSIM_HOST_THREADS": "1"}):
+        packed, down, info = _host_season(eng, forcing, params, ic, monkeypatch, True, **env)
+        assert info == (True, 0), (env, info)
+        assert down < 0.62 * down_plain, (env, down, down_plain)
+        for name in plain:
+            assert np.array_equal(packed[name].view(np.uint64), plain[name].view(np.uint64)), (name, env)
+    eng.close()
+
+
+def test_host_path_compacted_drain_falls_back_when_land_cells_change(cuda, monkeypatch):
+    """The packed form repeats a land cell's value of the last head slot; that land cells are constant from there on is
+    checked on the device, chunk by chunk.  With a single head slot (test knob) slot 1 differs from slot 0 on land, every
+    chunk is flagged and copied in full: the arrays are the same again, and the call says how many chunks it gave up."""
+    from nesosim_b200.engine import SnowBudgetEngine
+    mask = S.region_mask(dx=100000)
+    T, M = 8, 5
+    forcing = S.make_season(mask, T, seed=43)
+    ic = S.make_ic(mask, seed=43)
+    params = S.ensemble_params(M, seed=43)
+    eng = SnowBudgetEngine(mask, T, 100000, n_members=M)
+    plain, _, _ = _host_season(eng, forcing, params, ic, monkeypatch, False)
+    packed, _, info = _host_season(eng, forcing, params, ic, monkeypatch, True, NESOSIM_DRAIN_HEAD="1", NESOSIM_HOST_CHUNK_MB="0.5")
+    assert info[0] is True and info[1] >= 2, info
+    for name in plain:
+        assert np.array_equal(packed[name].view(np.uint64), plain[name].view(np.uint64)), name
+    eng.close()
+
+
+def test_host_path_compacted_drain_of_selected_arrays(cuda, monkeypatch):
+    """Only some arrays requested (with and without the member-independent snowAcc), one member (nothing to share)."""
+    from nesosim_b200.engine import SnowBudgetEngine
+    mask = S.region_mask(dx=100000)
+    T = 9
+    forcing = S.make_season(mask, T, seed=47)
+    ic = S.make_ic(mask, seed=47)
+    for M in (1, 4):
+        params = S.ensemble_params(M, seed=47)
+        eng = SnowBudgetEngine(mask, T, 100000, n_members=M, atmlossInc=1)
+        for names in (("snowDepths",), ("density", "snowAcc", "snowLead"), ("snowOcean",)):
+            plain, _, _ = _host_season(eng, forcing, params, ic, monkeypatch, False, names=names)
+            packed, _, info = _host_season(eng, forcing, params, ic, monkeypatch, True, names=names)
+            assert info[0] is (names != ("snowOcean",)), (names, info)
+            for name in names:
+                assert np.array_equal(packed[name].view(np.uint64), plain[name].view(np.uint64)), (name, names, M)
+        eng.close()
 
 
 @pytest.mark.parametrize("cluster,rows,land_cols", [("5", "18,36,54,72", 3), ("6", "16,30,44,60,76", 55),
