@@ -123,7 +123,11 @@ int nesosim_step_day(nesosim_ctx *ctx, int x, const double *conc_dev, const doub
  * Members are processed in batches so that device and pinned staging memory stay bounded; bytes moved are
  * reported through h2d_bytes / d2h_bytes when non-NULL.  snowAcc and snowOcean do not depend on the member (forcing
  * only, NESOSIM.py:263-270): with one shared forcing a single copy crosses the link and host threads replicate it into
- * every member's slot of the caller's arrays. */
+ * every member's slot of the caller's arrays.  When the process has at least 12 host threads to itself
+ * (NESOSIM_HOST_THREADS; default: cores / visible GPUs) and at most 60 % of the grid is ocean, the other ten arrays are
+ * drained in packed form -- ocean cells, plus the land cells of the first three time slots -- and scattered into the
+ * caller's arrays by those threads (NESOSIM_HOST_COMPACT=0/1 overrides); the arrays are the same either way
+ * (nesosim_host_drain_info). */
 int nesosim_run_season_host(nesosim_ctx *ctx, const double *precip, const double *conc, const double *wind,
                             const double *drift, const double *rho_clim,
                             const nesosim_member_params *params, const double *ic, int ic_per_member,
@@ -237,7 +241,7 @@ int64_t nesosim_rerun_count(const nesosim_ctx *ctx);
 
 /* How the last nesosim_run_season_host drained its results: *compacted = 1 if only the ocean cells (and the land cells
  * of the first three time slots) of the member-dependent arrays crossed the link and host threads scattered them into
- * the caller's arrays; *full_chunks = chunks of members (since creation) for which that was given up because their land
+ * the caller's arrays; *full_chunks = (member, array) blocks (since creation) for which that was given up because their land
  * cells were not constant in time, and which were copied in full instead.  The caller's arrays are the same either way
  * (the reference's genEmptyArrays contract, NESOSIM.py:350-376). */
 int nesosim_host_drain_info(const nesosim_ctx *ctx, int *compacted, int64_t *full_chunks);
