@@ -501,6 +501,10 @@ def run_e2e(args, eng, forcing, params, ic, rank, world, cells_per_step, barrier
     # host threads of this rank: its share of the cores (the library's own default assumes a rank per visible GPU)
     threads = max(1, min(32, (os.cpu_count() or 1) // world))
     os.environ.setdefault("NESOSIM_HOST_THREADS", str(threads))
+    # the compacted drain trades link bytes for host memory traffic, and the host's memory system is shared by the ranks
+    # of a box: measured better for a single rank (325-345 against 425-455 ms), worse for two (502 against 424 ms), even
+    # for eight (2202 against 2168 ms) -- profiles/r02_e2e_compacted_drain.jsonl
+    os.environ.setdefault("NESOSIM_HOST_COMPACT", "1" if (world == 1 and threads >= 8) else "0")
     names = list(__import__("nesosim_b200._lib", fromlist=["x"]).OUTPUT_NAMES)
     need = 12 * M * T * ny * nx * 8
     avail = None

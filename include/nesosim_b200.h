@@ -123,7 +123,7 @@ int nesosim_step_day(nesosim_ctx *ctx, int x, const double *conc_dev, const doub
  * Members are processed in batches so that device and pinned staging memory stay bounded; bytes moved are
  * reported through h2d_bytes / d2h_bytes when non-NULL.  snowAcc and snowOcean do not depend on the member (forcing
  * only, NESOSIM.py:263-270): with one shared forcing a single copy crosses the link and host threads replicate it into
- * every member's slot of the caller's arrays.  When the process has at least 12 host threads to itself
+ * every member's slot of the caller's arrays.  When the process has at least 16 host threads to itself
  * (NESOSIM_HOST_THREADS; default: cores / visible GPUs) and at most 60 % of the grid is ocean, the other ten arrays are
  * drained in packed form -- ocean cells, plus the land cells of the first three time slots -- and scattered into the
  * caller's arrays by those threads (NESOSIM_HOST_COMPACT=0/1 overrides); the arrays are the same either way

@@ -224,10 +224,12 @@ extern "C" int nesosim_run_season_host(nesosim_ctx *ctx, const double *precip, c
     // Measured (128 members x 260 days per GPU, 21.6 GB of arrays; tools/e2e_variants.py, tools/e2e_multi_gpu.py;
     // profiles/r02_e2e_compacted_drain.jsonl).  One rank on a 16-core box: plain drain 425-455 ms (the link: 54 GB/s);
     // compacted 1186 ms with 2 host threads, 665 with 4, 372 with 8, 325 with 12 or 16 -- then the host's memory system
-    // binds (the scatter writes 26 GB, and the ring is written and read once more).  Eight ranks on a 32-core box: plain
-    // 2168 ms, compacted 2202 ms with 4 or 8 threads per rank -- the box's memory system is shared, and it already
-    // bounds the plain drain there (11.5 GB/s per GPU).  So: compacted only where a rank has a dozen threads to itself.
-    bool compact = n_carr > 0 && T > DRAIN_HEAD && plane < (1ll << 31) && nthreads >= 12 && (double)hp->n_ocean <= 0.6 * (double)plane;
+    // binds (the scatter writes 26 GB, and the ring is written and read once more).  That memory system is shared by the
+    // ranks of a box: two ranks on a 24-core box 502 ms compacted against 424 ms plain, eight ranks on a 32-core box
+    // 2202 against 2168 ms (where it already bounds the plain drain: 11.5 GB/s per GPU).  So the compacted drain is for a
+    // rank that has the box to itself: by default only with 16 host threads (cores / visible GPUs); a caller who knows
+    // better says so (bench.py: NESOSIM_HOST_COMPACT=1 when it runs a single rank, 0 otherwise).
+    bool compact = n_carr > 0 && T > DRAIN_HEAD && plane < (1ll << 31) && nthreads >= 16 && (double)hp->n_ocean <= 0.6 * (double)plane;
     if (const char *e = getenv("NESOSIM_HOST_COMPACT")) compact = n_carr > 0 && plane < (1ll << 31) && atoi(e) != 0;
     int head = (int)std::min<long long>(DRAIN_HEAD, T);
     // (tests only: fewer head slots than the model needs, so that the land-cell check trips and the chunk is copied in full)
