@@ -502,10 +502,10 @@ def run_e2e(args, eng, forcing, params, ic, rank, world, cells_per_step, barrier
     threads = max(1, min(32, (os.cpu_count() or 1) // world))
     os.environ.setdefault("NESOSIM_HOST_THREADS", str(threads))
     # the compacted drain trades link bytes for host memory traffic, and the host's memory system is shared by the ranks
-    # of a box: measured better for a single rank (325-345 against 425-455 ms), worse for two (502 against 424 ms), even
-    # for eight (2202 against 2168 ms) -- profiles/r02_e2e_compacted_drain.jsonl
-    os.environ.setdefault("NESOSIM_HOST_COMPACT", "1" if (world == 1 and threads >= 8) else "0")
-    names = list(__import__("nesosim_b200._lib", fromlist=["x"]).OUTPUT_NAMES)
+    # of a box.  Measured (profiles/r02_e2e_compacted_drain.jsonl): one rank 330-345 ms against 425-455 ms plain; two
+    # ranks 402-420 against 418 ms (the hybrid split keeps it from falling behind, but there is nothing to gain); eight
+    # ranks 2202 (all packed) against 2168 ms.  So a single rank takes it, several ranks stay on the plain drain.
+    os.environ.setdefault("NESOSIM_HOST_COMPACT", "1" if (world == 1 and threads >= 4) else "0")
     need = 12 * M * T * ny * nx * 8
     avail = None
     try:
@@ -539,13 +539,15 @@ def run_e2e(args, eng, forcing, params, ic, rank, world, cells_per_step, barrier
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
     compacted, full_chunks = eng.host_drain_info()
+    blocks_packed, blocks_plain = eng.host_drain_blocks()
     res = {"value": world * cells_per_step * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(up),
            "d2h_bytes_per_step": int(down), "steps": steps, "ms_per_step": 1e3 * dt / steps, "outputs": note,
            "host_array_bytes_per_step": int(sum(v.numel() * 8 for v in host_out.values())),
-           "drain": ("compacted: ocean cells of the ten member-dependent arrays + the land cells of the first three time slots "
+           "drain": ("compacted: ocean cells of the nine member-dependent arrays + the land cells of the first three time slots "
                      "cross the link, %s host threads scatter them into the caller's arrays" % os.environ["NESOSIM_HOST_THREADS"])
            if compacted else "full: every byte of the arrays crosses the link",
-           "host_threads": int(os.environ["NESOSIM_HOST_THREADS"]), "chunks_copied_in_full": full_chunks}
+           "host_threads": int(os.environ["NESOSIM_HOST_THREADS"]), "chunks_copied_in_full": full_chunks,
+           "blocks_packed": blocks_packed, "blocks_copied_whole_by_the_link": blocks_plain}
     if dev_out is not None:       # the caller's arrays against the device-resident season of the headline run
         same = True
         for n in host_out:

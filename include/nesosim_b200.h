@@ -123,8 +123,8 @@ int nesosim_step_day(nesosim_ctx *ctx, int x, const double *conc_dev, const doub
  * Members are processed in batches so that device and pinned staging memory stay bounded; bytes moved are
  * reported through h2d_bytes / d2h_bytes when non-NULL.  snowAcc and snowOcean do not depend on the member (forcing
  * only, NESOSIM.py:263-270): with one shared forcing a single copy crosses the link and host threads replicate it into
- * every member's slot of the caller's arrays.  When the process has at least 16 host threads to itself
- * (NESOSIM_HOST_THREADS; default: cores / visible GPUs) and at most 60 % of the grid is ocean, the other ten arrays are
+ * every member's slot of the caller's arrays.  When the process has at least 6 host threads to itself
+ * (NESOSIM_HOST_THREADS; default: cores / visible GPUs) and at most 60 % of the grid is ocean, the other nine arrays are
  * drained in packed form -- ocean cells, plus the land cells of the first three time slots -- and scattered into the
  * caller's arrays by those threads (NESOSIM_HOST_COMPACT=0/1 overrides); the arrays are the same either way
  * (nesosim_host_drain_info). */
@@ -245,6 +245,12 @@ int64_t nesosim_rerun_count(const nesosim_ctx *ctx);
  * cells were not constant in time, and which were copied in full instead.  The caller's arrays are the same either way
  * (the reference's genEmptyArrays contract, NESOSIM.py:350-376). */
 int nesosim_host_drain_info(const nesosim_ctx *ctx, int *compacted, int64_t *full_chunks);
+
+/* The compacted drain shares the work between the host threads and the copy engine as it goes: whenever every slot of
+ * the pinned ring is taken (the threads are the bottleneck), the link copies whole (member, array) blocks of the same
+ * batch straight into the caller's arrays instead.  *packed / *plain = the blocks of the last call that went either
+ * way (both 0 after a plain drain). */
+int nesosim_host_drain_blocks(const nesosim_ctx *ctx, int64_t *packed, int64_t *plain);
 
 /* Host half of that drain, on its own: one member's packed block of one array -- [planes_per_slot*num_days][n_ocean]
  * ocean values (cells with mask 1..10, ascending), then [planes_per_slot*min(3,num_days)][n_land] land values of the

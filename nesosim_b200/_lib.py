@@ -74,6 +74,7 @@ _SIGNATURES = {
     "nesosim_launch_count": (C.c_int64, [C.c_void_p]),
     "nesosim_rerun_count": (C.c_int64, [C.c_void_p]),
     "nesosim_unpack_member_array": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "nesosim_host_drain_blocks": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "nesosim_host_drain_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
     "nesosim_season_kernel_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "nesosim_strip_setup": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),

@@ -9,7 +9,7 @@
 // PCIe, and host threads replicate it into the other members' slots while the remaining arrays are still draining
 // (2 of the 12 arrays per member: 16 % fewer bytes on the link that bounds this call).
 //
-// Compacted drain (drain_kernels.cuh; NESOSIM_HOST_COMPACT=0/1 overrides the choice): of the ten member-dependent arrays
+// Compacted drain (drain_kernels.cuh; NESOSIM_HOST_COMPACT=0/1 overrides the choice): of the nine member-dependent arrays
 // only the ocean cells (43 % of the polar grid) and the land cells of the first three time slots cross the link, in
 // chunks of a few members that land in a ring of pinned slots; a pool of host threads scatters every chunk into the
 // caller's arrays -- plane by plane through a cache-resident scratch plane and out with streaming stores -- while the
@@ -223,13 +223,14 @@ extern "C" int nesosim_run_season_host(nesosim_ctx *ctx, const double *precip, c
         if (harr[v] && v != 2 && v != 3) carr[n_carr++] = v;
     // Measured (128 members x 260 days per GPU, 21.6 GB of arrays; tools/e2e_variants.py, tools/e2e_multi_gpu.py;
     // profiles/r02_e2e_compacted_drain.jsonl).  One rank on a 16-core box: plain drain 425-455 ms (the link: 54 GB/s);
-    // compacted 1186 ms with 2 host threads, 665 with 4, 372 with 8, 325 with 12 or 16 -- then the host's memory system
-    // binds (the scatter writes 26 GB, and the ring is written and read once more).  That memory system is shared by the
-    // ranks of a box: two ranks on a 24-core box 502 ms compacted against 424 ms plain, eight ranks on a 32-core box
-    // 2202 against 2168 ms (where it already bounds the plain drain: 11.5 GB/s per GPU).  So the compacted drain is for a
-    // rank that has the box to itself: by default only with 16 host threads (cores / visible GPUs); a caller who knows
-    // better says so (bench.py: NESOSIM_HOST_COMPACT=1 when it runs a single rank, 0 otherwise).
-    bool compact = n_carr > 0 && T > DRAIN_HEAD && plane < (1ll << 31) && nthreads >= 16 && (double)hp->n_ocean <= 0.6 * (double)plane;
+    // every block packed: 1186 ms with 2 host threads, 665 with 4, 372 with 8, 325-336 with 12 or 16 -- then the host's
+    // memory system binds (the scatter writes 26 GB, and the ring is written and read once more); hybrid (below): 408-452
+    // with 2 threads, 356 with 4, 334-353 with 8, 330 with 16 -- never behind the plain drain.  That memory system is
+    // shared by the ranks of a box: two ranks on a 24-core box 418 ms plain, 502 all packed, 420 hybrid with 12 threads
+    // each, 402 with 6; eight ranks on a 32-core box 2168 ms plain, 2202 all packed (hybrid not measured there).
+    // So: the compacted (hybrid) drain from 6 host threads per rank on -- cores / visible GPUs by default, which keeps
+    // the 8-GPU box on the plain drain it was measured with.
+    bool compact = n_carr > 0 && T > DRAIN_HEAD && plane < (1ll << 31) && nthreads >= 6 && (double)hp->n_ocean <= 0.6 * (double)plane;
     if (const char *e = getenv("NESOSIM_HOST_COMPACT")) compact = n_carr > 0 && plane < (1ll << 31) && atoi(e) != 0;
     int head = (int)std::min<long long>(DRAIN_HEAD, T);
     // (tests only: fewer head slots than the model needs, so that the land-cell check trips and the chunk is copied in full)
@@ -287,27 +288,24 @@ extern "C" int nesosim_run_season_host(nesosim_ctx *ctx, const double *precip, c
         int t0, t1;             // blocks [t0, t1) of the batch; block t = member-in-batch * n_carr + array
         long long off, elems;   // inside the batch's packed buffer
     };
-    std::vector<Chunk> chunks;
-    std::vector<int> batch_last_chunk(n_batches, -1);
+    std::vector<Chunk> chunks;             // formed as the drain proceeds (see the pipeline below)
     long long max_chunk_elems = 0;
-    int max_chunk_blocks = 0;
+    int max_chunk_blocks = 0, total_blocks = 0;
     auto block_elems = [&](int i) { return (i + 1 < n_carr ? rec_off[i + 1] : rec_elems) - rec_off[i]; };
+    // hybrid drain: while the host threads are the bottleneck (every ring slot taken), the copy engine moves whole
+    // (member, array) blocks of the same batch straight into the caller's arrays, from the far end of the batch
+    bool hybrid = compact;
+    if (const char *e = getenv("NESOSIM_HOST_HYBRID")) hybrid = compact && atoi(e) != 0;
     if (compact) {
-        for (int nb = 0; nb < n_batches; ++nb) {
-            const int cnt = std::min(batch, M - nb * batch), nblk = cnt * n_carr;
-            for (int t = 0; t < nblk;) {
-                Chunk c{nb, t, t, (long long)(t / n_carr) * rec_elems + rec_off[t % n_carr], 0};
-                do {
-                    c.elems += block_elems(c.t1 % n_carr);
-                    ++c.t1;
-                } while (c.t1 < nblk && (c.elems + block_elems(c.t1 % n_carr)) * 8 <= chunk_target);
-                t = c.t1;
-                max_chunk_elems = std::max(max_chunk_elems, c.elems);
-                max_chunk_blocks = std::max(max_chunk_blocks, c.t1 - c.t0);
-                chunks.push_back(c);
-            }
-            batch_last_chunk[nb] = (int)chunks.size() - 1;
+        long long min_blk = block_elems(0), max_blk = block_elems(0);
+        for (int i = 1; i < n_carr; ++i) {
+            min_blk = std::min(min_blk, block_elems(i));
+            max_blk = std::max(max_blk, block_elems(i));
         }
+        max_chunk_elems = std::max(max_blk, chunk_target / 8);
+        max_chunk_blocks = (int)std::min<long long>((long long)batch * n_carr, chunk_target / 8 / std::max<long long>(1, min_blk) + 1);
+        total_blocks = M * n_carr;
+        chunks.reserve((size_t)total_blocks);
         if (!hp->cells_dev) {
             CU(cudaMalloc(&hp->cells_dev, (size_t)plane * sizeof(int)));
             CU(cudaMemcpy(hp->cells_dev, hp->ocean_idx.data(), (size_t)hp->n_ocean * sizeof(int), cudaMemcpyHostToDevice));
@@ -351,7 +349,7 @@ extern "C" int nesosim_run_season_host(nesosim_ctx *ctx, const double *precip, c
     // progress of the scatter, one counter per chunk of the call (guarded by prog_mu); declared before the pool, whose
     // destructor runs the queue dry
     std::mutex prog_mu;
-    std::vector<int> pending(chunks.size() + 1, 0);
+    std::vector<int> pending((size_t)total_blocks + 1, 0);   // (a chunk holds at least one block)
     DrainPool pool;
     const bool need_pool = compact || (share && (harr[2] || harr[3]));
     if (need_pool) pool.start(nthreads, compact ? (size_t)plane : 1);
@@ -466,57 +464,108 @@ extern "C" int nesosim_run_season_host(nesosim_ctx *ctx, const double *precip, c
             CU(cudaEventRecord(hp->drained[b], hp->copy));
         }
     } else {
-        // ---- compacted drain: one pipeline over all the chunks of the call.  The main thread launches batches as their
-        // buffers come free, keeps up to RING chunk copies queued on the link and hands every arrived chunk to the pool.
-        const int NC = (int)chunks.size();
-        int launched = 0, issued = 0, taken = 0;
-        bool plain_copies = false;      // copies out of a batch's full arrays are queued on the copy stream
+        // ---- compacted drain: one pipeline over all the blocks of the call.  The main thread launches batches as their
+        // buffers come free, keeps up to RING chunk copies queued on the link, hands every arrived chunk to the pool,
+        // and -- hybrid -- gives the link whole blocks to copy whenever the ring is full.
+        struct BatchDrain {
+            int lo = 0, hi = 0;         // blocks [lo, hi) not yet issued: packed chunks take from lo, plain copies from hi
+            int last_chunk = -1;        // index of the batch's last chunk (or of the last chunk before it)
+            int plain_out = 0;          // plain copies of the batch that have not completed
+            bool issued = false;
+        };
+        std::vector<BatchDrain> bd(n_batches);
+        constexpr int PLAIN_MAX = 2;
+        cudaEvent_t plain_ev[PLAIN_MAX];
+        int plain_nb[PLAIN_MAX], plain_n = 0, plain_head = 0;      // FIFO of plain copies in flight
+        for (int i = 0; i < PLAIN_MAX; ++i) {
+            while ((int)hp->arrived.size() < RING + PLAIN_MAX) {
+                cudaEvent_t ev;
+                CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                hp->arrived.push_back(ev);
+            }
+            plain_ev[i] = hp->arrived[RING + i];
+        }
+        int launched = 0, cur = 0, taken = 0;
+        long long n_plain = 0, n_packed = 0;
         auto slot_free = [&](int ch) {  // has the chunk that used this ring slot before been scattered?
             if (ch < RING) return true;
             std::lock_guard<std::mutex> lk(prog_mu);
             return pending[ch - RING] == 0;
         };
-        while (taken < NC) {
+        auto batch_drained = [&](int nb) {   // every copy out of the batch's device buffers has completed
+            return bd[nb].issued && taken > bd[nb].last_chunk && bd[nb].plain_out == 0;
+        };
+        while (cur < n_batches || taken < (int)chunks.size() || plain_n > 0) {
             bool progress = false;
-            // a batch may start when every packed chunk of the batch two before it has reached the host
-            if (launched < n_batches && (launched < 2 || taken > batch_last_chunk[launched - 2])) {
-                if (launched >= 2 && plain_copies) {
-                    CU(cudaStreamSynchronize(hp->copy));
-                    plain_copies = false;
-                }
+            if (launched < n_batches && (launched < 2 || batch_drained(launched - 2))) {
                 if ((rc = launch(launched))) return rc;
                 const BatchView &bv = views[launched];
+                bd[launched].hi = bv.cnt * n_carr;
                 CU(cudaStreamWaitEvent(hp->copy, hp->done[launched & 1], 0));
                 if (launched == 0 && share && (harr[2] || harr[3]) && (rc = drain_shared(bv))) return rc;
                 if (!share)
                     for (int v = 2; v <= 3; ++v)
-                        if (harr[v]) {
+                        if (harr[v]) {      // not shared: every member's copy crosses the link; tracked like a plain block copy
                             if ((rc = copy_full(bv, v, 0, bv.cnt))) return rc;
-                            plain_copies = true;
                         }
                 ++launched;
                 progress = true;
             }
-            while (issued < NC && chunks[issued].nb < launched && issued < taken + RING && slot_free(issued)) {
-                const Chunk &c = chunks[issued];
-                char *slot = (char *)hp->ring + (size_t)(issued % RING) * slot_bytes;
-                const int b = c.nb & 1;
-                CU(cudaMemcpyAsync(slot, hp->packed[b] + c.off, (size_t)c.elems * 8, cudaMemcpyDeviceToHost, hp->copy));
-                CU(cudaMemcpyAsync(slot + (size_t)max_chunk_elems * 8, hp->chunk_flags + (size_t)b * batch * n_carr + c.t0,
-                                   (size_t)(c.t1 - c.t0) * 8, cudaMemcpyDeviceToHost, hp->copy));
-                CU(cudaEventRecord(hp->arrived[issued % RING], hp->copy));
-                down += (int64_t)c.elems * 8 + (c.t1 - c.t0) * 8;
-                ++issued;
-                progress = true;
+            if (cur < launched) {
+                BatchDrain &d = bd[cur];
+                const BatchView &bv = views[cur];
+                const int b = cur & 1, issued = (int)chunks.size();
+                if (d.lo == d.hi) {
+                    d.issued = true;
+                    d.last_chunk = issued - 1;
+                    ++cur;
+                    progress = true;
+                } else if (issued < taken + RING && slot_free(issued)) {
+                    Chunk c{cur, d.lo, d.lo, (long long)(d.lo / n_carr) * rec_elems + rec_off[d.lo % n_carr], 0};
+                    do {
+                        c.elems += block_elems(c.t1 % n_carr);
+                        ++c.t1;
+                    } while (c.t1 < d.hi && (c.elems + block_elems(c.t1 % n_carr)) * 8 <= chunk_target && c.t1 - c.t0 < max_chunk_blocks);
+                    d.lo = c.t1;
+                    char *slot = (char *)hp->ring + (size_t)(issued % RING) * slot_bytes;
+                    CU(cudaMemcpyAsync(slot, hp->packed[b] + c.off, (size_t)c.elems * 8, cudaMemcpyDeviceToHost, hp->copy));
+                    CU(cudaMemcpyAsync(slot + (size_t)max_chunk_elems * 8, hp->chunk_flags + (size_t)b * batch * n_carr + c.t0,
+                                       (size_t)(c.t1 - c.t0) * 8, cudaMemcpyDeviceToHost, hp->copy));
+                    CU(cudaEventRecord(hp->arrived[issued % RING], hp->copy));
+                    down += (int64_t)c.elems * 8 + (c.t1 - c.t0) * 8;
+                    n_packed += c.t1 - c.t0;
+                    chunks.push_back(c);
+                    progress = true;
+                } else if (hybrid && plain_n < PLAIN_MAX) {
+                    const int t = --d.hi, slot_i = (plain_head + plain_n) % PLAIN_MAX;
+                    if ((rc = copy_full(bv, carr[t % n_carr], t / n_carr, 1))) return rc;
+                    CU(cudaEventRecord(plain_ev[slot_i], hp->copy));
+                    plain_nb[slot_i] = cur;
+                    ++plain_n;
+                    ++d.plain_out;
+                    ++n_plain;
+                    progress = true;
+                }
+            }
+            if (plain_n > 0) {
+                const cudaError_t q_ = cudaEventQuery(plain_ev[plain_head]);
+                if (q_ == cudaSuccess) {
+                    --bd[plain_nb[plain_head]].plain_out;
+                    plain_head = (plain_head + 1) % PLAIN_MAX;
+                    --plain_n;
+                    progress = true;
+                } else if (q_ != cudaErrorNotReady) {
+                    return cuda_fail(q_, "device->host copy of a block");
+                }
             }
             if (share && !replication_queued && cudaEventQuery(hp->shared_ready) == cudaSuccess) {
                 queue_replication();
                 progress = true;
             }
-            if (taken < issued) {
+            if (taken < (int)chunks.size()) {
                 const cudaError_t q_ = cudaEventQuery(hp->arrived[taken % RING]);
                 if (q_ == cudaSuccess) {
-                    const Chunk &c = chunks[taken];
+                    const Chunk c = chunks[taken];
                     const BatchView &bv = views[c.nb];
                     const char *slot = (const char *)hp->ring + (size_t)(taken % RING) * slot_bytes;
                     const unsigned long long *bad = (const unsigned long long *)(slot + (size_t)max_chunk_elems * 8);
@@ -533,7 +582,8 @@ extern "C" int nesosim_run_season_host(nesosim_ctx *ctx, const double *precip, c
                         boff += block_elems(i);
                         if (bad[t - c.t0]) {     // land cells not constant: the plain copy of this member's array
                             if ((rc = copy_full(bv, v, ml, 1))) return rc;
-                            plain_copies = true;
+                            // (rare path: waited for on the spot, the batch's buffers are reused two batches on)
+                            CU(cudaStreamSynchronize(hp->copy));
                             ctx->hp_full_chunks++;
                             continue;
                         }
@@ -557,6 +607,8 @@ extern "C" int nesosim_run_season_host(nesosim_ctx *ctx, const double *precip, c
             }
             if (!progress) std::this_thread::sleep_for(std::chrono::microseconds(10));
         }
+        ctx->hp_blocks_packed = n_packed;
+        ctx->hp_blocks_plain = n_plain;
     }
     if (share && (harr[2] || harr[3])) {
         CU(cudaEventSynchronize(hp->shared_ready));

@@ -215,7 +215,8 @@ struct nesosim_ctx {
     int path = 0;                   // 0 auto, 1 general per-day launches, 2 season-resident ensemble kernel
     int last_path = 0;              // which path the last run_season used (1 or 2)
     int hp_last_compact = 0;        // nesosim_run_season_host: did the last call use the compacted drain?
-    long long hp_full_chunks = 0;   // chunks of a compacted drain that had to be copied in full (land cells not constant)
+    long long hp_full_chunks = 0;   // blocks of a compacted drain that had to be copied in full (land cells not constant)
+    long long hp_blocks_packed = 0, hp_blocks_plain = 0;   // last compacted drain: (member, array) blocks sent packed / copied whole
     // row-strip domain decomposition over peer memory (nesosim_strip_*; StripLink in day_kernels.cuh)
     struct {
         bool on = false;
@@ -1464,6 +1465,13 @@ int nesosim_host_drain_info(const nesosim_ctx *ctx, int *compacted, int64_t *ful
     if (!ctx) return fail(NESOSIM_ERR_ARG, "NULL context");
     if (compacted) *compacted = ctx->hp_last_compact;
     if (full_chunks) *full_chunks = ctx->hp_full_chunks;
+    return NESOSIM_OK;
+}
+
+int nesosim_host_drain_blocks(const nesosim_ctx *ctx, int64_t *packed, int64_t *plain) {
+    if (!ctx) return fail(NESOSIM_ERR_ARG, "NULL context");
+    if (packed) *packed = ctx->hp_last_compact ? ctx->hp_blocks_packed : 0;
+    if (plain) *plain = ctx->hp_last_compact ? ctx->hp_blocks_plain : 0;
     return NESOSIM_OK;
 }
 int nesosim_season_kernel_time(const nesosim_ctx *ctx, double *total_ms, int64_t *launches) {

@@ -202,6 +202,13 @@ class SnowBudgetEngine:
         _lib.check(self.lib.nesosim_host_drain_info(self.handle, C.byref(c), C.byref(n)))
         return bool(c.value), int(n.value)
 
+    def host_drain_blocks(self):
+        """(packed, plain): the (member, array) blocks of the last `run_season_host` that crossed the link packed (ocean
+        cells, scattered by host threads) and whole (copy engine, straight into the caller's arrays)."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        _lib.check(self.lib.nesosim_host_drain_blocks(self.handle, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def season_kernel_time(self):
         """(total device ms, launches) of the season-resident kernel so far."""
         ms, n = C.c_double(0), C.c_int64(0)

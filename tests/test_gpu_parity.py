@@ -541,7 +541,8 @@ def test_host_path_regrows_its_staging_when_more_outputs_are_asked_for(cuda, mon
 
 def _host_season(eng, forcing, params, ic, monkeypatch, compact, names=None, **env):
     monkeypatch.setenv("NESOSIM_HOST_COMPACT", "1" if compact else "0")
-    for k in ("NESOSIM_HOST_BATCH_GB", "NESOSIM_HOST_CHUNK_MB", "NESOSIM_DRAIN_HEAD", "NESOSIM_HOST_THREADS"):
+    for k in ("NESOSIM_HOST_BATCH_GB", "NESOSIM_HOST_CHUNK_MB", "NESOSIM_DRAIN_HEAD", "NESOSIM_HOST_THREADS", "NESOSIM_HOST_HYBRID",
+              "NESOSIM_HOST_RING"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -577,14 +578,22 @@ def test_host_path_compacted_drain_matches_the_plain_one_bit_for_bit(cuda, monke
     ref0 = O.run_season(forcing, ic, mask, 100000, oracle_params(params[0]), O.Flags(atmlossInc=1))
     for name in plain:
         assert_parity(plain[name][0], ref0[name], name)
-    for env in ({}, {"NESOSIM_HOST_BATCH_GB": "0.03"}, {"NESOSIM_HOST_CHUNK_MB": "1.5"},
-                {"NESOSIM_HOST_CHUNK_MB": "0.1", "NESOSIM_HOST_THREADS": "3"},
-                {"NESOSIM_HOST_BATCH_GB": "0.05", "NESOSIM_HOST_CHUNK_MB": "0.1", "NESOSIM_HOST_THREADS": "1"}):
+    seen_plain = 0
+    for env in ({"NESOSIM_HOST_HYBRID": "0"}, {"NESOSIM_HOST_BATCH_GB": "0.03", "NESOSIM_HOST_HYBRID": "0"},
+                {"NESOSIM_HOST_CHUNK_MB": "1.5"}, {"NESOSIM_HOST_CHUNK_MB": "0.1", "NESOSIM_HOST_THREADS": "3"},
+                {"NESOSIM_HOST_BATCH_GB": "0.05", "NESOSIM_HOST_CHUNK_MB": "0.1", "NESOSIM_HOST_THREADS": "1", "NESOSIM_HOST_RING": "2"},
+                {"NESOSIM_HOST_BATCH_GB": "0.03", "NESOSIM_HOST_CHUNK_MB": "0.1", "NESOSIM_HOST_THREADS": "1", "NESOSIM_HOST_RING": "2"}):
         packed, down, info = _host_season(eng, forcing, params, ic, monkeypatch, True, **env)
         assert info == (True, 0), (env, info)
-        assert down < 0.62 * down_plain, (env, down, down_plain)
+        n_packed, n_plain = eng.host_drain_blocks()
+        assert n_packed + n_plain == 9 * M, (env, n_packed, n_plain)
+        if env.get("NESOSIM_HOST_HYBRID") == "0":       # every block packed: well under half of the bytes on the link
+            assert n_plain == 0 and down < 0.62 * down_plain, (env, down, down_plain, n_plain)
+        seen_plain += n_plain
         for name in plain:
             assert np.array_equal(packed[name].view(np.uint64), plain[name].view(np.uint64)), (name, env)
+    # with one slow host thread and a ring of two small slots the link must have taken whole blocks at some point
+    assert seen_plain > 0
     eng.close()
 
 

@@ -55,7 +55,7 @@ del d, h
 
 variants = os.environ.get("VARIANTS", "NESOSIM_HOST_COMPACT=0,NESOSIM_HOST_THREADS=@T;NESOSIM_HOST_COMPACT=1,NESOSIM_HOST_THREADS=@T;"
                           "NESOSIM_HOST_COMPACT=1,NESOSIM_HOST_THREADS=@T2").split(";")
-KEYS = ("NESOSIM_HOST_NO_SHARE", "NESOSIM_HOST_THREADS", "NESOSIM_HOST_BATCH_GB", "NESOSIM_HOST_COMPACT", "NESOSIM_HOST_CHUNK_MB", "NESOSIM_HOST_RING")
+KEYS = ("NESOSIM_HOST_NO_SHARE", "NESOSIM_HOST_THREADS", "NESOSIM_HOST_BATCH_GB", "NESOSIM_HOST_COMPACT", "NESOSIM_HOST_HYBRID", "NESOSIM_HOST_CHUNK_MB", "NESOSIM_HOST_RING")
 eng = SnowBudgetEngine(mask, T, DX, n_members=M, atmlossInc=1, device=local)
 ref = None
 for v in variants:
@@ -74,6 +74,7 @@ for v in variants:
         barrier()
         ts.append(max_over_ranks(time.perf_counter() - t0))
     info = eng.host_drain_info()
+    blocks = eng.host_drain_blocks()
     # same arrays whatever the drain: a digest of this rank's result against the first variant's
     dig = [float(host_out[n][[0, M // 2, M - 1]].nan_to_num(nan=-7.0).sum()) for n in ("snowDepths", "density", "snowLead", "snowAcc")]
     if ref is None:
@@ -81,7 +82,7 @@ for v in variants:
     same = max_over_ranks(0.0 if dig == ref else 1.0) == 0.0
     if rank == 0:
         ms = 1e3 * min(ts)
-        print(json.dumps({"gpus": world, "host_cores": cores, "variant": v, "drain": "compacted" if info[0] else "full",
+        print(json.dumps({"gpus": world, "host_cores": cores, "variant": v, "drain": "compacted" if info[0] else "full", "blocks_packed": blocks[0], "blocks_plain": blocks[1],
                           "ms_all": [round(1e3 * t, 1) for t in ts], "ms_per_season": ms, "d2h_GB_per_gpu": down / 1e9,
                           "link_GBs_per_gpu": link, "same_digest_as_first": same,
                           "cell_days_per_s": world * M * ny * nx * (T - 1) / (ms * 1e-3)}), flush=True)

@@ -28,7 +28,7 @@ link = 4 * (1 << 30) / (time.perf_counter() - t0) / 1e9
 del d, h
 variants = os.environ.get("VARIANTS", ";NESOSIM_HOST_NO_SHARE=1;NESOSIM_HOST_THREADS=2;NESOSIM_HOST_THREADS=4;NESOSIM_HOST_THREADS=16;"
                           "NESOSIM_HOST_BATCH_GB=2;NESOSIM_HOST_BATCH_GB=16;NESOSIM_HOST_BATCH_GB=2,NESOSIM_HOST_THREADS=4").split(";")
-KEYS = ("NESOSIM_HOST_NO_SHARE", "NESOSIM_HOST_THREADS", "NESOSIM_HOST_BATCH_GB", "NESOSIM_HOST_COMPACT", "NESOSIM_HOST_CHUNK_MB")
+KEYS = ("NESOSIM_HOST_NO_SHARE", "NESOSIM_HOST_THREADS", "NESOSIM_HOST_BATCH_GB", "NESOSIM_HOST_COMPACT", "NESOSIM_HOST_HYBRID", "NESOSIM_HOST_CHUNK_MB")
 for v in variants:
     for k in KEYS:
         os.environ.pop(k, None)
@@ -44,9 +44,10 @@ for v in variants:
         _, up, down = eng.run_season_host(hf, params, ic_h, host_out)
         ts.append(time.perf_counter() - t0)
     info = eng.host_drain_info()
+    blocks = eng.host_drain_blocks()
     eng.close()
     ms = 1e3 * min(ts)
-    print(json.dumps({"variant": v or "default", "drain": "compacted" if info[0] else "full", "chunks_copied_in_full": info[1],
+    print(json.dumps({"variant": v or "default", "drain": "compacted" if info[0] else "full", "blocks_packed": blocks[0], "blocks_plain": blocks[1], "chunks_copied_in_full": info[1],
                       "ms_all": [round(1e3 * t, 1) for t in ts], "host_cores": os.cpu_count(), "ms_per_season": ms, "d2h_GB": down / 1e9, "d2h_GBs": down / 1e9 / (ms * 1e-3),
                       "link_GBs": link, "fraction_of_link": down / 1e9 / (ms * 1e-3) / link,
                       "cell_days_per_s": M * ny * nx * (T - 1) / (ms * 1e-3)}), flush=True)
