@@ -506,6 +506,7 @@ def run_e2e(args, eng, forcing, params, ic, rank, world, cells_per_step, barrier
     # ranks 402-420 against 418 ms (the hybrid split keeps it from falling behind, but there is nothing to gain); eight
     # ranks 2202 (all packed) against 2168 ms.  So a single rank takes it, several ranks stay on the plain drain.
     os.environ.setdefault("NESOSIM_HOST_COMPACT", "1" if (world == 1 and threads >= 4) else "0")
+    names = list(__import__("nesosim_b200._lib", fromlist=["x"]).OUTPUT_NAMES)
     need = 12 * M * T * ny * nx * 8
     avail = None
     try:
