@@ -491,6 +491,17 @@ def run_ours(args):
         sys.exit(3)
 
 
+def host_drain_settings(world, cores):
+    """(host threads of this rank, compacted drain?) for nesosim_run_season_host.  Threads: this rank's share of the
+    cores (the library's own default assumes a rank per visible GPU).  The compacted drain trades link bytes for host
+    memory traffic, and the host's memory system is shared by the ranks of a box.  Measured
+    (profiles/r02_e2e_compacted_drain.jsonl): one rank 330-345 ms against 425-455 ms plain; two ranks 402-420 against
+    418 ms (the hybrid split keeps it from falling behind, but there is nothing to gain); eight ranks 2202 (all packed)
+    against 2168 ms.  So a single rank takes it, several ranks stay on the plain drain."""
+    threads = max(1, min(32, cores // world))
+    return threads, (world == 1 and threads >= 4)
+
+
 def run_e2e(args, eng, forcing, params, ic, rank, world, cells_per_step, barrier, dev_out=None):
     """Season through nesosim_run_season_host: pinned HOST forcing in, all 12 HOST arrays out, every step.  The
     library picks the drain: every byte of the arrays over the link, or -- when this rank has enough host threads --
@@ -498,14 +509,9 @@ def run_e2e(args, eng, forcing, params, ic, rank, world, cells_per_step, barrier
     below against the device-resident result of the headline run)."""
     import torch
     M, T, ny, nx = eng.M, eng.T, eng.ny, eng.nx
-    # host threads of this rank: its share of the cores (the library's own default assumes a rank per visible GPU)
-    threads = max(1, min(32, (os.cpu_count() or 1) // world))
+    threads, compact = host_drain_settings(world, os.cpu_count() or 1)
     os.environ.setdefault("NESOSIM_HOST_THREADS", str(threads))
-    # the compacted drain trades link bytes for host memory traffic, and the host's memory system is shared by the ranks
-    # of a box.  Measured (profiles/r02_e2e_compacted_drain.jsonl): one rank 330-345 ms against 425-455 ms plain; two
-    # ranks 402-420 against 418 ms (the hybrid split keeps it from falling behind, but there is nothing to gain); eight
-    # ranks 2202 (all packed) against 2168 ms.  So a single rank takes it, several ranks stay on the plain drain.
-    os.environ.setdefault("NESOSIM_HOST_COMPACT", "1" if (world == 1 and threads >= 4) else "0")
+    os.environ.setdefault("NESOSIM_HOST_COMPACT", "1" if compact else "0")
     names = list(__import__("nesosim_b200._lib", fromlist=["x"]).OUTPUT_NAMES)
     need = 12 * M * T * ny * nx * 8
     avail = None
@@ -534,11 +540,11 @@ def run_e2e(args, eng, forcing, params, ic, rank, world, cells_per_step, barrier
         _, up, down = eng.run_season_host(hf, params, ic_h, host_out)
     barrier()
     dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         import torch.distributed as dist
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t.item())
+        dt = float(t.item())
     compacted, full_chunks = eng.host_drain_info()
     blocks_packed, blocks_plain = eng.host_drain_blocks()
     res = {"value": world * cells_per_step * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(up),

@@ -86,3 +86,63 @@ def test_multiseason_batch_of_the_bench_matches_baseline_step_count():
         parts = [sharding.season_assignment(bench.MULTI_YEARS, r, world) for r in range(world)]
         assert sorted(y for p in parts for y in p) == bench.MULTI_YEARS
         assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_bench_end_to_end_leg_runs_against_a_stand_in_engine(monkeypatch):
+    """bench.run_e2e (the host-buffer leg of the JSON line) end to end on the CPU with a stand-in engine: the record's
+    keys, the byte counts it reports, the drain mode it asks the library for at one and at several ranks, and the check
+    of the host arrays against the device-resident result."""
+    import types
+    import torch
+    import bench
+
+    real_empty = torch.empty
+    monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{x: y for x, y in k.items() if x != "pin_memory"}))
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    for k in ("NESOSIM_HOST_THREADS", "NESOSIM_HOST_COMPACT"):
+        monkeypatch.delenv(k, raising=False)
+
+    class Engine:
+        M, T, ny, nx = 3, 4, 5, 6
+        calls = 0
+
+        def run_season_host(self, forcing, params, ic, outputs):
+            Engine.calls += 1
+            for i, n in enumerate(sorted(outputs)):
+                outputs[n].fill_(float(i))
+                outputs[n][0, 0].fill_(float("nan"))
+            return outputs, 111, 222
+
+        def host_drain_info(self):
+            return os.environ.get("NESOSIM_HOST_COMPACT") == "1", 0
+
+        def host_drain_blocks(self):
+            return (20, 7) if os.environ.get("NESOSIM_HOST_COMPACT") == "1" else (0, 0)
+
+    eng = Engine()
+    forcing = {k: np.zeros((4, 5, 6)) for k in ("precip", "conc", "wind")}
+    forcing["drift"] = np.zeros((4, 2, 5, 6))
+    args = types.SimpleNamespace(steps=2, e2e_steps=3)
+    monkeypatch.setattr(os, "cpu_count", lambda: 16)
+    rec = bench.run_e2e(args, eng, forcing, None, np.zeros((5, 6)), 0, 1, 1000.0, lambda: None)
+    assert Engine.calls == 3 and rec["steps"] == 2 and rec["value"] > 0 and rec["unit"] == bench.UNIT
+    assert rec["h2d_bytes_per_step"] == 111 and rec["d2h_bytes_per_step"] == 222
+    assert rec["host_array_bytes_per_step"] == 12 * 3 * 4 * 5 * 6 * 8
+    assert rec["drain"].startswith("compacted") and rec["host_threads"] == 16
+    assert rec["blocks_packed"] == 20 and rec["blocks_copied_whole_by_the_link"] == 7
+    assert "host_arrays_identical_to_device_result" not in rec
+    # against a "device" result: equal (NaNs in the same places), then different
+    from nesosim_b200 import _lib
+    dev = {}
+    for i, n in enumerate(sorted(_lib.OUTPUT_NAMES)):
+        dev[n] = torch.full((3, 4, 2, 5, 6) if n == "snowDepths" else (3, 4, 5, 6), float(i), dtype=torch.float64)
+        dev[n][0, 0] = float("nan")
+    rec = bench.run_e2e(args, eng, forcing, None, np.zeros((5, 6)), 0, 1, 1000.0, lambda: None, dev)
+    assert rec["host_arrays_identical_to_device_result"] is True
+    dev["density"][2, 3, 4, 5] += 1.0
+    rec = bench.run_e2e(args, eng, forcing, None, np.zeros((5, 6)), 0, 1, 1000.0, lambda: None, dev)
+    assert rec["host_arrays_identical_to_device_result"] is False
+    # several ranks on a box: the plain drain, and this rank's share of the cores
+    assert bench.host_drain_settings(1, 16) == (16, True) and bench.host_drain_settings(1, 64) == (32, True)
+    assert bench.host_drain_settings(2, 24) == (12, False) and bench.host_drain_settings(8, 32) == (4, False)
+    assert bench.host_drain_settings(1, 2) == (2, False) and bench.host_drain_settings(8, 4) == (1, False)
