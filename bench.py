@@ -498,7 +498,7 @@ def host_drain_settings(world, cores):
     (profiles/r02_e2e_compacted_drain.jsonl): one rank 330-345 ms against 425-455 ms plain; two ranks 402-420 against
     418 ms (the hybrid split keeps it from falling behind, but there is nothing to gain); eight ranks 2202 (all packed)
     against 2168 ms.  So a single rank takes it, several ranks stay on the plain drain."""
-    threads = max(1, min(32, cores // world))
+    threads = max(1, min(16, cores // world))      # (12 threads already saturate the host's memory system)
     return threads, (world == 1 and threads >= 4)
 
 

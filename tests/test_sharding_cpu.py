@@ -143,6 +143,6 @@ def test_bench_end_to_end_leg_runs_against_a_stand_in_engine(monkeypatch):
     rec = bench.run_e2e(args, eng, forcing, None, np.zeros((5, 6)), 0, 1, 1000.0, lambda: None, dev)
     assert rec["host_arrays_identical_to_device_result"] is False
     # several ranks on a box: the plain drain, and this rank's share of the cores
-    assert bench.host_drain_settings(1, 16) == (16, True) and bench.host_drain_settings(1, 64) == (32, True)
+    assert bench.host_drain_settings(1, 16) == (16, True) and bench.host_drain_settings(1, 64) == (16, True)
     assert bench.host_drain_settings(2, 24) == (12, False) and bench.host_drain_settings(8, 32) == (4, False)
     assert bench.host_drain_settings(1, 2) == (2, False) and bench.host_drain_settings(8, 4) == (1, False)
