@@ -13,7 +13,10 @@ Reported (one JSON line, rank 0):
   value      member-cell-days/s, all ranks, forcing resident in HBM, full 12-array output contract in HBM
   roofline   algorithmic HBM bytes (96 + 41/M per member-cell-day) / device time, against the
              measured copy bandwidth in MEASURED_PEAKS.json
-  e2e        the same metric through nesosim_run_season_host with HOST buffers (H2D + D2H inside the timing)
+  e2e        the same metric through nesosim_run_season_host with HOST buffers (H2D + D2H inside the timing): all
+             twelve arrays land in the caller's host memory; a single rank drains them compacted (ocean cells over
+             the link, host threads scatter), several ranks plainly -- `e2e.drain` says which, and the host arrays are
+             compared with the device-resident season
   cpu_baseline  the numpy oracle port of the reference's calcBudget loop on this box's host cores
 `--impl reference` times only that CPU port (all host cores) and prints the same line shape.
 """
