@@ -558,7 +558,7 @@ extern "C" int nesosim_run_season_host(nesosim_ctx *ctx, const double *precip, c
                     return cuda_fail(q_, "device->host copy of a block");
                 }
             }
-            if (share && !replication_queued && cudaEventQuery(hp->shared_ready) == cudaSuccess) {
+            if (share && (harr[2] || harr[3]) && !replication_queued && cudaEventQuery(hp->shared_ready) == cudaSuccess) {
                 queue_replication();
                 progress = true;
             }
