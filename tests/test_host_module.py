@@ -275,3 +275,46 @@ def test_calc_budget_shim_has_the_reference_in_place_contract(cuda, quiet):
         assert same(arr, ref[name]), name
     assert same(precipDays[:T - 1], forcing["precip"][:T - 1]) and not precipDays[T - 1].any()
     assert np.isnan(tempDays[:T - 1]).all()
+
+
+@needs_ref
+def test_drift_regridders_match_reference():
+    """`drift_smoothing.int_smooth_drifts_v2/v3` against the reference's own functions run verbatim
+    (utils.py:259-338; astropy's pair replaced by the restatement on both sides): scattered source points with NaN
+    drift, a model grid reaching outside their hull (NaN after interpolation -> the NaN-interpolating branch of the
+    convolution and the final mask), both kernel widths the reference uses."""
+    import sys
+    import numpy.ma as ma
+    from scipy.spatial import Delaunay
+    from nesosim_b200 import drift_smoothing as D
+    from oracle import astropy_restated as ar
+    ref_loader.load_reference()
+    ref_utils = sys.modules["utils"]
+    assert ref_utils.__file__.startswith(ref_loader.REFERENCE_SOURCE)
+
+    def cpu_smoother(gx, gy, sigma_factor=1, x_size_val=3):
+        k = ar.gaussian2d_kernel(x_stddev=sigma_factor, y_stddev=sigma_factor, theta=0.0, x_size=x_size_val, y_size=x_size_val)
+        out = ma.masked_all((2,) + gx.shape)
+        for i, c in enumerate((gx, gy)):
+            out[i] = ma.masked_where(np.isnan(c), ar.convolve_fill0(c, k))
+        return out
+
+    rng = np.random.default_rng(11)
+    jj, ii = np.meshgrid(np.arange(14.0), np.arange(12.0))
+    xF = ii * 9.0 + rng.normal(0, 1.0, ii.shape) + 5.0          # scattered (jittered) source points
+    yF = jj * 8.0 + rng.normal(0, 1.0, jj.shape) + 4.0
+    latsF = 60.0 + 0.2 * ii
+    drift = np.stack([np.sin(xF / 20.0) + 0.1 * rng.normal(size=xF.shape), np.cos(yF / 15.0) + 0.1 * rng.normal(size=xF.shape)])
+    drift[:, 4:6, 5:8] = np.nan                                 # a data gap
+    drift[1, 9, 2] = np.nan
+    gj, gi = np.meshgrid(np.linspace(-5.0, 118.0, 24), np.linspace(-3.0, 112.0, 20))
+    xG, yG = gi, gj
+    tri = Delaunay(np.column_stack([xF.ravel(), yF.ravel()]))
+    for sigma in (0.5, 1):
+        for name, args in (("int_smooth_drifts_v2", ()), ("int_smooth_drifts_v3", (tri,))):
+            got = getattr(D, name)(*args, xG, yG, xF, yF, latsF, drift, sigma_factor=sigma, smoother=cpu_smoother)
+            exp = getattr(ref_utils, name)(*args, xG, yG, xF, yF, latsF, drift, sigma_factor=sigma)
+            assert got.shape == exp.shape == (2, 20, 24)
+            assert np.array_equal(ma.getmaskarray(got), ma.getmaskarray(exp)), (name, sigma)
+            assert ma.getmaskarray(exp).any() and not ma.getmaskarray(exp).all()
+            assert np.array_equal(got.filled(-9.0), exp.filled(-9.0)), (name, sigma)
