@@ -12,6 +12,9 @@ Same public names, signatures and side effects as the reference for the hot path
   slot ``x`` of the forcing copies and slot ``x+1`` of the 11 budget arrays are written, nothing else.
 * ``loadData(...)``        -- the daily forcing reader (``NESOSIM.py:379-456``) with its fallbacks.
 * ``genEmptyArrays``, ``doyToMonth``, ``applyScaling`` -- same contracts.
+* ``calcLeadLoss``, ``calcAtmLoss``, ``calcWindPacking``, ``fillMaskAndNaNWithZero``, ``fill_nan_no_negative``,
+  ``smooth_snow``, ``calcDynamics``, ``densityCalc`` -- the functions ``calcBudget`` is made of (``NESOSIM.py:51-222,
+  458-473``), one GPU entry point each, for callers and tests that use them one by one.
 
 Model constants are module globals with the reference's names (``NESOSIM.py:517,527-541``) because callers of the
 reference set them that way; every native call receives them explicitly.  There is no numpy fallback for the
@@ -257,6 +260,74 @@ def calcBudget(xptsG, yptsG, snowDepths, iceConcDayT, precipDayT, driftGdayT, wi
     torch.cuda.synchronize()
     for n in _STATE_NAMES:
         host[n][x + 1] = dev[n][0, x + 1].cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------ the per-function operators
+# The functions calcBudget is made of, with the reference's names, arguments and return values (NESOSIM.py:51-222,
+# 458-473), each on the GPU through the matching per-function entry point of the C ABI (nesosim_op_*, nesosim_smooth):
+# what a caller -- or a test written against the reference -- that uses them one by one gets.  numpy in, numpy out; the
+# model constants are the module globals above, as in the reference.  (The season path does not go through these: it
+# runs the fused kernels.)
+
+def _ops():
+    """The native per-function operators (nesosim_b200.engine); tests on a machine without a GPU swap in a stand-in."""
+    from . import engine
+    return engine
+
+
+def _plain(arr, what):
+    if isinstance(arr, ma.MaskedArray):
+        raise TypeError(what + ": plain ndarrays only (what calcBudget passes); fill the masked array first")
+    return arr
+
+
+def calcLeadLoss(snowDepthT, windDayT, iceConcDaysT):
+    """Snow lost to leads from the new-snow layer (NESOSIM.py:51-72): ``-(windT*LLF*deltaT*h0*W*(1-C))``."""
+    return _ops().op_wind_terms(snowDepthT, windDayT, iceConcDaysT, _params_row(), deltaT, snowDensityFresh,
+                                snowDensityOld)[0]
+
+
+def calcAtmLoss(snowDepthT, windDayT):
+    """Snow lost to the atmosphere (NESOSIM.py:74-95): ``-(windT*deltaT*h0*W*ALF)``."""
+    return _ops().op_wind_terms(snowDepthT, windDayT, np.zeros_like(np.asarray(windDayT, dtype=np.float64)), _params_row(),
+                                deltaT, snowDensityFresh, snowDensityOld)[1]
+
+
+def calcWindPacking(windDayT, snowDepthT0):
+    """Wind packing (NESOSIM.py:97-125): loss from the new-snow layer, gain of the old-snow layer, net."""
+    out = _ops().op_wind_terms(snowDepthT0, windDayT, np.zeros_like(np.asarray(windDayT, dtype=np.float64)), _params_row(),
+                               deltaT, snowDensityFresh, snowDensityOld)
+    return out[2], out[3], out[4]
+
+
+def fillMaskAndNaNWithZero(arr):
+    """NaN and +-inf -> 0, in place (NESOSIM.py:127-139); returns None like the reference."""
+    _plain(arr, "fillMaskAndNaNWithZero")[...] = _ops().op_fill_zero(arr)
+
+
+def fill_nan_no_negative(arr, region_maskG, negative_to_zero=True):
+    """Non-finite, land/coast (mask > 10) and lake (mask < 1) cells -> NaN, then negative -> 0 if asked; in place
+    (NESOSIM.py:141-166); returns None like the reference."""
+    _plain(arr, "fill_nan_no_negative")[...] = _ops().op_fill_nan_no_negative(arr, region_maskG, negative_to_zero)
+
+
+def smooth_snow(arr, stddev_val=1, x_size_val=3, y_size_val=3):
+    """astropy ``convolve(arr, Gaussian2DKernel(stddev_val, x_size=3, y_size=3))`` (NESOSIM.py:170-187): both branches
+    of astropy's routine (plain, and NaN-interpolating when the input holds a NaN); returns a new array."""
+    if int(x_size_val) != 3 or int(y_size_val) != 3:
+        raise ValueError("the native smoother is the reference's 3x3 kernel (x_size_val = y_size_val = 3)")
+    return _ops().smooth(arr, stddev=float(stddev_val))
+
+
+def calcDynamics(driftGday, snowDepthsT, dx):
+    """Advection and divergence of both layers for one day (NESOSIM.py:189-222), NaN/inf filled with zero: returns
+    ``(snowAdvAllT, snowDivAllT)``, each ``(2, ny, nx)``."""
+    return _ops().op_dynamics(driftGday, snowDepthsT, dx, deltaT)
+
+
+def densityCalc(snowDepthsT, iceConcDayT, region_maskT):
+    """Bulk density of the two layers (NESOSIM.py:458-473); ``iceConcDayT`` is accepted and unused, as in the reference."""
+    return _ops().op_density(snowDepthsT, region_maskT, snowDensityFresh, snowDensityOld, minSnowD)
 
 
 # ------------------------------------------------------------------------------------------ the driver

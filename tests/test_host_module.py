@@ -318,3 +318,116 @@ def test_drift_regridders_match_reference():
             assert np.array_equal(ma.getmaskarray(got), ma.getmaskarray(exp)), (name, sigma)
             assert ma.getmaskarray(exp).any() and not ma.getmaskarray(exp).all()
             assert np.array_equal(got.filled(-9.0), exp.filled(-9.0)), (name, sigma)
+
+
+class _StandInOps:
+    """CPU stand-in for the native per-function operators of `nesosim_b200.engine` (same signatures, checked below),
+    backed by the oracle: lets the plumbing of the reference-named wrappers in `nesosim_b200.NESOSIM` be tested where
+    there is no GPU.  The native operators themselves are tested on the GPU (`tests/test_gpu_parity.py::test_op_*`)."""
+
+    @staticmethod
+    def _p(params, deltaT, rhoFresh, rhoOld, minSnowD=0.02):
+        from oracle import nesosim_oracle as O
+        wpf, wpt, llf, alf = params[0]
+        return O.Params(windPackFactor=wpf, windPackThresh=wpt, leadLossFactor=llf, atmLossFactor=alf, deltaT=deltaT,
+                        snowDensityFresh=rhoFresh, snowDensityOld=rhoOld, minSnowD=minSnowD)
+
+    @staticmethod
+    def op_wind_terms(h0, wind, conc, params, deltaT=86400., rhoFresh=200., rhoOld=350., device=0):
+        from oracle import nesosim_oracle as O
+        p = _StandInOps._p(params, deltaT, rhoFresh, rhoOld)
+        h0, wind, conc = (np.asarray(v, dtype=np.float64) for v in (h0, wind, conc))
+        with np.errstate(all="ignore"):
+            return [O.lead_loss(h0, wind, conc, p), O.atm_loss(h0, wind, p)] + list(O.wind_packing(wind, h0, p))
+
+    @staticmethod
+    def op_dynamics(drift, depths, dx, deltaT=86400., device=0):
+        from oracle import nesosim_oracle as O
+        return O.calc_dynamics(np.asarray(drift, dtype=np.float64), np.asarray(depths, dtype=np.float64), dx,
+                               _StandInOps._p([[0, 0, 0, 0]], deltaT, 200., 350.))
+
+    @staticmethod
+    def op_fill_zero(arr, device=0):
+        from oracle import nesosim_oracle as O
+        a = np.array(arr, dtype=np.float64)
+        O.fill_mask_nan_zero(a)
+        return a
+
+    @staticmethod
+    def op_fill_nan_no_negative(arr, mask, negative_to_zero=True, device=0):
+        from oracle import nesosim_oracle as O
+        a = np.array(arr, dtype=np.float64)
+        O.fill_nan_no_negative(a, np.asarray(mask), negative_to_zero)
+        return a
+
+    @staticmethod
+    def op_density(depths, mask, rhoFresh=200., rhoOld=350., minSnowD=0.02, device=0):
+        from oracle import nesosim_oracle as O
+        return O.density_calc(np.asarray(depths, dtype=np.float64), None, np.asarray(mask),
+                              _StandInOps._p([[0, 0, 0, 0]], 86400., rhoFresh, rhoOld, minSnowD))
+
+    @staticmethod
+    def smooth(arr, conv_variant="post_divide", device=0, stddev=1.0):
+        from oracle import astropy_restated as ar
+        k = ar.gaussian2d_kernel(x_stddev=stddev, y_stddev=stddev, theta=0.0, x_size=3, y_size=3)
+        return ar.convolve_fill0(np.asarray(arr, dtype=np.float64), k, variant=conv_variant)
+
+
+@needs_ref
+def test_per_function_operators_have_the_reference_contracts(monkeypatch):
+    """`calcLeadLoss`, `calcAtmLoss`, `calcWindPacking`, `fillMaskAndNaNWithZero`, `fill_nan_no_negative`, `smooth_snow`,
+    `calcDynamics`, `densityCalc` of the drop-in module against the reference's own functions run verbatim
+    (NESOSIM.py:51-222, 458-473): same arguments, same return values or in-place effect, the module globals as the
+    parameters.  The arithmetic is the stand-in's here; what is tested is everything around it."""
+    import inspect
+    from nesosim_b200 import engine as E
+    for name in ("op_wind_terms", "op_dynamics", "op_fill_zero", "op_fill_nan_no_negative", "op_density", "smooth"):
+        assert inspect.signature(getattr(_StandInOps, name)) == inspect.signature(getattr(E, name)), name
+    monkeypatch.setattr(N, "_ops", lambda: _StandInOps)
+    ref = ref_loader.load_reference()
+    ref_loader.set_globals(ref, 5.8e-7, 5., 2.9e-7, 2.2e-8)
+    for k, v in dict(windPackFactor=5.8e-7, windPackThresh=5., leadLossFactor=2.9e-7, atmLossFactor=2.2e-8).items():
+        monkeypatch.setattr(N, k, v)
+    rng = np.random.default_rng(5)
+    ny, nx = 9, 11
+    mask = rng.choice(np.array([0, 3, 8, 8, 8, 11, 12]), size=(ny, nx)).astype(float)
+    h = np.abs(rng.normal(0.1, 0.1, (2, ny, nx)))
+    h[:, mask > 10] = np.nan
+    h[0, 2, 3] = 0.0
+    h[1, 2, 3] = 0.0
+    W = rng.gamma(4.0, 1.5, (ny, nx))
+    W[0, :3] = 5.0
+    W[1, 1] = np.nan
+    C = np.clip(rng.random((ny, nx)), 0, 1)
+    drift = 0.1 * rng.normal(size=(2, ny, nx))
+    drift[:, 4:6, 4:7] = np.nan
+    with np.errstate(all="ignore"):
+        assert same(N.calcLeadLoss(h[0], W, C), ref.calcLeadLoss(h[0], W, C))
+        assert same(N.calcAtmLoss(h[0], W), ref.calcAtmLoss(h[0], W))
+        for g, e in zip(N.calcWindPacking(W, h[0]), ref.calcWindPacking(W, h[0])):
+            assert same(g, e)
+        for g, e in zip(N.calcDynamics(drift, h, 100000), ref.calcDynamics(drift, h, 100000)):
+            assert g.shape == (2, ny, nx) and same(g, e)
+        assert same(N.densityCalc(h, C, mask), ref.densityCalc(h, C, mask))
+        clean = np.nan_to_num(h[0], nan=0.0)
+        assert same(N.smooth_snow(clean), ref.smooth_snow(clean))
+        holes = h[0].copy()
+        assert same(N.smooth_snow(holes, stddev_val=0.5), ref.smooth_snow(holes, stddev_val=0.5))
+        with pytest.raises(ValueError):
+            N.smooth_snow(clean, x_size_val=5)
+        for negz in (True, False):
+            a = rng.normal(size=(ny, nx))
+            a[3, 3] = np.inf
+            a[4, 4] = np.nan
+            b = a.copy()
+            assert N.fill_nan_no_negative(a, mask, negative_to_zero=negz) is None
+            ref.fill_nan_no_negative(b, mask, negative_to_zero=negz)
+            assert same(a, b)
+        a = rng.normal(size=(ny, nx))
+        a[1, 2], a[2, 1], a[0, 0] = np.nan, np.inf, -np.inf
+        b = a.copy()
+        assert N.fillMaskAndNaNWithZero(a) is None
+        ref.fillMaskAndNaNWithZero(b)
+        assert same(a, b) and np.isfinite(a).all()
+        with pytest.raises(TypeError):
+            N.fillMaskAndNaNWithZero(np.ma.masked_invalid(b))
